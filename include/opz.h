@@ -1,0 +1,169 @@
+/* opz.h — C ABI of libopz.so: the B200-native NDE column-model hot path.
+ *
+ * Drop-in boundary for ONE path of CliMA/OceanParameterizations.jl: the neural differential
+ * equation (NDE) rollout of the wind_mixing column model and the gradient of its profile loss.
+ * The reference has no FFI layer (it is 100 % Julia); each entry point below replaces the Julia
+ * function named in its comment and is what a `ccall` shim binds (see INTEGRATION.md and
+ * julia/OPZ.jl).  Conventions:
+ *   - every call returns 0 on success, a negative OPZ_E* code on failure; the message is
+ *     available from opz_last_error() (thread-local);  nothing throws across the ABI;
+ *   - the caller owns all host buffers; Julia column-major `3Nz x Nt x B` is C `[B][Nt][3Nz]`;
+ *   - host-pointer calls are blocking (stream-synchronised before return);  `_dev` calls take
+ *     DEVICE pointers, enqueue on the context's stream and return without synchronising;
+ *   - one opz_ctx drives one GPU (one process per GPU); there is NO CPU fallback: creating a
+ *     context on a machine without an sm_100 device fails with OPZ_ENODEV.
+ */
+#ifndef OPZ_H
+#define OPZ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPZ_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define OPZ_OK 0
+#define OPZ_EINVAL (-1)  /* bad argument */
+#define OPZ_ENODEV (-2)  /* no usable sm_100 device */
+#define OPZ_ECUDA (-3)   /* CUDA runtime error (message has the detail) */
+#define OPZ_ENOMEM (-4)  /* device allocation failed */
+#define OPZ_EUNSUP (-5)  /* configuration not supported by the requested precision path */
+
+/* conditions NamedTuple -> flag bits (wind_mixing/src/NDE_training.jl:205-207) */
+#define OPZ_FLAG_MPP (1u << 0)                  /* modified_pacanowski_philander */
+#define OPZ_FLAG_CA (1u << 1)                   /* convective_adjustment (training_postprocessing.jl:118-121) */
+#define OPZ_FLAG_CA_SELECT_DUDZ (1u << 2)       /* reference quirk: predicate on du/dz (tp.jl:120); default dT/dz */
+#define OPZ_FLAG_BC_MINUS_SCALE0 (1u << 3)      /* boundary flux = bc - scale(0) (tp.jl:82-93; zero_weights) */
+#define OPZ_FLAG_DIURNAL (1u << 4)              /* wT_top(t) = scale_wT(Q sin(2 pi t tau/period)/(alpha g)) */
+#define OPZ_FLAG_DIURNAL_MINUS_SCALE0 (1u << 5) /* consistent offset; the reference omits it (tp.jl:143) */
+#define OPZ_FLAG_RI_EPS (1u << 6)               /* add eps to each gradient inside Ri (NDE_training.jl:115-119) */
+#define OPZ_FLAG_SMOOTH_NN (1u << 7)            /* 3-point box filter on NN output (NDE_training.jl:98-102) */
+#define OPZ_FLAG_SMOOTH_RI (1u << 8)            /* 3-point box filter on Ri (NDE_training.jl:121-123) */
+
+/* timestepper (replaces the OrdinaryDiffEq `timestepper` argument; fixed step) */
+#define OPZ_EULER 0
+#define OPZ_RK2 1 /* Heun */
+#define OPZ_RK4 2
+
+/* activation of the hidden Dense layers (NNlib names); the last layer is linear */
+#define OPZ_ACT_IDENTITY 0
+#define OPZ_ACT_RELU 1
+#define OPZ_ACT_TANH 2
+#define OPZ_ACT_MISH 3
+#define OPZ_ACT_SWISH 4
+#define OPZ_ACT_LEAKYRELU 5
+
+/* arithmetic of the batched MLP (physics and time stepping are always FP32) */
+#define OPZ_PREC_FP32 0   /* FP32 FMA on CUDA cores: the parity path (<= 1e-4) */
+#define OPZ_PREC_BF16 1   /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM */
+#define OPZ_PREC_BF16X2 2 /* as BF16 with weights split hi+lo (2 MMAs): ~TF32-grade */
+#define OPZ_PREC_BF16X3 3 /* activations and weights split hi+lo (3 MMAs): ~FP32-grade */
+
+#define OPZ_BC_STRIDE 8 /* floats per column in `bc` */
+
+/* constants + scalings of prepare_parameters_NDE_training (NDE_training.jl:1-44), flattened.
+ * mu/sigma order: u, v, T, uw, vw, wT  (six ZeroMeanUnitVarianceScaling objects,
+ * src/DataWrangling/feature_scaling.jl:7-23). 37 x 4 bytes, no padding. */
+typedef struct opz_params {
+  int32_t nz;    /* cells per column (32) */
+  float H;       /* abs(z_F[end]-z_F[1]) [m] */
+  float tau;     /* abs(t[end]-t[1]) [s]; model time is t/tau */
+  float f;       /* Coriolis [1/s] */
+  float g;       /* gravity */
+  float alpha;   /* thermal expansion */
+  float nu0;     /* background diffusivity */
+  float nu_m;    /* nu_- : shear-instability increment */
+  float Ric;     /* critical Richardson number */
+  float dRi;     /* width of the tanh switch */
+  float Pr;      /* Prandtl number */
+  float kappa;   /* convective-adjustment diffusivity */
+  float eps;     /* used when OPZ_FLAG_RI_EPS */
+  float mu[6];
+  float sigma[6];
+  uint32_t flags;
+  float diurnal_period; /* seconds (86400) */
+  float reserved[10];
+} opz_params;
+
+typedef struct opz_ctx opz_ctx;
+typedef struct opz_model opz_model;
+
+/* ---- lifecycle / errors ------------------------------------------------------------------ */
+int opz_version(void);
+const char* opz_last_error(void);
+int opz_ctx_create(int device, opz_ctx** out);
+int opz_ctx_destroy(opz_ctx* ctx);
+/* adopt an externally owned cudaStream_t (e.g. torch's current stream) for all later calls */
+int opz_ctx_set_stream(opz_ctx* ctx, void* cuda_stream);
+int opz_ctx_synchronize(opz_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t opz_ctx_launch_count(const opz_ctx* ctx);
+
+/* ---- model: three Flux Chains uw_NN, vw_NN, wT_NN of one architecture ----------------------
+ * Replaces `Flux.destructure(NN)` / `re(weights)` (NDE_training.jl:11-13,62-64;
+ * wind_mixing/construct_NN.jl:29-34).  sizes = {in, hidden..., out}, n_sizes = #layers + 1;
+ * in must be 3*nz and out nz-1.  Each w_* is one net's flat vector in Flux.destructure order
+ * [vec(W1) (out x in, column-major); b1; vec(W2); b2; ...] (HOST pointers). */
+int opz_model_create(opz_ctx* ctx, int nz, int n_sizes, const int* sizes, int act,
+                     const float* w_uw, const float* w_vw, const float* w_wT, opz_model** out);
+/* weights = [uw; vw; wT] flat, 3P floats (the `weights` vector train_NDE optimises) */
+int opz_model_set_weights(opz_model* m, const float* weights_host);
+int opz_model_get_weights(const opz_model* m, float* weights_host);
+int opz_model_set_weights_dev(opz_model* m, const float* weights_dev);
+int64_t opz_model_n_params(const opz_model* m); /* P per net */
+int opz_model_destroy(opz_model* m);
+
+/* ---- single right-hand-side evaluation ---------------------------------------------------
+ * Replaces NDE(x,p,t,...) / predict_NDE / predict_flux (NDE_training.jl:56-165) and NDE! /
+ * predict_flux! (training_postprocessing.jl:105-153) for B columns at once.
+ * x[B][3nz] scaled state; bc[B][8] = uw_bottom, uw_top, vw_bottom, vw_top, wT_bottom, wT_top
+ * (scaled, NDE_training.jl:238-243), Q_diurnal [m^2 s^-3], unused; t = time / tau.
+ * dxdt[B][3nz]; fluxes (optional, may be NULL) [B][3][nz+1] = total scaled uw, vw, wT. */
+int opz_rhs(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x, const float* bc,
+            float t, int64_t B, int precision, float* dxdt, float* fluxes);
+
+/* ---- forward rollout ------------------------------------------------------------------------
+ * Replaces solve_NDE_mutating(uw_NN, vw_NN, wT_NN, scalings, constants, BCs, derivatives, uvT0,
+ * ts, timestepper, conditions) (training_postprocessing.jl:55-159) for an ensemble of B
+ * columns: `timestepper` -> (scheme, dt_nd); ts -> t0 + i*save_every*dt_nd, i = 0..n_steps/save_every.
+ * out[B][n_save][3nz], n_save = n_steps/save_every + 1, snapshot 0 = x0 (as `saveat=ts`).
+ * save_every <= 0 saves the final state only: out[B][1][3nz]. */
+int opz_rollout_forward(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
+                        const float* bc, int64_t B, int scheme, float dt_nd, float t0,
+                        int n_steps, int save_every, int precision, float* out);
+int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p,
+                            const float* x0_dev, const float* bc_dev, int64_t B, int scheme,
+                            float dt_nd, float t0, int n_steps, int save_every, int precision,
+                            float* out_dev);
+
+/* ---- loss and its gradient w.r.t. the NN weights ----------------------------------------------
+ * Replaces loss_NDE / loss_gradient_NDE + Zygote.gradient through
+ * solve(...; sensealg=InterpolatingAdjoint(autojacvec=ZygoteVJP())) (NDE_training.jl:290-333)
+ * by the exact discrete adjoint (BPTT) of the fixed-step scheme.
+ * target[B][n_save][3nz]; loss_w[6] = weights of (u, v, T, du/dz, dv/dz, dT/dz) MSE terms
+ * (loss.jl:1-42); loss_out[7] = total then the six weighted components; grad_out[3P].
+ * The sums are over THIS context's B columns with the mean taken over `B_total` simulations
+ * (pass B_total = B on one GPU); multi-GPU callers all-reduce grad_out and loss_out (sum). */
+int opz_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
+                  const float* bc, int64_t B, int64_t B_total, int scheme, float dt_nd, float t0,
+                  int n_steps, int save_every, const float* target, const float* loss_w,
+                  int precision, float* loss_out, float* grad_out);
+int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0_dev,
+                      const float* bc_dev, int64_t B, int64_t B_total, int scheme, float dt_nd,
+                      float t0, int n_steps, int save_every, const float* target_dev,
+                      const float* loss_w_host, int precision, float* loss_out_dev,
+                      float* grad_out_dev);
+
+/* ---- batched MLP forward ------------------------------------------------------------------------
+ * Replaces predict(V, model; scaled=true) (src/predict.jl:12-34): one launch over Nt input
+ * columns.  which_net: 0 uw, 1 vw, 2 wT.  x[Nt][3nz] -> y[Nt][nz-1]. */
+int opz_mlp_forward(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt,
+                    int precision, float* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPZ_H */

@@ -1,0 +1,623 @@
+"""Host-side mirror of the reference's Julia interface for the NDE hot path.
+
+Julia is not available in this image, so the host side above the C ABI is written in Python and
+keeps the reference's names, argument order and meaning (INTEGRATION.md shows the equivalent
+Julia `ccall` shim, julia/OPZ.jl).  Everything numerical happens in libopz.so on the GPU; this
+file only packs arguments.
+
+Mirrored reference symbols (file:line in /root/reference):
+  ZeroMeanUnitVarianceScaling, scale, unscale      src/DataWrangling/feature_scaling.jl:7-23,53-54
+  Dᶜ, Dᶠ                                           src/differentiation_operators.jl:6-29
+  Dense / Chain / destructure                      Flux 0.11.6 as used by wind_mixing/construct_NN.jl:29-34
+  prepare_parameters_NDE_training                  wind_mixing/src/NDE_training.jl:1-44
+  NDE, predict_NDE, predict_flux                   wind_mixing/src/NDE_training.jl:56-165
+  prepare_BCs, solve_NDE_mutating                  wind_mixing/src/training_postprocessing.jl:35-159
+  loss, loss_NDE / loss_gradient_NDE, train_NDE    wind_mixing/src/loss.jl:1-42, NDE_training.jl:167-374
+  predict                                          src/predict.jl:12-34
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from types import SimpleNamespace
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+# --------------------------------------------------------------------------------------------------
+# activations (names as in NNlib) and scalers
+# --------------------------------------------------------------------------------------------------
+identity, relu, tanh, mish, swish, leakyrelu = "identity", "relu", "tanh", "mish", "swish", "leakyrelu"
+_ACT = {identity: L.ACT_IDENTITY, relu: L.ACT_RELU, tanh: L.ACT_TANH, mish: L.ACT_MISH, swish: L.ACT_SWISH,
+        leakyrelu: L.ACT_LEAKYRELU}
+
+
+@dataclasses.dataclass
+class ZeroMeanUnitVarianceScaling:
+    """feature_scaling.jl:7-23.  Callable: s(x) == scale(x, s); inv(s)(y) == unscale(y, s)."""
+    μ: float
+    σ: float
+
+    @classmethod
+    def from_data(cls, data):
+        data = np.asarray(data, dtype=np.float64)
+        return cls(float(data.mean()), float(data.std(ddof=1)))  # Julia std() is the n-1 estimator
+
+    def __call__(self, x):
+        return (np.asarray(x) - self.μ) / self.σ
+
+
+def scale(x, s: ZeroMeanUnitVarianceScaling):
+    return (np.asarray(x) - s.μ) / s.σ
+
+
+def unscale(y, s: ZeroMeanUnitVarianceScaling):
+    return s.σ * np.asarray(y) + s.μ
+
+
+def inv(s: ZeroMeanUnitVarianceScaling) -> Callable:
+    return lambda y: unscale(y, s)
+
+
+def Dᶜ(N: int, Δ: float) -> np.ndarray:
+    """N x (N+1) face->cell derivative (differentiation_operators.jl:6-14).  Kept for API parity;
+    on the device both operators are two-point differences."""
+    D = np.zeros((N, N + 1))
+    idx = np.arange(N)
+    D[idx, idx] = -1.0
+    D[idx, idx + 1] = 1.0
+    return D / Δ
+
+
+def Dᶠ(N: int, Δ: float) -> np.ndarray:
+    """(N+1) x N cell->face derivative with zero first/last rows (:21-29)."""
+    D = np.zeros((N + 1, N))
+    idx = np.arange(1, N)
+    D[idx, idx - 1] = -1.0
+    D[idx, idx] = 1.0
+    return D / Δ
+
+
+D_cell, D_face = Dᶜ, Dᶠ
+
+# --------------------------------------------------------------------------------------------------
+# Flux-shaped NN containers (weights only; evaluation happens on the GPU)
+# --------------------------------------------------------------------------------------------------
+
+
+class Dense:
+    """Dense(in, out, σ): W is out x in, b is out; default init glorot_uniform / zeros (Flux 0.11)."""
+
+    def __init__(self, nin: int, nout: int, σ: str = identity, *, rng: Optional[np.random.Generator] = None,
+                 W: Optional[np.ndarray] = None, b: Optional[np.ndarray] = None):
+        self.nin, self.nout, self.σ = int(nin), int(nout), σ
+        if W is None:
+            rng = rng or np.random.default_rng()
+            lim = math.sqrt(6.0 / (nin + nout))
+            W = rng.uniform(-lim, lim, size=(nout, nin))
+        self.W = np.asarray(W, dtype=np.float32).reshape(nout, nin)
+        self.b = np.zeros(nout, dtype=np.float32) if b is None else np.asarray(b, dtype=np.float32).reshape(nout)
+
+
+class Chain:
+    def __init__(self, *layers: Dense):
+        self.layers = list(layers)
+        for a, b in zip(self.layers[:-1], self.layers[1:]):
+            if a.nout != b.nin:
+                raise ValueError("layer sizes do not chain")
+        acts = {l.σ for l in self.layers[:-1]}
+        if len(acts) > 1:
+            raise ValueError("libopz supports one hidden activation per Chain")
+        if self.layers[-1].σ != identity:
+            raise ValueError("the last Dense layer must be linear")
+
+    @property
+    def sizes(self):
+        return [self.layers[0].nin] + [l.nout for l in self.layers]
+
+    @property
+    def activation(self) -> str:
+        return self.layers[0].σ if len(self.layers) > 1 else identity
+
+
+def destructure(chain: Chain):
+    """Flux.destructure: flat Float32 vector [vec(W1); b1; vec(W2); b2; ...] (column-major W) and a
+    restructure closure `re`."""
+    flat = np.concatenate([np.concatenate([l.W.T.reshape(-1), l.b]) for l in chain.layers]).astype(np.float32)
+    spec = [(l.nin, l.nout, l.σ) for l in chain.layers]
+
+    def re(w):
+        w = np.asarray(w, dtype=np.float32)
+        if w.size != flat.size:
+            raise ValueError("restructure: wrong number of parameters")
+        layers, off = [], 0
+        for nin, nout, σ in spec:
+            W = w[off:off + nin * nout].reshape(nin, nout).T
+            off += nin * nout
+            b = w[off:off + nout]
+            off += nout
+            layers.append(Dense(nin, nout, σ, W=W.copy(), b=b.copy()))
+        return Chain(*layers)
+
+    return flat, re
+
+
+# --------------------------------------------------------------------------------------------------
+# context / model handles
+# --------------------------------------------------------------------------------------------------
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+class Context:
+    """opz_ctx: one GPU, one stream."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        L.check(L.lib.opz_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def set_stream(self, cuda_stream_ptr: int):
+        L.check(L.lib.opz_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        L.check(L.lib.opz_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(L.lib.opz_ctx_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            L.lib.opz_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class NDEModel:
+    """opz_model: the three Chains uw_NN, vw_NN, wT_NN resident on the GPU."""
+
+    def __init__(self, uw_NN: Chain, vw_NN: Chain, wT_NN: Chain, Nz: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        if not (uw_NN.sizes == vw_NN.sizes == wT_NN.sizes and uw_NN.activation == vw_NN.activation == wT_NN.activation):
+            raise ValueError("the three nets must share one architecture")
+        self.Nz = int(Nz)
+        self.sizes = list(uw_NN.sizes)
+        self.activation = uw_NN.activation
+        ws = [destructure(n)[0] for n in (uw_NN, vw_NN, wT_NN)]
+        sizes = (C.c_int * len(self.sizes))(*self.sizes)
+        h = C.c_void_p()
+        L.check(L.lib.opz_model_create(self.ctx._h, self.Nz, len(self.sizes), sizes, _ACT[self.activation],
+                                       _fptr(ws[0]), _fptr(ws[1]), _fptr(ws[2]), C.byref(h)))
+        self._h = h
+        self.P = int(L.lib.opz_model_n_params(h))
+
+    def set_weights(self, weights):
+        w = _f32(weights, (3 * self.P,))
+        L.check(L.lib.opz_model_set_weights(self._h, _fptr(w)))
+
+    def get_weights(self) -> np.ndarray:
+        w = np.empty(3 * self.P, dtype=np.float32)
+        L.check(L.lib.opz_model_get_weights(self._h, _fptr(w)))
+        return w
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib.opz_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------------
+# parameters
+# --------------------------------------------------------------------------------------------------
+_SCALING_ORDER = ("u", "v", "T", "uw", "vw", "wT")
+
+
+def make_params(constants, scalings, flags: int, eps: float = 1e-7, diurnal_period: float = 86400.0) -> L.OpzParams:
+    g = lambda k, d=0.0: float(getattr(constants, k, d))
+    p = L.OpzParams()
+    p.nz = int(constants.Nz)
+    p.H, p.tau, p.f, p.g, p.alpha = g("H"), g("τ"), g("f"), g("g"), g("α")
+    p.nu0, p.nu_m, p.Ric, p.dRi, p.Pr = g("ν0"), g("ν_m"), g("Riᶜ"), g("ΔRi", 1.0), g("Pr", 1.0)
+    p.kappa = g("κ")
+    p.eps = eps
+    for i, n in enumerate(_SCALING_ORDER):
+        s = scalings[n] if isinstance(scalings, dict) else getattr(scalings, n)
+        p.mu[i], p.sigma[i] = s.μ, s.σ
+    p.flags = flags
+    p.diurnal_period = diurnal_period
+    return p
+
+
+def _cond(conditions, key, default=False):
+    if isinstance(conditions, dict):
+        return bool(conditions.get(key, default))
+    return bool(getattr(conditions, key, default))
+
+
+def inference_flags(conditions) -> int:
+    """Flag set of solve_NDE_mutating: mPP unconditional, boundary fluxes minus scale(0)
+    (training_postprocessing.jl:65,82-93,114-121)."""
+    f = L.FLAG_MPP | L.FLAG_BC_MINUS_SCALE0
+    if _cond(conditions, "convective_adjustment"):
+        f |= L.FLAG_CA
+        if _cond(conditions, "ca_select_dudz"):
+            f |= L.FLAG_CA_SELECT_DUDZ
+    if _cond(conditions, "diurnal"):
+        f |= L.FLAG_DIURNAL
+        if _cond(conditions, "diurnal_minus_scale0"):
+            f |= L.FLAG_DIURNAL_MINUS_SCALE0
+    return f
+
+
+def training_flags(conditions) -> int:
+    """Flag set of NDE / predict_flux (NDE_training.jl:83-147)."""
+    f = 0
+    if _cond(conditions, "modified_pacanowski_philander"):
+        f |= L.FLAG_MPP | L.FLAG_RI_EPS
+    elif _cond(conditions, "convective_adjustment"):
+        raise NotImplementedError("the reference's CA-only training branch reads an undefined κ "
+                                  "(NDE_training.jl:142); it is not reproduced")
+    if _cond(conditions, "zero_weights"):
+        f |= L.FLAG_BC_MINUS_SCALE0
+    if _cond(conditions, "smooth_NN"):
+        f |= L.FLAG_SMOOTH_NN
+    if _cond(conditions, "smooth_Ri"):
+        f |= L.FLAG_SMOOTH_RI
+    if _cond(conditions, "diurnal"):
+        f |= L.FLAG_DIURNAL
+    return f
+
+
+def prepare_parameters_NDE_training(𝒟train, uw_NN, vw_NN, wT_NN, f, Nz, g, α, ν0, ν_m, Riᶜ, ΔRi, Pr, κ, conditions):
+    """NDE_training.jl:1-44.  𝒟train needs: .uw.z (face heights), .t (times), .scalings (dict)."""
+    z = np.asarray(𝒟train.uw.z)
+    t = np.asarray(𝒟train.t).reshape(len(𝒟train.t), -1)[:, 0]
+    H = abs(float(z[-1] - z[0]))
+    τ = abs(float(t[-1] - t[0]))
+    sc = 𝒟train.scalings
+    uw_w, re_uw = destructure(uw_NN)
+    vw_w, re_vw = destructure(vw_NN)
+    wT_w, re_wT = destructure(wT_NN)
+    n1, n2, n3 = len(uw_w), len(vw_w), len(wT_w)
+    constants = SimpleNamespace(H=H, τ=τ, f=f, Nz=Nz, g=g, α=α)
+    if _cond(conditions, "modified_pacanowski_philander"):
+        constants.__dict__.update({"ν0": ν0, "ν_m": ν_m, "Riᶜ": Riᶜ, "ΔRi": ΔRi, "Pr": Pr})
+    if _cond(conditions, "convective_adjustment"):
+        constants.__dict__.update({"κ": κ})
+    scalings = SimpleNamespace(**{n: sc[n] for n in _SCALING_ORDER})
+    derivatives = SimpleNamespace(cell=Dᶜ(Nz, 1 / Nz).astype(np.float32), face=Dᶠ(Nz, 1 / Nz).astype(np.float32))
+    NN_constructions = SimpleNamespace(uw=re_uw, vw=re_vw, wT=re_wT)
+    weights = np.concatenate([uw_w, vw_w, wT_w]).astype(np.float32)
+    NN_sizes = SimpleNamespace(uw=n1, vw=n2, wT=n3)
+    NN_ranges = SimpleNamespace(uw=slice(0, n1), vw=slice(n1, n1 + n2), wT=slice(n1 + n2, n1 + n2 + n3))
+    filters = None  # the 3-point box filters are applied on the device (flags SMOOTH_NN / SMOOTH_RI)
+    return constants, scalings, derivatives, NN_constructions, weights, NN_sizes, NN_ranges, filters
+
+
+def prepare_BCs(𝒟, scalings, wT_top_function=None):
+    """training_postprocessing.jl:35-53: scaled boundary fluxes of the first data column."""
+    sc = scalings if not isinstance(scalings, dict) else SimpleNamespace(**scalings)
+    uw, vw, wT = np.asarray(𝒟.uw.coarse), np.asarray(𝒟.vw.coarse), np.asarray(𝒟.wT.coarse)
+    top = (lambda t: sc.wT(wT_top_function(t))) if wT_top_function is not None else float(sc.wT(wT[-1, 0]))
+    return SimpleNamespace(uw=SimpleNamespace(top=float(sc.uw(uw[-1, 0])), bottom=float(sc.uw(uw[0, 0]))),
+                           vw=SimpleNamespace(top=float(sc.vw(vw[-1, 0])), bottom=float(sc.vw(vw[0, 0]))),
+                           wT=SimpleNamespace(top=top, bottom=float(sc.wT(wT[0, 0]))))
+
+
+def pack_BCs(BCs, Q_diurnal: float = 0.0) -> np.ndarray:
+    """NamedTuple-shaped BCs -> one row of the C ABI's bc[B][8]."""
+    top = BCs.wT.top
+    return np.array([BCs.uw.bottom, BCs.uw.top, BCs.vw.bottom, BCs.vw.top, BCs.wT.bottom,
+                     0.0 if callable(top) else top, Q_diurnal, 0.0], dtype=np.float32)
+
+
+# --------------------------------------------------------------------------------------------------
+# timesteppers (replace OrdinaryDiffEq algorithm objects; dt is in units of τ)
+# --------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class _Stepper:
+    dt: float
+    scheme: int = L.SCHEME_RK4
+    precision: int = L.PREC_FP32
+
+
+def Euler(dt, precision=L.PREC_FP32):
+    return _Stepper(dt, L.SCHEME_EULER, precision)
+
+
+def Heun(dt, precision=L.PREC_FP32):
+    return _Stepper(dt, L.SCHEME_RK2, precision)
+
+
+def RK4(dt, precision=L.PREC_FP32):
+    return _Stepper(dt, L.SCHEME_RK4, precision)
+
+
+def _steps_from_ts(ts, dt):
+    ts = np.asarray(ts, dtype=np.float64)
+    if ts.size < 2:
+        return 0, 1, float(ts[0]) if ts.size else 0.0
+    gap = (ts[1] - ts[0]) / dt
+    save_every = int(round(gap))
+    if save_every < 1 or abs(gap - save_every) > 1e-4 * max(1.0, gap) or not np.allclose(np.diff(ts), ts[1] - ts[0], rtol=1e-5):
+        raise ValueError("ts must be uniformly spaced multiples of the timestepper's dt")
+    return save_every * (ts.size - 1), save_every, float(ts[0])
+
+
+# --------------------------------------------------------------------------------------------------
+# raw ensemble entry points (thin wrappers over the C ABI)
+# --------------------------------------------------------------------------------------------------
+
+
+def rhs(model: NDEModel, params: L.OpzParams, x, bc, t: float, *, with_fluxes=False, precision=L.PREC_FP32):
+    x = _f32(x)
+    B = x.shape[0]
+    bc = _f32(bc, (B, L.BC_STRIDE))
+    dxdt = np.empty_like(x)
+    fl = np.empty((B, 3, model.Nz + 1), dtype=np.float32) if with_fluxes else None
+    L.check(L.lib.opz_rhs(model.ctx._h, model._h, C.byref(params), _fptr(x), _fptr(bc), float(t), B, precision,
+                          _fptr(dxdt), _fptr(fl) if with_fluxes else None))
+    return (dxdt, fl) if with_fluxes else dxdt
+
+
+def rollout_forward(model: NDEModel, params: L.OpzParams, x0, bc, scheme: int, dt_nd: float, n_steps: int,
+                    save_every: int, *, t0: float = 0.0, precision: int = L.PREC_FP32) -> np.ndarray:
+    """Ensemble solve: x0[B,3Nz], bc[B,8] -> out[B, n_save, 3Nz]."""
+    x0 = _f32(x0)
+    B = x0.shape[0]
+    bc = _f32(bc, (B, L.BC_STRIDE))
+    n_save = n_steps // save_every + 1 if save_every > 0 else 1
+    out = np.empty((B, n_save, x0.shape[1]), dtype=np.float32)
+    L.check(L.lib.opz_rollout_forward(model.ctx._h, model._h, C.byref(params), _fptr(x0), _fptr(bc), B, scheme,
+                                      float(dt_nd), float(t0), int(n_steps), int(save_every), precision, _fptr(out)))
+    return out
+
+
+def rollout_forward_dev(model: NDEModel, params: L.OpzParams, x0_ptr: int, bc_ptr: int, B: int, scheme: int,
+                        dt_nd: float, n_steps: int, save_every: int, out_ptr: int, *, t0: float = 0.0,
+                        precision: int = L.PREC_FP32) -> None:
+    """Device-pointer variant: enqueues on the context's stream and returns."""
+    L.check(L.lib.opz_rollout_forward_dev(model.ctx._h, model._h, C.byref(params), C.c_void_p(x0_ptr),
+                                          C.c_void_p(bc_ptr), B, scheme, float(dt_nd), float(t0), int(n_steps),
+                                          int(save_every), precision, C.c_void_p(out_ptr)))
+
+
+def loss_grad(model: NDEModel, params: L.OpzParams, x0, bc, target, loss_w, scheme: int, dt_nd: float, n_steps: int,
+              save_every: int, *, t0: float = 0.0, B_total: Optional[int] = None, precision: int = L.PREC_FP32):
+    """Returns (total, components[6], grad[3P]) of the weighted profile loss (NDE_training.jl:290-323)."""
+    x0 = _f32(x0)
+    B = x0.shape[0]
+    bc = _f32(bc, (B, L.BC_STRIDE))
+    n_save = n_steps // save_every + 1
+    target = _f32(target, (B, n_save, x0.shape[1]))
+    lw = _f32(loss_w, (6,))
+    loss_out = np.zeros(7, dtype=np.float32)
+    grad = np.zeros(3 * model.P, dtype=np.float32)
+    L.check(L.lib.opz_loss_grad(model.ctx._h, model._h, C.byref(params), _fptr(x0), _fptr(bc), B,
+                                B if B_total is None else int(B_total), scheme, float(dt_nd), float(t0), int(n_steps),
+                                int(save_every), _fptr(target), _fptr(lw), precision, _fptr(loss_out), _fptr(grad)))
+    return float(loss_out[0]), loss_out[1:].copy(), grad
+
+
+def mlp_forward(model: NDEModel, which_net: int, x, precision: int = L.PREC_FP32) -> np.ndarray:
+    x = _f32(x)
+    y = np.empty((x.shape[0], model.Nz - 1), dtype=np.float32)
+    L.check(L.lib.opz_mlp_forward(model.ctx._h, model._h, which_net, _fptr(x), x.shape[0], precision, _fptr(y)))
+    return y
+
+
+# --------------------------------------------------------------------------------------------------
+# reference-shaped entry points
+# --------------------------------------------------------------------------------------------------
+_model_cache: dict = {}
+
+
+def _model_for(uw_NN, vw_NN, wT_NN, Nz) -> NDEModel:
+    key = (id(uw_NN), id(vw_NN), id(wT_NN), Nz)
+    m = _model_cache.get(key)
+    if m is None:
+        if len(_model_cache) > 8:
+            _model_cache.clear()
+        m = _model_cache[key] = NDEModel(uw_NN, vw_NN, wT_NN, Nz)
+    return m
+
+
+def solve_NDE_mutating(uw_NN, vw_NN, wT_NN, scalings, constants, BCs, derivatives, uvT0, ts, timestepper, conditions,
+                       Q_diurnal: float = 0.0):
+    """training_postprocessing.jl:55-159.  `timestepper` is Euler/Heun/RK4(dt) and `ts` uniformly spaced
+    multiples of dt.  Returns the 3Nz x length(ts) solution array like `Array(solve(...; saveat=ts))`.
+    A time-dependent `BCs.wT.top` is expressed through `Q_diurnal` (data_containers.jl:131-156)."""
+    cond = dict(conditions) if isinstance(conditions, dict) else dict(vars(conditions))
+    if callable(BCs.wT.top):
+        cond["diurnal"] = True
+    params = make_params(constants, scalings, inference_flags(cond))
+    model = _model_for(uw_NN, vw_NN, wT_NN, int(constants.Nz))
+    n_steps, save_every, t0 = _steps_from_ts(ts, timestepper.dt)
+    out = rollout_forward(model, params, np.asarray(uvT0, dtype=np.float32)[None, :], pack_BCs(BCs, Q_diurnal)[None, :],
+                          timestepper.scheme, timestepper.dt, n_steps, save_every, t0=t0,
+                          precision=timestepper.precision)
+    return out[0].T.copy()
+
+
+def predict_NDE(uw_NN, vw_NN, wT_NN, x, BCs, conditions, scalings, constants, derivatives, filters, t: float = 0.0):
+    """NDE_training.jl:149-165: the right-hand side for one column."""
+    params = make_params(constants, scalings, training_flags(conditions))
+    model = _model_for(uw_NN, vw_NN, wT_NN, int(constants.Nz))
+    return rhs(model, params, np.asarray(x, dtype=np.float32)[None, :], pack_BCs(BCs)[None, :], t)[0]
+
+
+def predict_flux(uw_NN, vw_NN, wT_NN, x, BCs, conditions, scalings, constants, derivatives, filters, t: float = 0.0):
+    """NDE_training.jl:83-147: total scaled fluxes (uw, vw, wT) on the Nz+1 faces."""
+    params = make_params(constants, scalings, training_flags(conditions))
+    model = _model_for(uw_NN, vw_NN, wT_NN, int(constants.Nz))
+    _, fl = rhs(model, params, np.asarray(x, dtype=np.float32)[None, :], pack_BCs(BCs)[None, :], t, with_fluxes=True)
+    return fl[0, 0], fl[0, 1], fl[0, 2]
+
+
+def NDE(x, p, t, NN_ranges, NN_constructions, conditions, scalings, constants, derivatives, filters):
+    """NDE_training.jl:56-66: p = [weights; uw_b, uw_t, vw_b, vw_t, wT_b, wT_t]."""
+    p = np.asarray(p, dtype=np.float32)
+    nW = NN_ranges.wT.stop
+    uw_NN = NN_constructions.uw(p[NN_ranges.uw])
+    vw_NN = NN_constructions.vw(p[NN_ranges.vw])
+    wT_NN = NN_constructions.wT(p[NN_ranges.wT])
+    b = p[nW:nW + 6]
+    BCs = SimpleNamespace(uw=SimpleNamespace(bottom=b[0], top=b[1]), vw=SimpleNamespace(bottom=b[2], top=b[3]),
+                          wT=SimpleNamespace(bottom=b[4], top=b[5]))
+    return predict_NDE(uw_NN, vw_NN, wT_NN, x, BCs, conditions, scalings, constants, derivatives, filters, t)
+
+
+def loss(a, b):
+    """Flux.mse (loss.jl:1-3)."""
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.mean((a - b) ** 2))
+
+
+def calculate_loss_scalings(losses, fractions, train_gradient):
+    """loss.jl:11-31."""
+    vs = (1 - fractions.T) / fractions.T * losses.T / (losses.u + losses.v)
+    profile_loss = vs * (losses.u + losses.v) + losses.T
+    if train_gradient:
+        vgs = (1 - fractions.dTdz) / fractions.dTdz * losses.dTdz / (losses.dudz + losses.dvdz)
+        gradient_loss = vgs * (losses.dudz + losses.dvdz) + losses.dTdz
+        tgs = (1 - fractions.profile) / fractions.profile * profile_loss / gradient_loss
+    else:
+        vgs = 0
+        tgs = 0
+    return SimpleNamespace(u=vs, v=vs, T=1, dudz=tgs * vgs, dvdz=tgs * vgs, dTdz=tgs)
+
+
+class ADAM:
+    """Flux.ADAM(η, β): m <- β1 m + (1-β1) g; v <- β2 v + (1-β2) g²; Δ = η m̂ / (sqrt(v̂) + 1e-8)."""
+
+    def __init__(self, η=1e-3, β=(0.9, 0.999)):
+        self.eta, self.beta = η, β
+        self.state = None
+
+    def apply(self, w: np.ndarray, g: np.ndarray) -> np.ndarray:
+        if self.state is None:
+            self.state = [np.zeros_like(w), np.zeros_like(w), np.array(self.beta, dtype=np.float64)]
+        m, v, bp = self.state
+        b1, b2 = self.beta
+        m *= b1
+        m += (1 - b1) * g
+        v *= b2
+        v += (1 - b2) * g * g
+        step = m / (1 - bp[0]) / (np.sqrt(v / (1 - bp[1])) + 1e-8) * self.eta
+        bp *= self.beta
+        return (w - step).astype(np.float32)
+
+
+def train_NDE(uw_NN, vw_NN, wT_NN, 𝒟train, tsteps, timestepper, optimizers, epochs, *, maxiters=500, ν0=1e-4,
+              ν_m=1e-1, ΔRi=1.0, Riᶜ=0.25, Pr=1.0, κ=10.0, f=1e-4, α=2e-4, g=9.80665,
+              modified_pacanowski_philander=False, convective_adjustment=False, smooth_NN=False, smooth_Ri=False,
+              train_gradient=False, zero_weights=False, gradient_scaling=5e-3, training_fractions=None,
+              diurnal=False, Q_diurnal=None, cb=None, comm=None):
+    """NDE_training.jl:167-374 with the data already in memory (the JLD2 loader is out of scope):
+    𝒟train carries .uvT_scaled [3Nz, n_steps*n_sim], .t, .uw/.vw/.wT (.scaled, .z), .scalings, .n_simulations.
+    Loss + exact discrete-adjoint gradient come from libopz; ADAM and the callback stay on the host.
+    `comm`, if given, is a callable all-reducing (sum) a numpy array in place across ranks."""
+    assert not (modified_pacanowski_philander and convective_adjustment)
+    if zero_weights:
+        assert modified_pacanowski_philander
+    conditions = dict(modified_pacanowski_philander=modified_pacanowski_philander,
+                      convective_adjustment=convective_adjustment, smooth_NN=smooth_NN, smooth_Ri=smooth_Ri,
+                      train_gradient=train_gradient, zero_weights=zero_weights, diurnal=diurnal)
+    Nz = len(𝒟train.u.z)
+    n_sim = int(𝒟train.n_simulations)
+    constants, scalings, derivatives, NN_constructions, weights, NN_sizes, NN_ranges, _ = \
+        prepare_parameters_NDE_training(𝒟train, uw_NN, vw_NN, wT_NN, f, Nz, g, α, ν0, ν_m, Riᶜ, ΔRi, Pr, κ, conditions)
+    t_all = np.asarray(𝒟train.t).reshape(len(𝒟train.t), -1)[:, 0]
+    n_steps_data = len(t_all) // n_sim
+    tsteps = np.asarray(tsteps)
+    uvT = np.asarray(𝒟train.uvT_scaled, dtype=np.float32)
+    x0 = np.stack([uvT[:, n_steps_data * i + tsteps[0]] for i in range(n_sim)])
+    target = np.stack([uvT[:, n_steps_data * i:n_steps_data * (i + 1)][:, tsteps].T for i in range(n_sim)])
+    t_train = t_all[tsteps] / constants.τ
+    bc = np.zeros((n_sim, L.BC_STRIDE), dtype=np.float32)
+    for i in range(n_sim):
+        c = n_steps_data * i + tsteps[0]
+        bc[i, :6] = [𝒟train.uw.scaled[0, c], 𝒟train.uw.scaled[-1, c], 𝒟train.vw.scaled[0, c],
+                     𝒟train.vw.scaled[-1, c], 𝒟train.wT.scaled[0, c], 𝒟train.wT.scaled[-1, c]]
+        if diurnal:
+            bc[i, 6] = Q_diurnal[i]
+    params = make_params(constants, scalings, training_flags(conditions))
+    n_steps, save_every, t0 = _steps_from_ts(t_train, timestepper.dt)
+    model = NDEModel(uw_NN, vw_NN, wT_NN, Nz)
+
+    def evaluate(w, lw):
+        model.set_weights(w)
+        total, comps, grad = loss_grad(model, params, x0, bc, target, lw, timestepper.scheme, timestepper.dt,
+                                       n_steps, save_every, t0=t0, precision=timestepper.precision)
+        if comm is not None:
+            buf = np.concatenate([[total], comps, grad]).astype(np.float32)
+            comm(buf)
+            total, comps, grad = float(buf[0]), buf[1:7], buf[7:]
+        return total, comps, grad
+
+    if training_fractions is None:
+        gs = gradient_scaling if train_gradient else 0.0
+        lw = np.array([1, 1, 1, gs, gs, gs], dtype=np.float32)
+    else:
+        ones = np.array([1, 1, 1, 1, 1, 1] if train_gradient else [1, 1, 1, 0, 0, 0], dtype=np.float32)
+        _, c, _ = evaluate(weights, ones)
+        ls = calculate_loss_scalings(SimpleNamespace(u=c[0], v=c[1], T=c[2], dudz=c[3], dvdz=c[4], dTdz=c[5]),
+                                     training_fractions, train_gradient)
+        lw = np.array([ls.u, ls.v, ls.T, ls.dudz, ls.dvdz, ls.dTdz], dtype=np.float32)
+    history = []
+    for opt in optimizers:
+        for _epoch in range(epochs):
+            for it in range(maxiters):
+                total, comps, grad = evaluate(weights, lw)
+                history.append((total, comps.copy()))
+                if cb is not None:
+                    cb(weights, total, comps, lw)
+                weights = opt.apply(weights, grad)
+    model.close()
+    out = tuple(NN_constructions.__dict__[k](weights[NN_ranges.__dict__[k]]) for k in ("uw", "vw", "wT"))
+    return out + (history,)
+
+
+def predict(𝒱, model: NDEModel, which_net: int, *, scaled: bool = False):
+    """src/predict.jl:12-34: apply one net to every column of 𝒱.uvT_scaled (3Nz x Nt) in one launch.
+    Returns (predictions (Nz-1) x Nt, truth)."""
+    x = np.asarray(𝒱.uvT_scaled, dtype=np.float32).T
+    y = mlp_forward(model, which_net, x).T
+    if scaled:
+        return y, 𝒱.scaled
+    return 𝒱.unscale_fn(y), 𝒱.coarse

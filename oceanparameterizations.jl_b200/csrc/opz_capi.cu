@@ -1,0 +1,359 @@
+// opz_capi.cu — the extern "C" surface declared in include/opz.h.
+// Host-pointer entry points stage through grow-only device scratch owned by the context and
+// are blocking; `_dev` entry points enqueue on the context stream and return.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "opz_internal.h"
+
+namespace opz {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return OPZ_ECUDA;
+}
+
+int ensure_scratch(opz_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) {
+      OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+      OPZ_CUDA(cudaFree(ctx->scratch[slot]));
+      ctx->scratch[slot] = nullptr;
+      ctx->scratch_bytes[slot] = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], bytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("device allocation of " + std::to_string(bytes) + " bytes failed");
+      return OPZ_ENOMEM;
+    }
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->scratch[slot];
+  return OPZ_OK;
+}
+
+static int check_common(const opz_ctx* ctx, const opz_model* m, const opz_params* p) {
+  if (!ctx || !m || !p) { set_error("null ctx/model/params"); return OPZ_EINVAL; }
+  if (m->ctx != ctx) { set_error("model belongs to another context"); return OPZ_EINVAL; }
+  if (p->nz != m->nz) { set_error("params.nz does not match the model"); return OPZ_EINVAL; }
+  return OPZ_OK;
+}
+
+static int check_rollout(int64_t B, int scheme, int n_steps, int save_every) {
+  if (B < 0 || n_steps < 0) { set_error("negative B or n_steps"); return OPZ_EINVAL; }
+  if (scheme != OPZ_EULER && scheme != OPZ_RK2 && scheme != OPZ_RK4) { set_error("unknown scheme"); return OPZ_EINVAL; }
+  if (save_every > 0 && n_steps % save_every != 0) {
+    set_error("n_steps must be a multiple of save_every (ts must be multiples of dt)");
+    return OPZ_EINVAL;
+  }
+  return OPZ_OK;
+}
+
+static int n_save_of(int n_steps, int save_every) { return save_every > 0 ? n_steps / save_every + 1 : 1; }
+
+}  // namespace opz
+
+using namespace opz;
+
+extern "C" {
+
+int opz_version(void) { return OPZ_VERSION; }
+const char* opz_last_error(void) { return g_err.c_str(); }
+
+int opz_ctx_create(int device, opz_ctx** out) {
+  if (!out) { set_error("null out"); return OPZ_EINVAL; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device: libopz has no CPU fallback");
+    return OPZ_ENODEV;
+  }
+  if (device < 0 || device >= n) { set_error("device index out of range"); return OPZ_EINVAL; }
+  cudaDeviceProp prop{};
+  OPZ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("device '") + prop.name + "' is not sm_100: libopz is built for sm_100a only");
+    return OPZ_ENODEV;
+  }
+  OPZ_CUDA(cudaSetDevice(device));
+  opz_ctx* c = new (std::nothrow) opz_ctx();
+  if (!c) { set_error("host allocation failed"); return OPZ_ENOMEM; }
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+  c->owns_stream = true;
+  *out = c;
+  return OPZ_OK;
+}
+
+int opz_ctx_destroy(opz_ctx* ctx) {
+  if (!ctx) return OPZ_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return OPZ_OK;
+}
+
+int opz_ctx_set_stream(opz_ctx* ctx, void* cuda_stream) {
+  if (!ctx) { set_error("null ctx"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->owns_stream && ctx->stream) OPZ_CUDA(cudaStreamDestroy(ctx->stream));
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->owns_stream = false;
+  return OPZ_OK;
+}
+
+int opz_ctx_synchronize(opz_ctx* ctx) {
+  if (!ctx) { set_error("null ctx"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
+int64_t opz_ctx_launch_count(const opz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int opz_model_create(opz_ctx* ctx, int nz, int n_sizes, const int* sizes, int act, const float* w_uw,
+                     const float* w_vw, const float* w_wT, opz_model** out) {
+  if (!ctx || !sizes || !out || !w_uw || !w_vw || !w_wT) { set_error("null argument"); return OPZ_EINVAL; }
+  *out = nullptr;
+  const int L = n_sizes - 1;
+  if (L < 1 || L > kMaxLayers) { set_error("1..6 Dense layers supported"); return OPZ_EINVAL; }
+  if (nz < 2 || nz > kMaxNz) { set_error("nz must be in [2, 64]"); return OPZ_EINVAL; }
+  if (sizes[0] != 3 * nz || sizes[L] != nz - 1) {
+    set_error("the nets must map 3*nz inputs to nz-1 interior-face outputs");
+    return OPZ_EINVAL;
+  }
+  if (act < OPZ_ACT_IDENTITY || act > OPZ_ACT_LEAKYRELU) { set_error("unknown activation"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  opz_model* m = new (std::nothrow) opz_model();
+  if (!m) { set_error("host allocation failed"); return OPZ_ENOMEM; }
+  m->ctx = ctx;
+  m->nz = nz;
+  m->nd.n_layers = L;
+  m->nd.act = act;
+  int64_t off = 0;
+  m->max_hidden = 0;
+  for (int l = 0; l <= L; ++l) {
+    if (sizes[l] < 1) { delete m; set_error("layer sizes must be positive"); return OPZ_EINVAL; }
+    m->nd.sizes[l] = sizes[l];
+    if (l > 0 && l < L && sizes[l] > m->max_hidden) m->max_hidden = sizes[l];
+  }
+  for (int l = 0; l < L; ++l) {
+    m->nd.w_off[l] = off; off += (int64_t)sizes[l] * sizes[l + 1];
+    m->nd.b_off[l] = off; off += sizes[l + 1];
+  }
+  m->nd.P = off;
+  cudaError_t e = cudaMalloc(&m->w_dev, sizeof(float) * 3 * (size_t)off);
+  if (e != cudaSuccess) { delete m; (void)cudaGetLastError(); set_error("device allocation failed"); return OPZ_ENOMEM; }
+  const float* src[3] = {w_uw, w_vw, w_wT};
+  for (int i = 0; i < 3; ++i) {
+    e = cudaMemcpyAsync(m->w_dev + (size_t)i * off, src[i], sizeof(float) * (size_t)off, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(m->w_dev); delete m; return cuda_fail(e, "weights H2D"); }
+  }
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(m->w_dev); delete m; return cuda_fail(e, "weights H2D sync"); }
+  m->tc_pack_valid = false;
+  *out = m;
+  return OPZ_OK;
+}
+
+int opz_model_set_weights(opz_model* m, const float* w) {
+  if (!m || !w) { set_error("null argument"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(m->ctx->device));
+  OPZ_CUDA(cudaMemcpyAsync(m->w_dev, w, sizeof(float) * 3 * (size_t)m->nd.P, cudaMemcpyHostToDevice, m->ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  m->tc_pack_valid = false;
+  return OPZ_OK;
+}
+
+int opz_model_set_weights_dev(opz_model* m, const float* w) {
+  if (!m || !w) { set_error("null argument"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(m->ctx->device));
+  OPZ_CUDA(cudaMemcpyAsync(m->w_dev, w, sizeof(float) * 3 * (size_t)m->nd.P, cudaMemcpyDeviceToDevice, m->ctx->stream));
+  m->tc_pack_valid = false;
+  return OPZ_OK;
+}
+
+int opz_model_get_weights(const opz_model* m, float* w) {
+  if (!m || !w) { set_error("null argument"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(m->ctx->device));
+  OPZ_CUDA(cudaMemcpyAsync(w, m->w_dev, sizeof(float) * 3 * (size_t)m->nd.P, cudaMemcpyDeviceToHost, m->ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return OPZ_OK;
+}
+
+int64_t opz_model_n_params(const opz_model* m) { return m ? m->nd.P : 0; }
+
+int opz_model_destroy(opz_model* m) {
+  if (!m) return OPZ_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  tc_model_release(m);
+  if (m->w_dev) cudaFree(m->w_dev);
+  delete m;
+  return OPZ_OK;
+}
+
+// ---- single RHS -------------------------------------------------------------------------------
+int opz_rhs(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x, const float* bc, float t,
+            int64_t B, int precision, float* dxdt, float* fluxes) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if (!x || !bc || !dxdt || B < 0) { set_error("null buffer or negative B"); return OPZ_EINVAL; }
+  if (precision != OPZ_PREC_FP32) { set_error("opz_rhs: only OPZ_PREC_FP32"); return OPZ_EUNSUP; }
+  if (B == 0) return OPZ_OK;
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t S = 3 * (size_t)m->nz, nf = 3 * (size_t)(m->nz + 1);
+  float *dx, *dbc, *dk, *dfl = nullptr;
+  if ((rc = ensure_scratch(ctx, 0, sizeof(float) * B * S, (void**)&dx))) return rc;
+  if ((rc = ensure_scratch(ctx, 1, sizeof(float) * B * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
+  if ((rc = ensure_scratch(ctx, 2, sizeof(float) * B * S, (void**)&dk))) return rc;
+  if (fluxes && (rc = ensure_scratch(ctx, 3, sizeof(float) * B * nf, (void**)&dfl))) return rc;
+  OPZ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * B * S, cudaMemcpyHostToDevice, ctx->stream));
+  OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fp32_rhs(ctx, m, make_dev_params(*p), dx, dbc, t, B, dk, dfl))) return rc;
+  OPZ_CUDA(cudaMemcpyAsync(dxdt, dk, sizeof(float) * B * S, cudaMemcpyDeviceToHost, ctx->stream));
+  if (fluxes) OPZ_CUDA(cudaMemcpyAsync(fluxes, dfl, sizeof(float) * B * nf, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
+// ---- forward rollout --------------------------------------------------------------------------
+int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
+                            const float* bc, int64_t B, int scheme, float dt_nd, float t0, int n_steps,
+                            int save_every, int precision, float* out) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
+  if (!x0 || !bc || !out) { set_error("null buffer"); return OPZ_EINVAL; }
+  if (B == 0) return OPZ_OK;
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  RolloutCall c{};
+  c.P = make_dev_params(*p);
+  c.x0 = x0; c.bc = bc; c.out = out; c.B = B; c.scheme = scheme; c.dt = dt_nd; c.t0 = t0;
+  c.n_steps = n_steps; c.save_every = save_every; c.n_save = n_save_of(n_steps, save_every);
+  if (precision == OPZ_PREC_FP32) return fp32_rollout(ctx, m, c);
+  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
+    if (!m->tc_pack_valid && (rc = tc_model_prepare(const_cast<opz_model*>(m)))) return rc;
+    return tc_rollout(ctx, m, c, precision);
+  }
+  set_error("unknown precision");
+  return OPZ_EINVAL;
+}
+
+int opz_rollout_forward(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
+                        const float* bc, int64_t B, int scheme, float dt_nd, float t0, int n_steps,
+                        int save_every, int precision, float* out) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
+  if (!x0 || !bc || !out) { set_error("null buffer"); return OPZ_EINVAL; }
+  if (B == 0) return OPZ_OK;
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t S = 3 * (size_t)m->nz;
+  const size_t n_save = n_save_of(n_steps, save_every);
+  float *dx, *dbc, *dout;
+  if ((rc = ensure_scratch(ctx, 0, sizeof(float) * B * S, (void**)&dx))) return rc;
+  if ((rc = ensure_scratch(ctx, 1, sizeof(float) * B * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
+  if ((rc = ensure_scratch(ctx, 2, sizeof(float) * B * n_save * S, (void**)&dout))) return rc;
+  OPZ_CUDA(cudaMemcpyAsync(dx, x0, sizeof(float) * B * S, cudaMemcpyHostToDevice, ctx->stream));
+  OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = opz_rollout_forward_dev(ctx, m, p, dx, dbc, B, scheme, dt_nd, t0, n_steps, save_every, precision, dout)))
+    return rc;
+  OPZ_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * B * n_save * S, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
+// ---- loss + gradient ----------------------------------------------------------------------------
+int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                      int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps,
+                      int save_every, const float* target, const float* loss_w, int precision,
+                      float* loss_out, float* grad_out) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
+  if (!x0 || !bc || !target || !loss_w || !loss_out || !grad_out) { set_error("null buffer"); return OPZ_EINVAL; }
+  if (save_every <= 0) { set_error("opz_loss_grad needs save_every > 0"); return OPZ_EINVAL; }
+  if (B_total < B || B_total < 1) { set_error("B_total must be >= B and >= 1"); return OPZ_EINVAL; }
+  if (precision != OPZ_PREC_FP32) { set_error("opz_loss_grad: only OPZ_PREC_FP32 so far"); return OPZ_EUNSUP; }
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  LossGradCall c{};
+  c.r.P = make_dev_params(*p);
+  c.r.x0 = x0; c.r.bc = bc; c.r.out = nullptr; c.r.B = B; c.r.scheme = scheme; c.r.dt = dt_nd; c.r.t0 = t0;
+  c.r.n_steps = n_steps; c.r.save_every = save_every; c.r.n_save = n_save_of(n_steps, save_every);
+  c.target = target;
+  for (int i = 0; i < 6; ++i) c.loss_w[i] = loss_w[i];
+  c.B_total = B_total;
+  c.loss_out = loss_out;
+  c.grad_out = grad_out;
+  return fp32_loss_grad(ctx, m, c);
+}
+
+int opz_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                  int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps, int save_every,
+                  const float* target, const float* loss_w, int precision, float* loss_out, float* grad_out) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
+  if (!x0 || !bc || !target || !loss_w || !loss_out || !grad_out) { set_error("null buffer"); return OPZ_EINVAL; }
+  if (save_every <= 0) { set_error("opz_loss_grad needs save_every > 0"); return OPZ_EINVAL; }
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t S = 3 * (size_t)m->nz;
+  const size_t n_save = n_save_of(n_steps, save_every);
+  const size_t P3 = 3 * (size_t)m->nd.P;
+  float *dx, *dbc, *dtgt, *dloss, *dgrad;
+  if ((rc = ensure_scratch(ctx, 0, sizeof(float) * (B ? B : 1) * S, (void**)&dx))) return rc;
+  if ((rc = ensure_scratch(ctx, 1, sizeof(float) * (B ? B : 1) * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
+  if ((rc = ensure_scratch(ctx, 2, sizeof(float) * (B ? B : 1) * n_save * S, (void**)&dtgt))) return rc;
+  if ((rc = ensure_scratch(ctx, 3, sizeof(float) * (P3 + 8), (void**)&dgrad))) return rc;
+  dloss = dgrad + P3;
+  if (B > 0) {
+    OPZ_CUDA(cudaMemcpyAsync(dx, x0, sizeof(float) * B * S, cudaMemcpyHostToDevice, ctx->stream));
+    OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+    OPZ_CUDA(cudaMemcpyAsync(dtgt, target, sizeof(float) * B * n_save * S, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((rc = opz_loss_grad_dev(ctx, m, p, dx, dbc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, dtgt, loss_w,
+                              precision, dloss, dgrad)))
+    return rc;
+  OPZ_CUDA(cudaMemcpyAsync(grad_out, dgrad, sizeof(float) * P3, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaMemcpyAsync(loss_out, dloss, sizeof(float) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
+// ---- batched MLP --------------------------------------------------------------------------------
+int opz_mlp_forward(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt, int precision,
+                    float* y) {
+  if (!ctx || !m || !x || !y) { set_error("null argument"); return OPZ_EINVAL; }
+  if (m->ctx != ctx) { set_error("model belongs to another context"); return OPZ_EINVAL; }
+  if (which_net < 0 || which_net > 2 || Nt < 0) { set_error("which_net must be 0..2, Nt >= 0"); return OPZ_EINVAL; }
+  if (precision != OPZ_PREC_FP32) { set_error("opz_mlp_forward: only OPZ_PREC_FP32"); return OPZ_EUNSUP; }
+  if (Nt == 0) return OPZ_OK;
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t S = 3 * (size_t)m->nz, NO = (size_t)m->nz - 1;
+  float *dx, *dy;
+  int rc;
+  if ((rc = ensure_scratch(ctx, 0, sizeof(float) * Nt * S, (void**)&dx))) return rc;
+  if ((rc = ensure_scratch(ctx, 2, sizeof(float) * Nt * NO, (void**)&dy))) return rc;
+  OPZ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * Nt * S, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fp32_mlp(ctx, m, which_net, dx, Nt, dy))) return rc;
+  OPZ_CUDA(cudaMemcpyAsync(y, dy, sizeof(float) * Nt * NO, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// opz_fp32.cu — FP32 CUDA-core kernels: persistent fixed-step rollout, single RHS, batched MLP.
+//
+// One CTA owns a tile of M ocean columns for the WHOLE rollout: the state x_n, the RK
+// accumulator and the stage input never leave shared memory between time steps; HBM sees the
+// initial profiles once, the forcing once and the saved snapshots.  Per RHS the three nets run
+// as batched FP32 GEMM chains (opz_simt.cuh) with the weights streamed from L2, then one thread
+// per column evaluates the physics (opz_device.cuh::column_rhs) and folds the tendency straight
+// into the Runge-Kutta registers.
+//
+// Replaces solve_NDE_mutating (wind_mixing/src/training_postprocessing.jl:55-159) with a
+// fixed-step Euler / Heun / RK4 scheme (north_star replaces OrdinaryDiffEq's ROCK4).
+#include "opz_internal.h"
+#include "opz_simt.cuh"
+
+namespace opz {
+
+struct Fp32Args {
+  DevParams P;
+  NetDesc nd;
+  const float* w;   // [3P]
+  const float* x0;
+  const float* bc;
+  float* out;
+  float* aux;       // fluxes for the rhs kernel
+  int64_t B;
+  int scheme;
+  float dt, t0;
+  int n_steps, save_every, n_save;
+  int max_hidden;
+  int which_net;
+};
+
+template <int M>
+struct Smem {
+  float *xn, *kacc, *xs[2], *Y, *bufA, *bufB, *stage;
+  __device__ Smem(float* base, int nz, int max_hidden) {
+    const int S = 3 * nz * M;
+    xn = base; base += S;
+    kacc = base; base += S;
+    xs[0] = base; base += S;
+    xs[1] = base; base += S;
+    Y = base; base += 3 * nz * M;
+    bufA = base; base += max_hidden * M;
+    bufB = base; base += max_hidden * M;
+    stage = base;
+  }
+  static size_t bytes(int nz, int max_hidden) {
+    return sizeof(float) * ((size_t)5 * 3 * nz * M + (size_t)2 * max_hidden * M + SimtCfg<M>::STAGE_TOTAL);
+  }
+};
+
+template <int M>
+__device__ __forceinline__ void run_three_nets(const Fp32Args& a, const Smem<M>& s, const float* in) {
+  for (int net = 0; net < 3; ++net)
+    mlp_chain_fp32<M>(a.nd, a.w + (size_t)net * a.nd.P, in, s.bufA, s.bufB, s.Y + (size_t)net * a.P.nz * M, s.stage);
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads, 1) rollout_fp32_kernel(const __grid_constant__ Fp32Args a) {
+  extern __shared__ __align__(16) float smem_f[];
+  const Smem<M> s(smem_f, a.P.nz, a.max_hidden);
+  const int tid = threadIdx.x;
+  const int nz = a.P.nz, S = 3 * nz;
+  const int64_t n_tiles = (a.B + M - 1) / M;
+  const float h = a.dt;
+  const int stages = a.scheme == OPZ_RK4 ? 4 : (a.scheme == OPZ_RK2 ? 2 : 1);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t col0 = tile * M;
+    // ---- load the initial profiles: global [col][i] -> shared [i][m] ----
+    for (int e = tid; e < M * S; e += kThreads) {
+      const int m = e / S, i = e - m * S;
+      const int64_t col = col0 + m;
+      const float v = col < a.B ? a.x0[col * S + i] : 0.0f;
+      s.xn[i * M + m] = v;
+      s.xs[0][i * M + m] = v;
+    }
+    float bc[OPZ_BC_STRIDE];
+    if (tid < M) {
+      const int64_t col = col0 + tid;
+#pragma unroll
+      for (int q = 0; q < OPZ_BC_STRIDE; ++q) bc[q] = col < a.B ? a.bc[col * OPZ_BC_STRIDE + q] : 0.0f;
+    }
+    __syncthreads();
+    auto save = [&](int slot) {
+      for (int e = tid; e < M * S; e += kThreads) {
+        const int m = e / S, i = e - m * S;
+        const int64_t col = col0 + m;
+        if (col < a.B) a.out[(col * a.n_save + slot) * S + i] = s.xn[i * M + m];
+      }
+    };
+    if (a.save_every > 0) save(0);
+
+    int cur = 0;
+    for (int n = 0; n < a.n_steps; ++n) {
+      const float tn = a.t0 + (float)n * h;
+      for (int st = 0; st < stages; ++st) {
+        run_three_nets<M>(a, s, s.xs[cur]);  // ends with __syncthreads
+        if (tid < M) {
+          const float* xin = s.xs[cur];
+          float* xnext = s.xs[cur ^ 1];
+          float ts = tn;
+          if (a.scheme == OPZ_RK4) ts = (st == 0) ? tn : (st == 3 ? tn + h : tn + h * 0.5f);
+          else if (a.scheme == OPZ_RK2) ts = (st == 0) ? tn : tn + h;
+          auto X = [&](int i) { return xin[i * M + tid]; };
+          auto Y = [&](int net, int j) { return s.Y[(net * nz + j) * M + tid]; };
+          const int scheme = a.scheme;
+          auto K = [&](int i, float k) {
+            const int o = i * M + tid;
+            const float xo = s.xn[o];
+            if (scheme == OPZ_RK4) {
+              if (st == 0) { s.kacc[o] = k; xnext[o] = xo + (h * 0.5f) * k; }
+              else if (st == 1) { s.kacc[o] = s.kacc[o] + 2.0f * k; xnext[o] = xo + (h * 0.5f) * k; }
+              else if (st == 2) { s.kacc[o] = s.kacc[o] + 2.0f * k; xnext[o] = xo + h * k; }
+              else { const float xv = xo + (h / 6.0f) * (s.kacc[o] + k); s.xn[o] = xv; xnext[o] = xv; }
+            } else if (scheme == OPZ_RK2) {
+              if (st == 0) { s.kacc[o] = k; xnext[o] = xo + h * k; }
+              else { const float xv = xo + (h * 0.5f) * (s.kacc[o] + k); s.xn[o] = xv; xnext[o] = xv; }
+            } else {
+              const float xv = xo + h * k; s.xn[o] = xv; xnext[o] = xv;
+            }
+          };
+          column_rhs(a.P, bc, ts, X, Y, K, NoFlux());
+        }
+        cur ^= 1;
+        __syncthreads();
+      }
+      if (a.save_every > 0 && (n + 1) % a.save_every == 0) save((n + 1) / a.save_every);
+    }
+    if (a.save_every <= 0) save(0);
+    __syncthreads();
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads, 1) rhs_fp32_kernel(const __grid_constant__ Fp32Args a) {
+  extern __shared__ __align__(16) float smem_f[];
+  const Smem<M> s(smem_f, a.P.nz, a.max_hidden);
+  const int tid = threadIdx.x;
+  const int nz = a.P.nz, S = 3 * nz;
+  const int64_t n_tiles = (a.B + M - 1) / M;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t col0 = tile * M;
+    for (int e = tid; e < M * S; e += kThreads) {
+      const int m = e / S, i = e - m * S;
+      const int64_t col = col0 + m;
+      s.xs[0][i * M + m] = col < a.B ? a.x0[col * S + i] : 0.0f;
+    }
+    __syncthreads();
+    run_three_nets<M>(a, s, s.xs[0]);
+    const int64_t col = col0 + tid;
+    if (tid < M && col < a.B) {
+      float bc[OPZ_BC_STRIDE];
+#pragma unroll
+      for (int q = 0; q < OPZ_BC_STRIDE; ++q) bc[q] = a.bc[col * OPZ_BC_STRIDE + q];
+      auto X = [&](int i) { return s.xs[0][i * M + tid]; };
+      auto Y = [&](int net, int j) { return s.Y[(net * nz + j) * M + tid]; };
+      auto K = [&](int i, float k) { a.out[col * S + i] = k; };
+      if (a.aux) {
+        auto FL = [&](int v, int f, float val) { a.aux[(col * 3 + v) * (nz + 1) + f] = val; };
+        column_rhs(a.P, bc, a.t0, X, Y, K, FL);
+      } else {
+        column_rhs(a.P, bc, a.t0, X, Y, K, NoFlux());
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// predict(V, model) (src/predict.jl:12-34): x[Nt][3nz] -> y[Nt][nz-1] for one net.
+template <int M>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fp32_kernel(const __grid_constant__ Fp32Args a) {
+  extern __shared__ __align__(16) float smem_f[];
+  const Smem<M> s(smem_f, a.P.nz, a.max_hidden);
+  const int tid = threadIdx.x;
+  const int nz = a.P.nz, S = 3 * nz, NO = a.nd.sizes[a.nd.n_layers];
+  const int64_t n_tiles = (a.B + M - 1) / M;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t col0 = tile * M;
+    for (int e = tid; e < M * S; e += kThreads) {
+      const int m = e / S, i = e - m * S;
+      const int64_t col = col0 + m;
+      s.xs[0][i * M + m] = col < a.B ? a.x0[col * S + i] : 0.0f;
+    }
+    __syncthreads();
+    mlp_chain_fp32<M>(a.nd, a.w + (size_t)a.which_net * a.nd.P, s.xs[0], s.bufA, s.bufB, s.Y, s.stage);
+    for (int e = tid; e < M * NO; e += kThreads) {
+      const int m = e / NO, j = e - m * NO;
+      const int64_t col = col0 + m;
+      if (col < a.B) a.out[col * NO + j] = s.Y[j * M + m];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- host launchers ---------------------------------------------------------------------------
+static int pick_tile(const opz_ctx* ctx, const opz_model* m) {
+  if ((int)Smem<64>::bytes(m->nz, m->max_hidden) <= ctx->smem_optin) return 64;
+  if ((int)Smem<32>::bytes(m->nz, m->max_hidden) <= ctx->smem_optin) return 32;
+  return 0;
+}
+
+template <class KernelT>
+static int launch(opz_ctx* ctx, KernelT kern, size_t smem, int64_t n_tiles, const Fp32Args& a) {
+  OPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = n_tiles < (int64_t)ctx->sm_count ? n_tiles : (int64_t)ctx->sm_count;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(a);
+  OPZ_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return OPZ_OK;
+}
+
+static Fp32Args base_args(const opz_model* m, const DevParams& P) {
+  Fp32Args a{};
+  a.P = P;
+  a.nd = m->nd;
+  a.w = m->w_dev;
+  a.max_hidden = m->max_hidden;
+  return a;
+}
+
+int fp32_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c) {
+  const int M = pick_tile(ctx, m);
+  if (!M) { set_error("fp32 path: hidden width / nz too large for shared memory"); return OPZ_EUNSUP; }
+  Fp32Args a = base_args(m, c.P);
+  a.x0 = c.x0; a.bc = c.bc; a.out = c.out; a.B = c.B; a.scheme = c.scheme; a.dt = c.dt; a.t0 = c.t0;
+  a.n_steps = c.n_steps; a.save_every = c.save_every; a.n_save = c.n_save;
+  if (M == 64) return launch(ctx, rollout_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (c.B + 63) / 64, a);
+  return launch(ctx, rollout_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (c.B + 31) / 32, a);
+}
+
+int fp32_rhs(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* x, const float* bc, float t,
+             int64_t B, float* dxdt, float* fluxes) {
+  const int M = pick_tile(ctx, m);
+  if (!M) { set_error("fp32 path: hidden width / nz too large for shared memory"); return OPZ_EUNSUP; }
+  Fp32Args a = base_args(m, P);
+  a.x0 = x; a.bc = bc; a.out = dxdt; a.aux = fluxes; a.B = B; a.t0 = t;
+  if (M == 64) return launch(ctx, rhs_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (B + 63) / 64, a);
+  return launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (B + 31) / 32, a);
+}
+
+int fp32_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt, float* y) {
+  const int M = pick_tile(ctx, m);
+  if (!M) { set_error("fp32 path: hidden width / nz too large for shared memory"); return OPZ_EUNSUP; }
+  DevParams P{};
+  P.nz = m->nz;
+  Fp32Args a = base_args(m, P);
+  a.x0 = x; a.out = y; a.B = Nt; a.which_net = which_net;
+  if (M == 64) return launch(ctx, mlp_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (Nt + 63) / 64, a);
+  return launch(ctx, mlp_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (Nt + 31) / 32, a);
+}
+
+}  // namespace opz

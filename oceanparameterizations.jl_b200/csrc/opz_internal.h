@@ -1,0 +1,78 @@
+// opz_internal.h — host-side objects behind the opaque handles of include/opz.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "opz_device.cuh"
+
+struct opz_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int smem_optin = 0;        // max dynamic shared memory per block
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  int64_t launches = 0;
+  // grow-only device scratch (staging of host buffers; BPTT checkpoints)
+  void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct opz_model {
+  opz_ctx* ctx = nullptr;
+  int nz = 0;
+  opz::NetDesc nd{};
+  int max_hidden = 0;
+  float* w_dev = nullptr;        // [3P] FP32, Flux.destructure order, nets uw|vw|wT
+  // tensor-core path: weights re-packed as BF16 (hi, lo) images of the shared-memory B tiles
+  void* tc_pack = nullptr;
+  size_t tc_pack_bytes = 0;
+  bool tc_pack_valid = false;
+  void* tc_plan = nullptr;       // opaque (opz_tc.cu)
+};
+
+namespace opz {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);  // records the message, returns OPZ_ECUDA
+
+#define OPZ_CUDA(expr)                                          \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return ::opz::cuda_fail(_e, #expr);  \
+  } while (0)
+
+int ensure_scratch(opz_ctx* ctx, int slot, size_t bytes, void** out);
+
+struct RolloutCall {
+  DevParams P;
+  const float* x0;   // device [B][3nz]
+  const float* bc;   // device [B][8]
+  float* out;        // device [B][n_save][3nz]
+  int64_t B;
+  int scheme;
+  float dt, t0;
+  int n_steps, save_every, n_save;
+};
+
+// FP32 CUDA-core path (opz_fp32.cu)
+int fp32_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c);
+int fp32_rhs(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* x, const float* bc, float t,
+             int64_t B, float* dxdt, float* fluxes);
+int fp32_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt, float* y);
+
+struct LossGradCall {
+  RolloutCall r;          // r.out unused
+  const float* target;    // device [B][n_save][3nz]
+  float loss_w[6];
+  int64_t B_total;
+  float* loss_out;        // device [7]
+  float* grad_out;        // device [3P]
+};
+int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c);
+
+// tcgen05 tensor-core path (opz_tc.cu)
+int tc_model_prepare(opz_model* m);          // (re)pack weights after set_weights
+void tc_model_release(opz_model* m);
+int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
+
+}  // namespace opz

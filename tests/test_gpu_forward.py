@@ -1,0 +1,206 @@
+"""GPU parity of the forward path (rhs, rollout, batched MLP) against the CPU oracle and the
+committed golden vectors.  Everything goes through the C ABI (ctypes -> libopz.so)."""
+import numpy as np
+import pytest
+
+from helpers import product_model, product_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4  # north_star: max relative profile error of the FP32 path after the full rollout
+
+
+@pytest.fixture(scope="module")
+def ctx(opz):
+    return opz.default_context()
+
+
+def test_no_cpu_fallback_and_native_lib_loaded(opz, ctx):
+    import os
+    assert os.path.exists(opz.LIB_PATH)
+    assert opz.lib.opz_version() == 100
+    n0 = ctx.launch_count
+    assert n0 >= 0
+
+
+def test_rhs_flavours_match_golden(opz, oracle, golden_dir, ctx):
+    g = np.load(f"{golden_dir}/rhs_flavours.npz")
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=3)
+    model = product_model(opz, m)
+    names = [k[2:] for k in g.files if k.startswith("k_")]
+    assert len(names) == 8
+    for name in names:
+        p = oracle.Params(flags=int(g["flags_" + name]))
+        k, F = opz.rhs(model, product_params(opz, p), g["x"], g["bc"], 0.37, with_fluxes=True)
+        # raw Glorot weights: O(1) fluxes; compare per variable against its own amplitude
+        for v in range(3):
+            assert rel_err(F[:, v], g["F_" + name][:, v]) < 2e-5, (name, "flux", v)
+            sl = slice(32 * v, 32 * (v + 1))
+            assert rel_err(k[:, sl], g["k_" + name][:, sl]) < 5e-5, (name, "tendency", v)
+    model.close()
+
+
+@pytest.mark.parametrize("sizes,act", [((96, 50, 20, 31), "mish"), ((96, 400, 31), "swish"), ((96, 31), "identity"),
+                                        ((96, 64, 48, 40, 31), "tanh"), ((96, 400, 400, 31), "leakyrelu")])
+def test_rhs_architectures(opz, oracle, ctx, sizes, act):
+    actc = {"identity": 0, "relu": 1, "tanh": 2, "mish": 3, "swish": 4, "leakyrelu": 5}[act]
+    m = oracle.make_model(sizes, actc, seed=11)
+    p = oracle.Params(flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS)
+    rng = np.random.default_rng(5)
+    B = 37  # ragged: not a multiple of any tile
+    x = rng.normal(size=(B, 96)).astype(np.float32)
+    _, bc = oracle.synthetic_columns(B, p)
+    model = product_model(opz, m)
+    k = opz.rhs(model, product_params(opz, p), x, bc, 0.0)
+    kr = oracle.rhs(x, bc, 0.0, m, p)
+    for v in range(3):
+        sl = slice(32 * v, 32 * (v + 1))
+        assert rel_err(k[:, sl], kr[:, sl]) < 5e-5
+    model.close()
+
+
+def test_mlp_forward_matches_oracle(opz, oracle, ctx):
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=2)
+    model = product_model(opz, m)
+    x = np.random.default_rng(0).normal(size=(130, 96)).astype(np.float32)
+    for net, w in enumerate((m.w_uw, m.w_vw, m.w_wT)):
+        y = opz.mlp_forward(model, net, x)
+        yr = oracle.mlp_forward(x, w, m.sizes, m.act)
+        assert rel_err(y, yr) < 1e-5
+    model.close()
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2])
+def test_short_rollout_all_schemes(opz, oracle, ctx, scheme):
+    p = oracle.Params()
+    B = 9
+    x0, bc = oracle.synthetic_columns(B, p)
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1)
+    model = product_model(opz, m)
+    dt = 30.0 / p.tau
+    out = opz.rollout_forward(model, product_params(opz, p), x0, bc, scheme, dt, 40, 10)
+    ref = oracle.rollout(x0, bc, m, p, scheme, dt, 40, 10)
+    assert out.shape == ref.shape == (B, 5, 96)
+    assert np.array_equal(out[:, 0], x0)  # snapshot 0 is the initial state (saveat=ts)
+    assert oracle.profile_error(out, ref, 32) < 2e-5
+    # final-state-only mode
+    fin = opz.rollout_forward(model, product_params(opz, p), x0, bc, scheme, dt, 40, 0)
+    assert fin.shape == (B, 1, 96)
+    assert np.array_equal(fin[:, 0], out[:, -1])
+    model.close()
+
+
+def test_config1_full_two_day_rollout_fp32(opz, oracle, golden_dir, ctx):
+    """BASELINE configs[0]: construct_NN + mPP + CA, 2 days, RK4 dt=30 s (5760 steps), FP32 path
+    within 1e-4 of the FP32 CPU solve at every saved snapshot."""
+    g = np.load(f"{golden_dir}/config1_rk4_2day.npz")
+    p = oracle.Params()
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=int(g["seed"]), out_scale=float(g["out_scale"]))
+    model = product_model(opz, m)
+    out = opz.rollout_forward(model, product_params(opz, p), g["x0"], g["bc"], opz.SCHEME_RK4, float(g["dt_nd"]),
+                              int(g["n_steps"]), int(g["save_every"]))
+    err = oracle.profile_error(out, g["sol32"], 32)
+    floor = float(g["floor"])
+    print(f"config1 fp32 rollout: err vs fp32 oracle {err:.3e} (fp32-vs-fp64 oracle floor {floor:.3e})")
+    assert np.isfinite(out).all()
+    assert err < TOL_FP32
+    model.close()
+
+
+def test_small_mish_diurnal_heun_golden(opz, oracle, golden_dir, ctx):
+    g = np.load(f"{golden_dir}/small_mish_diurnal_heun.npz")
+    p = oracle.Params(tau=691200.0, flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS | oracle.FLAG_BC_MINUS_SCALE0 | oracle.FLAG_DIURNAL)
+    m = oracle.make_model((96, 50, 20, 31), oracle.ACT_MISH, seed=1, out_scale=0.1)
+    model = product_model(opz, m)
+    out = opz.rollout_forward(model, product_params(opz, p), g["x0"], g["bc"], opz.SCHEME_RK2, float(g["dt_nd"]),
+                              int(g["n_steps"]), int(g["save_every"]))
+    err = oracle.profile_error(out, g["sol32"], 32)
+    print(f"small mish diurnal heun: err {err:.3e}")
+    assert err < TOL_FP32
+    model.close()
+
+
+def test_ensemble_4096_shard_invariance(opz, oracle, ctx):
+    """BASELINE configs[1] size: 4,096 columns.  Columns are independent, so any subset solved alone
+    must reproduce the ensemble BIT-exactly (this is what makes column sharding communication-free),
+    and a sample of columns must match the oracle."""
+    p = oracle.Params()
+    B = 4096
+    x0, bc = oracle.synthetic_columns(B, p)
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    full = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 8, 4)
+    assert np.isfinite(full).all()
+    pick = np.array([0, 1, 31, 32, 63, 64, 1000, 2047, 2048, 4095])
+    sub = opz.rollout_forward(model, pp, x0[pick], bc[pick], opz.SCHEME_RK4, dt, 8, 4)
+    assert np.array_equal(sub, full[pick])
+    lo, hi = 1024, 1024 + 517  # a ragged shard, as a rank of a multi-GPU run would own
+    shard = opz.rollout_forward(model, pp, x0[lo:hi], bc[lo:hi], opz.SCHEME_RK4, dt, 8, 4)
+    assert np.array_equal(shard, full[lo:hi])
+    ref = oracle.rollout(x0[pick], bc[pick], m, p, oracle.SCHEME_RK4, dt, 8, 4)
+    assert oracle.profile_error(full[pick], ref, 32) < 2e-5
+    model.close()
+
+
+def test_edge_cases_and_errors(opz, oracle, ctx):
+    p = oracle.Params()
+    m = oracle.make_model((96, 50, 20, 31), oracle.ACT_MISH, seed=1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    x0, bc = oracle.synthetic_columns(3, p)
+    # empty ensemble
+    out = opz.rollout_forward(model, pp, x0[:0], bc[:0], opz.SCHEME_RK4, 1e-4, 4, 2)
+    assert out.shape == (0, 3, 96)
+    # zero steps returns the initial state
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, 1e-4, 0, 1)
+    assert np.array_equal(out[:, 0], x0)
+    # ts not multiples of dt
+    with pytest.raises(opz.OpzError) as e:
+        opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, 1e-4, 5, 2)
+    assert e.value.code == opz.OPZ_EINVAL
+    # nz mismatch
+    bad = product_params(opz, p)
+    bad.nz = 16
+    with pytest.raises(opz.OpzError):
+        opz.rollout_forward(model, bad, x0, bc, opz.SCHEME_RK4, 1e-4, 4, 2)
+    # unknown scheme
+    with pytest.raises(opz.OpzError):
+        opz.rollout_forward(model, pp, x0, bc, 7, 1e-4, 4, 2)
+    # IEEE hazard of the reference kept: S2 = 0 and dT/dz = 0 with eps = 0 gives NaN
+    xz = np.zeros((1, 96), dtype=np.float32)
+    k = opz.rhs(model, pp, xz, bc[:1], 0.0)
+    kr = oracle.rhs(xz, bc[:1], 0.0, m, p)
+    assert np.array_equal(np.isnan(k), np.isnan(kr))
+    model.close()
+
+
+def test_reference_shaped_api(opz, oracle, ctx):
+    """solve_NDE_mutating / predict_NDE / predict_flux with the reference's argument lists."""
+    from types import SimpleNamespace as NS
+    p = oracle.Params()
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1)
+    from helpers import chains_from_oracle_model
+    uw_NN, vw_NN, wT_NN = chains_from_oracle_model(opz, m)
+    sc = {n: opz.ZeroMeanUnitVarianceScaling(p.mu[i], p.sigma[i]) for i, n in enumerate(("u", "v", "T", "uw", "vw", "wT"))}
+    scalings = NS(**sc)
+    constants = NS(H=p.H, τ=p.tau, f=p.f, Nz=32, g=p.g, α=p.alpha, ν0=p.nu0, ν_m=p.nu_m, Riᶜ=p.Ric, ΔRi=p.dRi, Pr=p.Pr, κ=p.kappa)
+    derivatives = NS(cell=opz.Dᶜ(32, 1 / 32), face=opz.Dᶠ(32, 1 / 32))
+    x0, bc = oracle.synthetic_columns(4, p)
+    BCs = NS(uw=NS(bottom=bc[3, 0], top=bc[3, 1]), vw=NS(bottom=bc[3, 2], top=bc[3, 3]), wT=NS(bottom=bc[3, 4], top=bc[3, 5]))
+    dt = 30.0 / p.tau
+    ts = np.arange(0, 5) * (10 * dt)
+    conditions = NS(convective_adjustment=True)
+    sol = opz.solve_NDE_mutating(uw_NN, vw_NN, wT_NN, scalings, constants, BCs, derivatives, x0[3], ts, opz.RK4(dt), conditions)
+    assert sol.shape == (96, 5)
+    ref = oracle.rollout(x0[3:4], bc[3:4], m, p, oracle.SCHEME_RK4, dt, 40, 10)
+    assert oracle.profile_error(sol.T[None], ref, 32) < 2e-5
+    # training-flavour RHS
+    cond_t = NS(modified_pacanowski_philander=True, convective_adjustment=False, zero_weights=True, smooth_NN=False, smooth_Ri=False)
+    k = opz.predict_NDE(uw_NN, vw_NN, wT_NN, x0[3], BCs, cond_t, scalings, constants, derivatives, None)
+    pt = oracle.Params(flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS | oracle.FLAG_BC_MINUS_SCALE0)
+    kr = oracle.rhs(x0[3:4], bc[3:4], 0.0, m, pt)[0]
+    assert rel_err(k, kr) < 5e-5
+    uw, vw, wT = opz.predict_flux(uw_NN, vw_NN, wT_NN, x0[3], BCs, cond_t, scalings, constants, derivatives, None)
+    assert uw.shape == (33,)
