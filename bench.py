@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — NDE column-timesteps/s of the forward rollout on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[2], the configuration the metric "1/2/4/8 B200" is quoted on):
+an ensemble of 2^20 columns PER GPU (Nz=32; construct_NN 96-400-400-31 relu x3, random init;
+mPP diffusivity + convective adjustment; swept wind stress / buoyancy flux), sharded by column
+with no inter-GPU communication ("scaling": "weak").  One bench "step" advances every column by a
+window of W_t fixed-dt RK4 timesteps of the 8-day rollout (dt = 30 s), state resident on chip
+within the window and in HBM between windows; successive steps continue the same rollout.
+
+  value  : column-timesteps/s with inputs resident in HBM (device pointers, CUDA events on the
+           launching stream, max over ranks).
+  e2e    : the same window through the host-buffer C ABI call opz_rollout_forward (pinned host
+           memory, H2D of profiles+forcing and D2H of the new profiles inside the timed region).
+  roofline : the dominant (only) kernel is the rollout kernel; bound = tensor pipe for the
+           batched MLP; achieved = algorithmic FLOPs per launch / measured launch time.
+  cpu_baseline : oracle/nde_oracle.c (a C port of the reference's per-column solve; Julia is not
+           installed) on the host cores, bounded sample of the same workload.
+
+`--impl reference` times that CPU port with all host threads on the same config instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SIZES = (96, 400, 400, 31)
+FLOP_PER_RHS = 2 * 3 * sum(SIZES[i] * SIZES[i + 1] for i in range(len(SIZES) - 1)) + 1800
+STAGES = 4
+DT_SECONDS = 30.0
+TAU = 691200.0  # 8-day suite
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(columns, seed=0):
+    from oracle import nde_oracle as O  # synthetic-input generator only (bench harness, not product path)
+    p = O.Params(tau=TAU)
+    m = O.make_model(SIZES, O.ACT_RELU, seed=seed, out_scale=0.1)
+    # the forcing sweep repeats every 4096 columns (64 x 64 grid of (Q_u, Q_b), configs[1])
+    x0s, bcs = O.synthetic_columns(4096, p)
+    reps = (columns + 4095) // 4096
+    x0 = np.tile(x0s, (reps, 1))[:columns]
+    bc = np.tile(bcs, (reps, 1))[:columns]
+    return O, p, m, x0, bc
+
+
+def run_reference(args):
+    """CPU arm: the C port of the reference's per-column solve on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle as CO
+    cores = CO.max_threads()
+    cols = args.ref_columns or 64 * cores
+    O, p, m, x0, bc = workload(cols)
+    dt = DT_SECONDS / p.tau
+    x = x0
+    CO.rollout(x[:cores], bc[:cores], m, p, 2, dt, 1, 0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        out = CO.rollout(x, bc, m, p, 2, dt, args.window, 0, t0=i * args.window * dt)
+        el = time.perf_counter() - t
+        x = out[:, 0]
+        if i >= args.warmup:
+            times.append(el)
+    tot = sum(times)
+    value = cols * args.window * args.steps / tot
+    sample = f"{cols} columns x {args.window} RK4 steps per bench step (C port of solve_NDE_mutating, one column per thread)"
+    line = {
+        "impl": "reference", "metric": "NDE column-timesteps/sec at Nz=32", "value": value, "unit": "column-timesteps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, cols),
+        "cpu_baseline": {"value": value, "unit": "column-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, columns_per_gpu):
+    return {
+        "workload": "BASELINE configs[2]: ensemble of 2^20 columns per GPU sharded by column, 8-day rollout "
+                    "(tau=691200 s), construct_NN 96-400-400-31 relu x3 random init (last layer x0.1), mPP + convective "
+                    "adjustment (kappa=1), RK4 dt=30 s; one step = a window of RK4 timesteps of that rollout",
+        "columns_per_gpu": columns_per_gpu, "nz": 32, "scheme": "RK4", "dt_seconds": DT_SECONDS,
+        "window_timesteps": args.window, "precision": args.precision,
+        "l2_policy": "inputs larger than L2 (profiles alone are 384 B x columns)",
+        "parallelism": f"columns sharded over {args.gpus} GPU(s), no communication",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--columns", type=int, default=1 << 20, help="columns per GPU")
+    ap.add_argument("--window", type=int, default=0, help="RK4 timesteps per bench step (0 = per-precision default)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "bf16x2", "bf16x3"])
+    ap.add_argument("--ref-columns", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        if args.window == 0:
+            args.window = 64
+        run_reference(args)
+        return
+
+    import torch
+    import opz_import
+    from helpers import product_model, product_params
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    opz = opz_import.load()
+    ctx = opz.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    prec_name = args.precision
+    if prec_name == "auto":
+        prec_name = os.environ.get("OPZ_BENCH_PRECISION", "fp32")
+    prec = {"fp32": opz.PREC_FP32, "bf16": opz.PREC_BF16, "bf16x2": opz.PREC_BF16X2, "bf16x3": opz.PREC_BF16X3}[prec_name]
+    args.precision = prec_name
+    if args.window == 0:
+        args.window = 1 if prec_name == "fp32" else 16
+    cols = args.columns
+    O, p, m, x0, bc = workload(cols, seed=0)
+    model = product_model(opz, m, ctx=ctx)
+    pp = product_params(opz, p)
+    dt = DT_SECONDS / p.tau
+
+    xa = torch.from_numpy(x0).cuda()
+    xb = torch.empty_like(xa)
+    bcd = torch.from_numpy(bc).cuda()
+
+    def window(i, src, dst):
+        opz.rollout_forward_dev(model, pp, src.data_ptr(), bcd.data_ptr(), cols, opz.SCHEME_RK4, dt, args.window, 0,
+                                dst.data_ptr(), t0=i * args.window * dt, precision=prec)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    bufs = [xa, xb]
+    for i in range(args.warmup):
+        window(i, bufs[i & 1], bufs[(i + 1) & 1])
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    n0 = ctx.launch_count
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
+        i = args.warmup + k
+        window(i, bufs[i & 1], bufs[(i + 1) & 1])
+        evs[k + 1].record(stream)
+    barrier()
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    final = bufs[(args.warmup + args.steps) & 1]
+    finite = bool(torch.isfinite(final).all().item())
+
+    # ---- end-to-end through the host-buffer C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.from_numpy(x0).pin_memory()
+        hb = torch.from_numpy(bc).pin_memory()
+        ho = torch.empty((cols, 1, 96), dtype=torch.float32).pin_memory()
+        import ctypes as C
+
+        def e2e_step(i):
+            opz.check(opz.lib.opz_rollout_forward(ctx._h, model._h, C.byref(pp), C.c_void_p(hx.data_ptr()),
+                                                  C.c_void_p(hb.data_ptr()), cols, opz.SCHEME_RK4, dt, i * args.window * dt,
+                                                  args.window, 0, prec, C.c_void_p(ho.data_ptr())))
+            hx.copy_(ho.view(cols, 96))  # the caller's next window starts from the returned profiles (host side)
+
+        e2e_step(0)
+        barrier()
+        t = time.perf_counter()
+        e_steps = max(2, min(args.steps, 5))
+        for k in range(e_steps):
+            e2e_step(1 + k)
+        barrier()
+        e2e_ms = (time.perf_counter() - t) * 1e3 / e_steps
+        e2e = {"ms": e2e_ms, "h2d": int(x0.nbytes + bc.nbytes), "d2h": int(x0.nbytes)}
+
+    # ---- max over ranks ----
+    t_ms = total_ms
+    e_ms = e2e["ms"] if e2e else 0.0
+    if dist is not None:
+        tt = torch.tensor([t_ms, e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms, e_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    colsteps_per_step = cols * args.window * world
+    value = colsteps_per_step * args.steps / (t_ms * 1e-3)
+    flop_per_launch = cols * args.window * STAGES * FLOP_PER_RHS
+    avg_kernel_ms = float(np.mean(kernel_ms))
+    achieved = flop_per_launch / (avg_kernel_ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    line = {
+        "metric": "NDE column-timesteps/sec at Nz=32", "value": value, "unit": "column-timesteps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x2": "bf16", "bf16x3": "bf16"}[prec_name], "data": "synthetic",
+        "config": config_dict(args, cols),
+        "clocks": clocks, "gpu_launches": int(launches), "finite": finite,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "kernel": "rollout kernel (" + prec_name + ")", "flop_per_launch": flop_per_launch,
+                     "fp32_fma_peak_tflops_at_max_clock": 74.4},
+    }
+    if e2e:
+        line["e2e"] = {"value": colsteps_per_step / (e_ms * 1e-3), "unit": "column-timesteps/s",
+                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e_ms}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle as CO
+        cores = CO.max_threads()
+        cb_cols = 64 * cores
+        t = time.perf_counter()
+        CO.rollout(x0[:cb_cols], bc[:cb_cols], m, p, 2, dt, 4, 0)  # pilot: sizes the sample to ~12 s
+        pilot = time.perf_counter() - t
+        cb_steps = int(min(1024, max(8, 4 * 12.0 / max(pilot, 1e-3))))
+        t = time.perf_counter()
+        CO.rollout(x0[:cb_cols], bc[:cb_cols], m, p, 2, dt, cb_steps, 0)
+        el = time.perf_counter() - t
+        line["cpu_baseline"] = {"value": cb_cols * cb_steps / el, "unit": "column-timesteps/s", "cores": cores, "kind": "port",
+                                "sample": f"first {cb_cols} columns x {cb_steps} RK4 steps, oracle/nde_oracle.c (C port; Julia absent), "
+                                          f"{el:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import unicodedata
 from types import SimpleNamespace
 from typing import Callable, Optional, Sequence
 
@@ -248,7 +249,8 @@ _SCALING_ORDER = ("u", "v", "T", "uw", "vw", "wT")
 
 
 def make_params(constants, scalings, flags: int, eps: float = 1e-7, diurnal_period: float = 86400.0) -> L.OpzParams:
-    g = lambda k, d=0.0: float(getattr(constants, k, d))
+    # Python NFKC-normalises identifiers (Riᶜ -> Ric), so attribute names are looked up normalised
+    g = lambda k, d=0.0: float(getattr(constants, unicodedata.normalize("NFKC", k), d))
     p = L.OpzParams()
     p.nz = int(constants.Nz)
     p.H, p.tau, p.f, p.g, p.alpha = g("H"), g("τ"), g("f"), g("g"), g("α")
@@ -316,9 +318,9 @@ def prepare_parameters_NDE_training(𝒟train, uw_NN, vw_NN, wT_NN, f, Nz, g, α
     n1, n2, n3 = len(uw_w), len(vw_w), len(wT_w)
     constants = SimpleNamespace(H=H, τ=τ, f=f, Nz=Nz, g=g, α=α)
     if _cond(conditions, "modified_pacanowski_philander"):
-        constants.__dict__.update({"ν0": ν0, "ν_m": ν_m, "Riᶜ": Riᶜ, "ΔRi": ΔRi, "Pr": Pr})
+        constants.ν0, constants.ν_m, constants.Riᶜ, constants.ΔRi, constants.Pr = ν0, ν_m, Riᶜ, ΔRi, Pr
     if _cond(conditions, "convective_adjustment"):
-        constants.__dict__.update({"κ": κ})
+        constants.κ = κ
     scalings = SimpleNamespace(**{n: sc[n] for n in _SCALING_ORDER})
     derivatives = SimpleNamespace(cell=Dᶜ(Nz, 1 / Nz).astype(np.float32), face=Dᶠ(Nz, 1 / Nz).astype(np.float32))
     NN_constructions = SimpleNamespace(uw=re_uw, vw=re_vw, wT=re_wT)
