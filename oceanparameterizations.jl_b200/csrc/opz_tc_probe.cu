@@ -1,0 +1,141 @@
+// opz_tc_probe.cu — one-tile tcgen05 GEMM used by the tests to pin the descriptor / TMEM layout
+// conventions the fused rollout kernel relies on:  D[128 x N] = A[128 x K] * B[N x K]^T with BF16
+// operands, FP32 accumulation in tensor memory.
+//   mode 0: A and B from shared memory (K-major, no swizzle, bulk-async-copied images)
+//   mode 1: A from tensor memory (written with tcgen05.st as packed BF16 pairs), B from shared memory
+// Exported as opz_debug_umma (a debug entry point, not part of include/opz.h).
+#include <cuda_bf16.h>
+#include <vector>
+#include "opz_internal.h"
+#include "opz_ptx.cuh"
+
+namespace opz {
+
+struct ProbeArgs {
+  const uint8_t* a_img;   // [K/8][128][8] bf16
+  const uint8_t* b_img;   // [K/8][N][8] bf16
+  const uint16_t* a_rows; // [128][K] bf16 row-major (mode 1)
+  float* d;               // [128][N]
+  int N, K, mode;
+};
+
+__global__ void __launch_bounds__(192, 1) umma_probe_kernel(const __grid_constant__ ProbeArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t bytesA = 128u * a.K * 2u, bytesB = (uint32_t)a.N * a.K * 2u;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + bytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bytesA + bytesB);
+  uint64_t* bar_full = bars + 0;
+  uint64_t* bar_done = bars + 1;
+  uint64_t* bar_aready = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_init(bar_full, 1);
+      ptx::mbar_init(bar_done, 1);
+      ptx::mbar_init(bar_aready, 128);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_a = tmem + 256;  // columns [256, 256 + K/2) hold A in mode 1
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(bar_full, bytesA + bytesB);
+      ptx::bulk_g2s(sA, a.a_img, bytesA, bar_full);
+      ptx::bulk_g2s(sB, a.b_img, bytesB, bar_full);
+    }
+  } else if (warp == 1) {
+    ptx::mbar_wait(bar_full, 0);
+    if (a.mode == 1) ptx::mbar_wait(bar_aready, 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::idesc_bf16(128, a.N);
+      const uint32_t lboA = 128 * 16, lboB = (uint32_t)a.N * 16;
+      for (int ks = 0; ks < a.K / 16; ++ks) {
+        const uint64_t bd = ptx::smem_desc(ptx::smem_u32(sB) + ks * 2 * lboB, lboB, 128);
+        if (a.mode == 0) {
+          const uint64_t ad = ptx::smem_desc(ptx::smem_u32(sA) + ks * 2 * lboA, lboA, 128);
+          ptx::mma_ss(tmem, ad, bd, idesc, ks > 0);
+        } else {
+          ptx::mma_ts(tmem, tmem_a + ks * 8, bd, idesc, ks > 0);
+        }
+      }
+      ptx::tc_commit(bar_done);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp % 4;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    if (a.mode == 1) {
+      for (int c = 0; c < a.K / 2; c += 8) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t lo = a.a_rows[(size_t)row * a.K + 2 * (c + j)];
+          const uint32_t hi = a.a_rows[(size_t)row * a.K + 2 * (c + j) + 1];
+          r[j] = lo | (hi << 16);
+        }
+        ptx::tmem_st8(tmem_a + lane_addr + c, r);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_aready);
+    }
+    ptx::mbar_wait(bar_done, 0);
+    ptx::tc_fence_after();
+    for (int c = 0; c < a.N; c += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld16(tmem + lane_addr + c, r);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a.d[(size_t)row * a.N + c + j] = __uint_as_float(r[j]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace opz
+
+using namespace opz;
+
+// A: [128][K] bf16 bits row-major, B: [N][K] bf16 bits, D: [128][N] float.  HOST pointers.
+extern "C" int opz_debug_umma(int N, int K, int mode, const uint16_t* A, const uint16_t* B, float* D) {
+  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 512) { set_error("probe: bad N/K"); return OPZ_EINVAL; }
+  std::vector<uint16_t> ai((size_t)128 * K), bi((size_t)N * K);
+  for (int k = 0; k < K; ++k)
+    for (int r = 0; r < 128; ++r) ai[((size_t)(k / 8) * 128 + r) * 8 + (k % 8)] = A[(size_t)r * K + k];
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) bi[((size_t)(k / 8) * N + n) * 8 + (k % 8)] = B[(size_t)n * K + k];
+  uint8_t *da, *db;
+  uint16_t* dar;
+  float* dd;
+  OPZ_CUDA(cudaMalloc(&da, ai.size() * 2));
+  OPZ_CUDA(cudaMalloc(&db, bi.size() * 2));
+  OPZ_CUDA(cudaMalloc(&dar, ai.size() * 2));
+  OPZ_CUDA(cudaMalloc(&dd, sizeof(float) * 128 * N));
+  OPZ_CUDA(cudaMemcpy(da, ai.data(), ai.size() * 2, cudaMemcpyHostToDevice));
+  OPZ_CUDA(cudaMemcpy(db, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice));
+  OPZ_CUDA(cudaMemcpy(dar, A, ai.size() * 2, cudaMemcpyHostToDevice));
+  OPZ_CUDA(cudaMemset(dd, 0, sizeof(float) * 128 * N));
+  ProbeArgs pa{da, db, dar, dd, N, K, mode};
+  const size_t smem = (size_t)128 * K * 2 + (size_t)N * K * 2 + 64;
+  OPZ_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<<<1, 192, smem>>>(pa);
+  OPZ_CUDA(cudaGetLastError());
+  OPZ_CUDA(cudaDeviceSynchronize());
+  OPZ_CUDA(cudaMemcpy(D, dd, sizeof(float) * 128 * N, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dar); cudaFree(dd);
+  return OPZ_OK;
+}
