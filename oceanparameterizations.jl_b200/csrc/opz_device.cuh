@@ -145,13 +145,15 @@ __device__ __forceinline__ float wT_top_value(const DevParams& P, const float* b
 // X(i): scaled state, i in [0,3Nz) = [u; v; T], cell 0 at the bottom.
 // Y(net, j): NN output of net (0 uw, 1 vw, 2 wT) for interior face j+1, j in [0, Nz-1).
 // K(i, value): receives d x_i / d(t/tau).   FL(v, f, value): optional total flux on face f.
-template <class XF, class YF, class KF, class FLF>
+// NZ_CT > 0 fixes Nz at compile time so that the face loop unrolls and X/Y may live in registers.
+// SMOOTH = false compiles the two box-filter branches out (the tensor-core kernel rejects those flags).
+template <int NZ_CT = 0, bool SMOOTH = true, class XF, class YF, class KF, class FLF>
 __device__ __forceinline__ void column_rhs(const DevParams& P, const float* bc, float t, XF X, YF Y,
                                            KF K, FLF FL) {
-  const int Nz = P.nz;
+  const int Nz = NZ_CT > 0 ? NZ_CT : P.nz;
   const bool mpp = P.flags & OPZ_FLAG_MPP;
-  const bool smooth_nn = P.flags & OPZ_FLAG_SMOOTH_NN;
-  const bool smooth_ri = P.flags & OPZ_FLAG_SMOOTH_RI;
+  const bool smooth_nn = SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_NN);
+  const bool smooth_ri = SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_RI);
 
   // bottom boundary fluxes
   float Fp_u = bc[0] - P.off[0];
@@ -169,7 +171,8 @@ __device__ __forceinline__ void column_rhs(const DevParams& P, const float* bc, 
     Ri_m = richardson(P, 0.f, 0.f, 0.f);  // boundary face 0: zero gradients (D^f first row)
     Ri_c = richardson(P, (X(1) - u_lo) * P.nzf, (X(Nz + 1) - v_lo) * P.nzf, (X(2 * Nz + 1) - T_lo) * P.nzf);
   }
-  for (int f = 1; f <= Nz; ++f) {
+#pragma unroll
+  for (int f = 1; f <= (NZ_CT > 0 ? NZ_CT : Nz); ++f) {
     float F_u, F_v, F_T;
     float u_hi = 0.f, v_hi = 0.f, T_hi = 0.f;
     if (f < Nz) {
