@@ -61,6 +61,8 @@ extern "C" {
 #define OPZ_PREC_BF16 1   /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM */
 #define OPZ_PREC_BF16X2 2 /* as BF16 with weights split hi+lo (2 MMAs): ~TF32-grade */
 #define OPZ_PREC_BF16X3 3 /* activations and weights split hi+lo (3 MMAs): ~FP32-grade */
+#define OPZ_PREC_FP16 4   /* tcgen05 kind::f16, IEEE-half operands (saturating), FP32 accumulate in TMEM:
+                             same speed as BF16, 8x finer operand rounding; the default reduced-precision path */
 
 #define OPZ_BC_STRIDE 8 /* floats per column in `bc` */
 

@@ -246,8 +246,18 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
   c.x0 = x0; c.bc = bc; c.out = out; c.B = B; c.scheme = scheme; c.dt = dt_nd; c.t0 = t0;
   c.n_steps = n_steps; c.save_every = save_every; c.n_save = n_save_of(n_steps, save_every);
   if (precision == OPZ_PREC_FP32) return fp32_rollout(ctx, m, c);
-  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
-    if (!m->tc_pack_valid && (rc = tc_model_prepare(const_cast<opz_model*>(m)))) return rc;
+  if (precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
+    set_error("the split-operand tensor-core modes are not built; use OPZ_PREC_FP16, OPZ_PREC_BF16 or OPZ_PREC_FP32");
+    return OPZ_EUNSUP;
+  }
+  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16) {
+    if (c.P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {
+      set_error("tensor-core path: smooth_NN / smooth_Ri are only available with OPZ_PREC_FP32");
+      return OPZ_EUNSUP;
+    }
+    opz_model* mm = const_cast<opz_model*>(m);  // the packed weight tape is a cache
+    if ((!m->tc_pack_valid || m->tc_pack_precision != precision) && (rc = tc_model_prepare(mm, precision))) return rc;
+    mm->tc_pack_precision = precision;
     return tc_rollout(ctx, m, c, precision);
   }
   set_error("unknown precision");

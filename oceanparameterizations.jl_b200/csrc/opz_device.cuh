@@ -37,6 +37,7 @@ struct DevParams {
   float alpha_g;        // alpha*g
   float mu_wT, s_wT;
   float diurnal_off;    // scale_wT(0) if OPZ_FLAG_DIURNAL_MINUS_SCALE0 else 0
+  float two_inv_dRi, inv_Pr;  // fast-math physics of the tensor-core path
 };
 
 inline DevParams make_dev_params(const opz_params& p) {
@@ -69,6 +70,8 @@ inline DevParams make_dev_params(const opz_params& p) {
   d.mu_wT = p.mu[5];
   d.s_wT = p.sigma[5];
   d.diurnal_off = (p.flags & OPZ_FLAG_DIURNAL_MINUS_SCALE0) ? ((-p.mu[5]) / p.sigma[5]) : 0.0f;
+  d.two_inv_dRi = 2.0f / p.dRi;
+  d.inv_Pr = 1.0f / p.Pr;
   return d;
 }
 
@@ -81,6 +84,20 @@ __device__ __forceinline__ float act_fn(float z) {
     const float sp = fmaxf(z, 0.0f) + log1pf(expf(-fabsf(z)));
     return z * tanhf(sp);
   } else if constexpr (ACT == OPZ_ACT_SWISH) return z / (1.0f + expf(-z));
+  else if constexpr (ACT == OPZ_ACT_LEAKYRELU) return fmaxf(0.01f * z, z);
+  else return z;
+}
+// Fast variants for the reduced-precision tensor-core path (results feed a 16-bit operand):
+// one MUFU.EX2 + one MUFU.RCP each, ~1e-6 relative.
+template <int ACT>
+__device__ __forceinline__ float act_fast(float z) {
+  if constexpr (ACT == OPZ_ACT_RELU) return fmaxf(z, 0.0f);
+  else if constexpr (ACT == OPZ_ACT_TANH) return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
+  else if constexpr (ACT == OPZ_ACT_MISH) {  // tanh(log(1+n)) = w/(w+2), w = n(n+2), n = e^z
+    const float n = __expf(fminf(z, 20.0f));
+    const float w = n * (n + 2.0f);
+    return z > 20.0f ? z : z * __fdividef(w, w + 2.0f);
+  } else if constexpr (ACT == OPZ_ACT_SWISH) return __fdividef(z, 1.0f + __expf(-z));
   else if constexpr (ACT == OPZ_ACT_LEAKYRELU) return fmaxf(0.01f * z, z);
   else return z;
 }
@@ -115,22 +132,31 @@ __device__ __forceinline__ float act_grad_dyn(float z, int act) {
 struct FaceDiff {
   float nu, nuT;
 };
+// FAST = true (tensor-core path only): approximate division / exponential; S2 = 0 still gives
+// +-Inf / NaN, and (1 - tanh z)/2 is evaluated as 1/(1 + e^{2z}), which keeps RELATIVE accuracy
+// in the stable tail where nu -> nu0.
+template <bool FAST = false>
 __device__ __forceinline__ float richardson(const DevParams& P, float gu, float gv, float gT) {
   const float Bz = P.cBz * (gT + P.eps);
   const float a = P.s_u * (gu + P.eps);
   const float b = P.s_v * (gv + P.eps);
   const float S2 = a * a + b * b;
-  return Bz / S2;  // IEEE division: S2 = 0 gives +-Inf / NaN exactly like the reference
+  if constexpr (FAST) return __fdividef(Bz, S2);
+  else return Bz / S2;  // IEEE division: S2 = 0 gives +-Inf / NaN exactly like the reference
 }
+template <bool FAST = false>
 __device__ __forceinline__ float nu_of_ri(const DevParams& P, float Ri) {
-  return P.nu0 + P.nu_m * ((1.0f - tanhf((Ri - P.Ric) / P.dRi)) / 2.0f);
+  if constexpr (FAST) return P.nu0 + __fdividef(P.nu_m, 1.0f + __expf((Ri - P.Ric) * P.two_inv_dRi));
+  else return P.nu0 + P.nu_m * ((1.0f - tanhf((Ri - P.Ric) / P.dRi)) / 2.0f);
 }
+template <bool FAST = false>
 __device__ __forceinline__ float nuT_of(const DevParams& P, float nu, float gu, float gT) {
+  const float nuT = FAST ? nu * P.inv_Pr : nu / P.Pr;
   if (P.flags & OPZ_FLAG_CA) {
     const float sel = (P.flags & OPZ_FLAG_CA_SELECT_DUDZ) ? gu : gT;
-    return sel > 0.0f ? nu / P.Pr : P.kappa;
+    return sel > 0.0f ? nuT : P.kappa;
   }
-  return nu / P.Pr;
+  return nuT;
 }
 
 __device__ __forceinline__ float wT_top_value(const DevParams& P, const float* bc, float t) {
@@ -147,7 +173,8 @@ __device__ __forceinline__ float wT_top_value(const DevParams& P, const float* b
 // K(i, value): receives d x_i / d(t/tau).   FL(v, f, value): optional total flux on face f.
 // NZ_CT > 0 fixes Nz at compile time so that the face loop unrolls and X/Y may live in registers.
 // SMOOTH = false compiles the two box-filter branches out (the tensor-core kernel rejects those flags).
-template <int NZ_CT = 0, bool SMOOTH = true, class XF, class YF, class KF, class FLF>
+// FAST = true selects the approximate division / exponential (tensor-core path).
+template <int NZ_CT = 0, bool SMOOTH = true, bool FAST = false, class XF, class YF, class KF, class FLF>
 __device__ __forceinline__ void column_rhs(const DevParams& P, const float* bc, float t, XF X, YF Y,
                                            KF K, FLF FL) {
   const int Nz = NZ_CT > 0 ? NZ_CT : P.nz;
@@ -203,10 +230,10 @@ __device__ __forceinline__ void column_rhs(const DevParams& P, const float* bc, 
           Ri = (Ri_m + Ri_c + Ri_p) * (1.0f / 3.0f);
           Ri_m = Ri_c; Ri_c = Ri_p;
         } else {
-          Ri = richardson(P, gu, gv, gT);
+          Ri = richardson<FAST>(P, gu, gv, gT);
         }
-        const float nu = nu_of_ri(P, Ri);
-        const float nuT = nuT_of(P, nu, gu, gT);
+        const float nu = nu_of_ri<FAST>(P, Ri);
+        const float nuT = nuT_of<FAST>(P, nu, gu, gT);
         F_u -= P.c_u * nu * gu;
         F_v -= P.c_v * nu * gv;
         F_T -= P.c_T * nuT * gT;

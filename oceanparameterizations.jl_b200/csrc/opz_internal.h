@@ -27,6 +27,7 @@ struct opz_model {
   void* tc_pack = nullptr;
   size_t tc_pack_bytes = 0;
   bool tc_pack_valid = false;
+  int tc_pack_precision = -1;    // OPZ_PREC_* the tape was packed for
   void* tc_plan = nullptr;       // opaque (opz_tc.cu)
 };
 
@@ -71,7 +72,7 @@ struct LossGradCall {
 int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c);
 
 // tcgen05 tensor-core path (opz_tc.cu)
-int tc_model_prepare(opz_model* m);          // (re)pack weights after set_weights
+int tc_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights
 void tc_model_release(opz_model* m);
 int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
 

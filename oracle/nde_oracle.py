@@ -223,6 +223,12 @@ def quant_bf16(a: np.ndarray) -> np.ndarray:
     return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
 
 
+def quant_fp16(a: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even float32 -> IEEE half (saturating at +-65504) -> float32."""
+    a = np.clip(np.ascontiguousarray(a, dtype=np.float32), -65504.0, 65504.0)
+    return a.astype(np.float16).astype(np.float32)
+
+
 def quant_tf32(a: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.float32)
     u = a.view(np.uint32)

