@@ -13,7 +13,9 @@ within the window and in HBM between windows; successive steps continue the same
   e2e    : the same window through the host-buffer C ABI call opz_rollout_forward (pinned host
            memory, H2D of profiles+forcing and D2H of the new profiles inside the timed region).
   roofline : the dominant (only) kernel is the rollout kernel; bound = tensor pipe for the
-           batched MLP; achieved = algorithmic FLOPs per launch / measured launch time.
+           batched MLP (default precision fp16 = tcgen05 kind::f16 with IEEE-half operands and FP32
+           accumulation; --precision fp32 times the CUDA-core parity path instead);
+           achieved = algorithmic FLOPs per launch / measured launch time.
   cpu_baseline : oracle/nde_oracle.c (a C port of the reference's per-column solve; Julia is not
            installed) on the host cores, bounded sample of the same workload.
 
@@ -159,7 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--columns", type=int, default=1 << 20, help="columns per GPU")
     ap.add_argument("--window", type=int, default=0, help="RK4 timesteps per bench step (0 = per-precision default)")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "bf16x2", "bf16x3"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "bf16"])
     ap.add_argument("--ref-columns", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -192,8 +194,8 @@ def main():
 
     prec_name = args.precision
     if prec_name == "auto":
-        prec_name = os.environ.get("OPZ_BENCH_PRECISION", "fp32")
-    prec = {"fp32": opz.PREC_FP32, "bf16": opz.PREC_BF16, "bf16x2": opz.PREC_BF16X2, "bf16x3": opz.PREC_BF16X3}[prec_name]
+        prec_name = os.environ.get("OPZ_BENCH_PRECISION", "fp16")
+    prec = {"fp32": opz.PREC_FP32, "bf16": opz.PREC_BF16, "fp16": opz.PREC_FP16}[prec_name]
     args.precision = prec_name
     if args.window == 0:
         args.window = 1 if prec_name == "fp32" else 16
@@ -285,12 +287,13 @@ def main():
         "metric": "NDE column-timesteps/sec at Nz=32", "value": value, "unit": "column-timesteps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x2": "bf16", "bf16x3": "bf16"}[prec_name], "data": "synthetic",
+        "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[prec_name], "data": "synthetic",
         "config": config_dict(args, cols),
         "clocks": clocks, "gpu_launches": int(launches), "finite": finite,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "kernel": "rollout kernel (" + prec_name + ")", "flop_per_launch": flop_per_launch,
+                     "kernel": ("rollout_fp32_kernel" if prec_name == "fp32" else "rollout_tc_kernel (tcgen05, " + prec_name + " operands, fp32 accumulate)"),
+                     "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_kernel_ms,
                      "fp32_fma_peak_tflops_at_max_clock": 74.4},
     }
     if e2e:

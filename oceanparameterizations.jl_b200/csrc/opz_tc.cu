@@ -97,6 +97,7 @@ struct Plan {                     // host-side, cached on the model
   Op ops[kMaxOps];
   int L = 0;                      // Dense layers (2 or 3)
   int hpad[2] = {0, 0};           // padded hidden widths
+  int ks_full[2] = {1, 1}, ks_tail[2] = {1, 1};  // k-steps per stage (64-row chunks / tail chunk)
   int act = 0;
   bool fp16 = false;              // operand format of the tape (IEEE half instead of bfloat16)
   int bias_per_net = 0;           // floats
@@ -120,6 +121,7 @@ struct Args {
   int n_steps, save_every, n_save;
   int n_ops, L, act, bias_per_net;
   int hpad[2];
+  int ks_full[2], ks_tail[2];   // k-steps per weight stage for 64-row / tail chunks of hidden layer j
   uint32_t tape_bytes;
   uint32_t tape_stride;
   int n_copies;
@@ -213,51 +215,81 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // The whole warp walks the op table with warp-uniform values (so descriptors and addresses stay
-    // in uniform registers); one lane issues the tcgen05.mma / tcgen05.commit instructions.
+    // The whole warp walks the schedule with warp-uniform loop counters (the same nested loops that
+    // build_plan() used to lay out the tape), so descriptors and addresses live in uniform registers;
+    // one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
     if (n_rhs > 0) {
       // released state for the barriers this warp waits on as "empty": D-drained
       uint32_t mask = (1u << (B_DEMPTY + 0)) | (1u << (B_DEMPTY + 1));
-      int slot = 0;
-      uint32_t g = 0, buf = 0;
-      int h1_waited = 0;
+      uint32_t slot = 0, g = 0;
       const uint32_t ring_u32 = ptx::smem_u32(s_ring);
+      const uint32_t idesc0 = ptx::idesc_f16kind(kM, 0, FP16);
+      const int L = a.L;
+      // one weight stage: wait for its bytes, issue ks MMAs D (+)= A[k] * B[k]^T, release the slot
+      auto stage = [&](uint32_t d, uint32_t a_col, uint32_t rows, int ks, bool acc_first) {
+        bar_wait(bars, B_FULL + slot, mask);
+        ptx::tc_fence_after();
+        const uint64_t bd0 = ptx::smem_desc(ring_u32 + slot * kSlotBytes, rows * 16u, 128);
+        const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kMaxKsteps; ++k)
+            if (k < ks) ptx::mma_ts(tmem + d, tmem + a_col + (uint32_t)k * 8u, bd0 + (uint64_t)((uint32_t)k * 2u * rows), idesc, acc_first || k > 0);
+          ptx::tc_commit(bars + B_EMPTY + slot);
+        }
+        __syncwarp();
+        slot = slot + 1 == kSlots ? 0 : slot + 1;
+      };
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int r = 0; r < n_rhs; ++r) {
-#pragma unroll 1
-          for (int i = 0; i < a.n_ops; ++i) {
-            const Op op = a.ops[i];
-            if (op.flags & F_WAIT_X) bar_wait(bars, B_XFULL, mask);
-            if (op.flags & F_NEW_CHUNK) {
-              buf = g & 1u;
-              ++g;
-              bar_wait(bars, B_DEMPTY + buf, mask);
-            }
-            if (op.flags & F_H1_RESET) h1_waited = 0;
-            while (h1_waited < op.h1_need) { bar_wait(bars, B_H1 + h1_waited, mask); ++h1_waited; }
-            if (op.flags & F_WAIT_H2) bar_wait(bars, B_H2FULL, mask);
-            bar_wait(bars, B_FULL + slot, mask);
-            ptx::tc_fence_after();
-            const uint32_t d = tmem + ((op.flags & F_D_IS_Y) ? (uint32_t)op.d_col : kColD0 + buf * kCW);
-            const uint32_t idesc = ptx::idesc_f16kind(kM, op.n, FP16);
-            const uint32_t lbo = (uint32_t)op.n * 16u;
-            const uint64_t bd0 = ptx::smem_desc(ring_u32 + (uint32_t)slot * kSlotBytes, lbo, 128);
-            const uint32_t a0 = tmem + op.a_col;
-            const uint32_t kstride = 2u * op.n;  // descriptor start-address units (16 B) per k-step
-            const bool acc0 = op.flags & F_ACC;
+          bool have_pend = false;
+          uint32_t pend_net = 0, pend_c = 0, pend_rows = 0;
+          // output-layer MMAs for one H2c chunk: Y_net (+)= H2c * W_out[:, chunk]^T
+          auto out_op = [&](bool final_op) {
+            bar_wait(bars, B_H2FULL, mask);
+            stage(kColY + 32u * pend_net, kColH2, 32u, (int)(pend_rows >> 4), pend_c > 0);
             if (ptx::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < kMaxKsteps; ++k)
-                if (k < op.ksteps) ptx::mma_ts(d, a0 + (uint32_t)k * 8u, bd0 + (uint64_t)(k * kstride), idesc, acc0 || k > 0);
-              ptx::tc_commit(bars + B_EMPTY + slot);
-              if (op.flags & F_COMMIT_D) ptx::tc_commit(bars + B_DFULL + buf);
-              if (op.flags & F_COMMIT_H2E) ptx::tc_commit(bars + B_H2EMPTY);
-              if (op.flags & F_COMMIT_Y) ptx::tc_commit(bars + B_YFULL);
+              ptx::tc_commit(bars + B_H2EMPTY);
+              if (final_op) ptx::tc_commit(bars + B_YFULL);
             }
             __syncwarp();
-            slot = slot + 1 == kSlots ? 0 : slot + 1;
+          };
+          bar_wait(bars, B_XFULL, mask);
+#pragma unroll 1
+          for (int net = 0; net < 3; ++net) {
+#pragma unroll 1
+            for (int j = 0; j < L - 1; ++j) {
+              const bool fused = (j == L - 2);
+              const int kin = (j == 0) ? kS / 16 : a.hpad[j - 1] / 16;
+              const int hp = a.hpad[j];
+              const uint32_t a_base = (j == 0) ? kColX : kColHF;
+              int h1_waited = 0;
+#pragma unroll 1
+              for (int c0 = 0; c0 < hp; c0 += kCW) {
+                const uint32_t rows = (uint32_t)min(kCW, hp - c0);
+                const int ks_per = (rows == (uint32_t)kCW) ? a.ks_full[j] : a.ks_tail[j];
+                const uint32_t buf = g & 1u;
+                ++g;
+                bar_wait(bars, B_DEMPTY + buf, mask);
+#pragma unroll 1
+                for (int k0 = 0; k0 < kin; k0 += ks_per) {
+                  const int ks = min(ks_per, kin - k0);
+                  if (j > 0) {  // HF chunks covering inputs [0, 16 (k0 + ks)) must have been written
+                    const int need = ((k0 + ks) * 16 + kCW - 1) / kCW;
+                    while (h1_waited < need) { bar_wait(bars, B_H1 + h1_waited, mask); ++h1_waited; }
+                  }
+                  stage(kColD0 + buf * kCW, a_base + (uint32_t)k0 * 8u, rows, ks, k0 > 0);
+                }
+                if (ptx::elect_one()) ptx::tc_commit(bars + B_DFULL + buf);
+                __syncwarp();
+                // the output-layer MMAs of the PREVIOUS fused chunk go after this chunk's MMAs
+                if (have_pend) { out_op(false); have_pend = false; }
+                if (fused) { have_pend = true; pend_net = (uint32_t)net; pend_c = (uint32_t)(c0 / kCW); pend_rows = rows; }
+              }
+            }
           }
+          out_op(true);
         }
       }
     }
@@ -527,6 +559,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
         const int max_ks = std::min(kMaxKsteps, kSlotBytes / (rows * 32));
         const int n_stage = (ksteps_total + max_ks - 1) / max_ks;
         const int ks_per = (ksteps_total + n_stage - 1) / n_stage;
+        if (net == 0) (rows == kCW ? pl.ks_full[j] : pl.ks_tail[j]) = ks_per;
         for (int s = 0, k = 0; k < ksteps_total; ++s, k += ks_per) {
           const int ks = std::min(ks_per, ksteps_total - k);
           Op op{};
@@ -625,6 +658,7 @@ int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int preci
   a.n_steps = c.n_steps; a.save_every = c.save_every; a.n_save = c.n_save;
   a.n_ops = pl->n_ops; a.L = pl->L; a.act = pl->act; a.bias_per_net = pl->bias_per_net;
   a.hpad[0] = pl->hpad[0]; a.hpad[1] = pl->hpad[1];
+  for (int j = 0; j < 2; ++j) { a.ks_full[j] = pl->ks_full[j]; a.ks_tail[j] = pl->ks_tail[j]; }
   a.tape_bytes = (uint32_t)pl->tape_bytes;
   a.tape_stride = (uint32_t)pl->tape_stride;
   a.n_copies = pl->n_copies;

@@ -1,0 +1,167 @@
+"""PyTorch-autograd twin of oracle/nde_oracle.py (TEST INFRASTRUCTURE, not product).
+
+Same right-hand side, same fixed-step schemes, same loss, written with differentiable torch ops on
+the CPU so that `torch.autograd` yields the EXACT discrete-adjoint (BPTT) gradient of the profile
+loss with respect to the flat NN weight vector — the ground truth the CUDA BPTT kernel
+(opz_loss_grad) is compared with.  It replaces, as a checker, what the reference obtains from
+Zygote through `solve(...; sensealg=InterpolatingAdjoint(autojacvec=ZygoteVJP()))`
+(wind_mixing/src/NDE_training.jl:290-333); the reference's own adjoint is continuous and its
+solver adaptive, so agreement with Julia to rounding is not a goal (parity unpinned).
+
+Follows: NDE / predict_NDE / predict_flux (NDE_training.jl:56-165), loss (loss.jl:1-42),
+loss_NDE / loss_gradient_NDE (NDE_training.jl:290-323).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import nde_oracle as O
+
+
+def _act(z, act):
+    if act == O.ACT_IDENTITY:
+        return z
+    if act == O.ACT_RELU:
+        return torch.relu(z)
+    if act == O.ACT_TANH:
+        return torch.tanh(z)
+    if act == O.ACT_MISH:
+        return z * torch.tanh(torch.nn.functional.softplus(z))
+    if act == O.ACT_SWISH:
+        return z * torch.sigmoid(z)
+    if act == O.ACT_LEAKYRELU:
+        return torch.maximum(0.01 * z, z)
+    raise ValueError(act)
+
+
+def mlp(x, flat, sizes, act):
+    """x[B,in] -> [B,out] with `flat` in Flux.destructure order (NDE_training.jl:11-13)."""
+    h, off = x, 0
+    L = len(sizes) - 1
+    for l in range(L):
+        nin, nout = sizes[l], sizes[l + 1]
+        W = flat[off:off + nin * nout].reshape(nin, nout)  # element (k_in, n_out)
+        off += nin * nout
+        b = flat[off:off + nout]
+        off += nout
+        z = h @ W + b
+        h = _act(z, act) if l < L - 1 else z
+    return h
+
+
+def _box3(a):
+    third = 1.0 / 3.0
+    mid = (a[..., :-2] + a[..., 1:-1] + a[..., 2:]) * third
+    lo = ((a[..., 0] + a[..., 1]) * 0.5).unsqueeze(-1)
+    hi = ((a[..., -2] + a[..., -1]) * 0.5).unsqueeze(-1)
+    return torch.cat([lo, mid, hi], dim=-1)
+
+
+def rhs(x, bc, t, w, sizes, act, p: O.Params):
+    """d x / d(t/tau); x[B,3Nz], bc[B,8], w flat [3P] (torch tensors of one dtype)."""
+    Nz = p.Nz
+    P = O.n_params(sizes)
+    dt = x.dtype
+    s_u, s_v, s_T, s_uw, s_vw, s_wT = (float(s) for s in p.sigma)
+    mu_u, mu_v = float(p.mu[0]), float(p.mu[1])
+    u, v, T = x[:, :Nz], x[:, Nz:2 * Nz], x[:, 2 * Nz:]
+    nn = [mlp(x, w[i * P:(i + 1) * P], sizes, act) for i in range(3)]
+    if p.flags & O.FLAG_SMOOTH_NN:
+        nn = [_box3(a) for a in nn]
+    sub = 1.0 if (p.flags & O.FLAG_BC_MINUS_SCALE0) else 0.0
+    off = [-p.mu[3 + i] / p.sigma[3 + i] for i in range(3)]
+    bot = [bc[:, 2 * i] - sub * off[i] for i in range(3)]
+    top = [bc[:, 2 * i + 1] - sub * off[i] for i in range(3)]
+    if p.flags & O.FLAG_DIURNAL:
+        phys = bc[:, 6] * math.sin(2.0 * math.pi / p.diurnal_period * (float(t) * p.tau)) / (p.alpha * p.g)
+        tp = (phys - p.mu[5]) / p.sigma[5]
+        if p.flags & O.FLAG_DIURNAL_MINUS_SCALE0:
+            tp = tp - off[2]
+        top[2] = tp
+    F = [a for a in nn]
+    if p.flags & O.FLAG_MPP:
+        g = [(c[:, 1:] - c[:, :-1]) * float(Nz) for c in (u, v, T)]  # interior faces 1..Nz-1
+        e = p.eps if (p.flags & O.FLAG_RI_EPS) else 0.0
+        if p.flags & O.FLAG_SMOOTH_RI:
+            z = torch.zeros_like(g[0][:, :1])
+            gf = [torch.cat([z, a, z], dim=1) for a in g]
+            Ri = (p.H * p.g * p.alpha * s_T * (gf[2] + e)) / ((s_u * (gf[0] + e)) ** 2 + (s_v * (gf[1] + e)) ** 2)
+            Ri = _box3(Ri)[:, 1:-1]
+        else:
+            Ri = (p.H * p.g * p.alpha * s_T * (g[2] + e)) / ((s_u * (g[0] + e)) ** 2 + (s_v * (g[1] + e)) ** 2)
+        nu = p.nu0 + p.nu_m * ((1.0 - torch.tanh((Ri - p.Ric) / p.dRi)) / 2.0)
+        if p.flags & O.FLAG_CA:
+            sel = g[0] if (p.flags & O.FLAG_CA_SELECT_DUDZ) else g[2]
+            nuT = torch.where(sel > 0, nu / p.Pr, torch.full_like(nu, p.kappa))
+        else:
+            nuT = nu / p.Pr
+        F[0] = F[0] - s_u / s_uw / p.H * nu * g[0]
+        F[1] = F[1] - s_v / s_vw / p.H * nu * g[1]
+        F[2] = F[2] - s_T / s_wT / p.H * nuT * g[2]
+    full = [torch.cat([bot[i].unsqueeze(1), F[i], top[i].unsqueeze(1)], dim=1) for i in range(3)]
+    div = [(f[:, 1:] - f[:, :-1]) * float(Nz) for f in full]
+    A = -p.tau / p.H
+    ft = p.f * p.tau
+    du = A * s_uw / s_u * div[0] + ft / s_u * (s_v * v + mu_v)
+    dv = A * s_vw / s_v * div[1] - ft / s_v * (s_u * u + mu_u)
+    dT = A * s_wT / s_T * div[2]
+    return torch.cat([du, dv, dT], dim=1).to(dt)
+
+
+def step(x, bc, t, h, w, sizes, act, p, scheme):
+    if scheme == O.SCHEME_EULER:
+        return x + h * rhs(x, bc, t, w, sizes, act, p)
+    if scheme == O.SCHEME_RK2:
+        k1 = rhs(x, bc, t, w, sizes, act, p)
+        k2 = rhs(x + h * k1, bc, t + h, w, sizes, act, p)
+        return x + (h * 0.5) * (k1 + k2)
+    k1 = rhs(x, bc, t, w, sizes, act, p)
+    k2 = rhs(x + (h * 0.5) * k1, bc, t + h * 0.5, w, sizes, act, p)
+    k3 = rhs(x + (h * 0.5) * k2, bc, t + h * 0.5, w, sizes, act, p)
+    k4 = rhs(x + h * k3, bc, t + h, w, sizes, act, p)
+    return x + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+
+
+def rollout(x0, bc, w, sizes, act, p, scheme, dt_nd, n_steps, save_every, t0=0.0):
+    x = x0
+    out = [x]
+    for n in range(n_steps):
+        x = step(x, bc, t0 + n * dt_nd, dt_nd, w, sizes, act, p, scheme)
+        if (n + 1) % save_every == 0:
+            out.append(x)
+    return torch.stack(out, dim=1)  # [B, n_save, 3Nz]
+
+
+def loss_components(sol, target, Nz, B_total=None):
+    """Six unweighted components (u, v, T, du/dz, dv/dz, dT/dz): mean over simulations of Flux.mse over
+    an Nz x Nt (resp. (Nz+1) x Nt with two zero rows) block (loss.jl:1-9; NDE_training.jl:290-317)."""
+    B, Nt = sol.shape[0], sol.shape[1]
+    Bt = B if B_total is None else B_total
+    comps = []
+    for i in range(3):
+        d = sol[:, :, i * Nz:(i + 1) * Nz] - target[:, :, i * Nz:(i + 1) * Nz]
+        comps.append((d ** 2).sum() / (Nz * Nt * Bt))
+    for i in range(3):
+        a = sol[:, :, i * Nz:(i + 1) * Nz]
+        b = target[:, :, i * Nz:(i + 1) * Nz]
+        d = ((a[:, :, 1:] - a[:, :, :-1]) - (b[:, :, 1:] - b[:, :, :-1])) * float(Nz)
+        comps.append((d ** 2).sum() / ((Nz + 1) * Nt * Bt))
+    return comps
+
+
+def loss_and_grad(x0, bc, model: O.Model, p: O.Params, scheme, dt_nd, n_steps, save_every, target, loss_w, t0=0.0,
+                  dtype=torch.float64, B_total=None):
+    """Returns (total, components[6] (weighted), grad[3P]) as numpy float64."""
+    w = torch.tensor(np.asarray(model.flat(), dtype=np.float64), dtype=dtype, requires_grad=True)
+    x0t = torch.tensor(np.asarray(x0, dtype=np.float64), dtype=dtype)
+    bct = torch.tensor(np.asarray(bc, dtype=np.float64), dtype=dtype)
+    tg = torch.tensor(np.asarray(target, dtype=np.float64), dtype=dtype)
+    sol = rollout(x0t, bct, w, tuple(model.sizes), model.act, p, scheme, dt_nd, n_steps, save_every, t0)
+    comps = loss_components(sol, tg, p.Nz, B_total)
+    weighted = [float(loss_w[i]) * comps[i] for i in range(6)]
+    total = sum(weighted)
+    total.backward()
+    return float(total.detach()), np.array([float(c.detach()) for c in weighted]), w.grad.detach().numpy().astype(np.float64)
