@@ -1,5 +1,847 @@
-// opz_bptt.cu — discrete-adjoint (BPTT) kernels (placeholder until the kernel lands).
+// opz_bptt.cu — loss of the fixed-step NDE solve and its exact discrete adjoint (BPTT) w.r.t. the
+// NN weights, FP32.
+//
+// Replaces loss_NDE / loss_gradient_NDE + Zygote.gradient through
+// solve(...; sensealg = InterpolatingAdjoint(autojacvec = ZygoteVJP()))
+// (wind_mixing/src/NDE_training.jl:290-333; loss: wind_mixing/src/loss.jl:1-42).
+//
+// The training batch of the reference is 18 columns (train_NDE_args.jl:39-60), far too few to fill
+// 148 SMs column-by-column, and the rollout is strictly sequential in time.  So this path is laid out
+// the other way round from the forward ensemble kernels: ONE right-hand side is spread over the whole
+// GPU, layer by layer (every CTA owns a slice of a layer's units and all B columns), and the
+// launch-bound chain of small kernels is captured once into CUDA graphs that are replayed over the
+// time steps; a device-side cursor carries the step index so that the graphs never need re-parametrising.
+//
+//   forward sweep     x_n -> x_{n+1}: per stage  [hidden layers ...] -> [last layer + physics + RK update]
+//                     every stage's input, hidden activations h_l and act'(z_l) are RECORDED in HBM
+//   backward sweep    per stage  [physics VJP + last layer^T] -> [hidden layers^T ...] -> [first layer^T + RK adjoint]
+//                     act'(z_l) records are overwritten in place by dz_l
+//   weight gradient   dW_l = sum over all recorded right-hand sides of h_{l-1}^T dz_l : ONE large
+//                     reduction GEMM per layer over (columns x stages x steps) rows, instead of a
+//                     read-modify-write of the 2.5 MB gradient per right-hand side.
+// If the records of the whole rollout do not fit the memory budget, the rollout is cut into time
+// segments (state checkpoints x_n are kept for every step): the forward sweep runs without records,
+// then each segment is recomputed with records right before its backward sweep.
+//
+// The recurrences are the ones restated and checked against autograd in oracle/nde_adjoint.py.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
 #include "opz_internal.h"
+
 namespace opz {
-int fp32_loss_grad(opz_ctx*, const opz_model*, const LossGradCall&) { set_error("BPTT path not built yet"); return OPZ_EUNSUP; }
+namespace bptt {
+
+constexpr int kCT = 20;        // columns per GEMM column tile (18 training cases + padding)
+constexpr int kNT = 16;        // units per CTA
+constexpr int kKS = 16;        // split of the reduction dimension inside a CTA
+constexpr int kGemmThreads = kNT * kKS;
+constexpr int kMaxStages = 4;
+
+struct Cursor {
+  int n;        // base time step of the graph launch in flight
+  int seg_n0;   // first step of the recorded segment
+};
+
+struct Args {
+  DevParams P;
+  NetDesc nd;
+  const float* w;        // [3P] Flux order
+  const float* wT;       // transposed copies of layers 0..L-2, per net
+  int64_t wT_off[kMaxLayers];   // offset of layer l inside one net's block
+  int64_t wT_net;        // floats per net
+  const float* bc;       // [B][8]
+  const float* target;   // [B][n_save][3nz]
+  float* XN;             // [n_steps+1][B][3nz] state checkpoints
+  float* X;              // [Rcap][B][3nz] stage inputs
+  float* H[kMaxLayers];  // [3][Rcap*B][n_l] hidden activations
+  float* G[kMaxLayers];  // [3][Rcap*B][n_l] act'(z_l), then dz_l
+  float* DY;             // [3][Rcap*B][nout]
+  float* KACC;           // [B][3nz] Runge-Kutta accumulator (forward)
+  float* LAM;            // [B][3nz] dL/dx_{n+1} -> dL/dx_n
+  float* KBAR;           // [B][3nz] cotangent of the current stage's tendency
+  float* XSUM;           // [B][3nz] sum of the stage-input cotangents of the step
+  float* XPHYS;          // [B][3nz] physics part of the current stage-input cotangent
+  double* loss_part;     // [B][6]
+  float* loss_out;       // [7]
+  float* grad;           // [3P]
+  const Cursor* cur;
+  int64_t B, B_total;
+  int64_t rows_cap;      // Rcap * B
+  int S3, nout, L;
+  int scheme, stages;
+  int n_steps, save_every, n_save;
+  int record;            // 1: record index = (n - seg_n0)*stages + s ; 0: ring of `stages` records
+  int rcap;              // Rcap
+  float h, t0;
+  float rk_b[kMaxStages], rk_a[kMaxStages], rk_c[kMaxStages];
+  float loss_w[6];
+};
+
+__device__ __forceinline__ int rec_index(const Args& a, int n, int s) {
+  return a.record ? (n - a.cur->seg_n0) * a.stages + s : s;
 }
+
+// ---- cursor -----------------------------------------------------------------------------------------
+__global__ void set_cursor_kernel(Cursor* c, int n, int seg_n0) { c->n = n; c->seg_n0 = seg_n0; }
+__global__ void bump_cursor_kernel(Cursor* c, int dn) { c->n += dn; }
+
+// ---- layer-parallel skinny GEMM ------------------------------------------------------------------------
+// out[c][j] = sum_i A[c][i] * M[i*J + j] for a tile of kCT columns x kNT outputs, reduction split kKS ways.
+enum { MODE_FWD = 0, MODE_BWD_HID = 1, MODE_BWD_IN = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads) skinny_kernel(const __grid_constant__ Args a, int layer, int stage, int dn) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  const int nl = tid % kNT, ks = tid / kNT;
+  const int n = a.cur->n + dn;
+  const int q = rec_index(a, n, stage);
+  const int64_t col0 = (int64_t)blockIdx.y * kCT;
+  const int ncols = (int)min((int64_t)kCT, a.B - col0);
+  const int64_t r0 = (int64_t)q * a.B + col0;
+  const int net0 = (MODE == MODE_BWD_IN) ? 0 : blockIdx.z;
+  const int nsum = (MODE == MODE_BWD_IN) ? 3 : 1;
+
+  int I, J;
+  if (MODE == MODE_FWD) { I = a.nd.sizes[layer]; J = a.nd.sizes[layer + 1]; }
+  else if (MODE == MODE_BWD_HID) { I = a.nd.sizes[layer + 1]; J = a.nd.sizes[layer]; }   // dz_layer -> dz_{layer-1}
+  else { I = a.nd.sizes[1]; J = a.S3; }
+  float* As = sm;                 // [I][kCT]
+  float* red = sm + (size_t)I * kCT;  // [kKS][kCT][kNT]
+  const int j = blockIdx.x * kNT + nl;
+
+  float acc[kCT];
+#pragma unroll
+  for (int c = 0; c < kCT; ++c) acc[c] = 0.0f;
+
+  for (int ns = 0; ns < nsum; ++ns) {
+    const int net = net0 + ns;
+    const float* A;
+    int lda;
+    const float* M;
+    if (MODE == MODE_FWD) {
+      if (layer == 0) { A = a.X + r0 * a.S3; lda = a.S3; }
+      else { lda = a.nd.sizes[layer]; A = a.H[layer - 1] + ((int64_t)net * a.rows_cap + r0) * lda; }
+      M = a.w + (int64_t)net * a.nd.P + a.nd.w_off[layer];
+    } else if (MODE == MODE_BWD_HID) {
+      lda = I;
+      A = a.G[layer] + ((int64_t)net * a.rows_cap + r0) * lda;
+      M = a.wT + (int64_t)net * a.wT_net + a.wT_off[layer];
+    } else {
+      lda = I;
+      A = a.G[0] + ((int64_t)net * a.rows_cap + r0) * lda;
+      M = a.wT + (int64_t)net * a.wT_net + a.wT_off[0];
+    }
+    if (ns > 0) __syncthreads();
+    for (int e = tid; e < I * kCT; e += kGemmThreads) {
+      const int c = e / I, i = e - c * I;
+      As[i * kCT + c] = c < ncols ? A[(int64_t)c * lda + i] : 0.0f;
+    }
+    __syncthreads();
+    if (j < J) {
+#pragma unroll 5
+      for (int i = ks; i < I; i += kKS) {
+        const float wv = __ldg(M + (size_t)i * J + j);
+        const float4* ap = reinterpret_cast<const float4*>(As + i * kCT);
+#pragma unroll
+        for (int v = 0; v < kCT / 4; ++v) {
+          const float4 a4 = ap[v];
+          acc[4 * v + 0] = fmaf(wv, a4.x, acc[4 * v + 0]);
+          acc[4 * v + 1] = fmaf(wv, a4.y, acc[4 * v + 1]);
+          acc[4 * v + 2] = fmaf(wv, a4.z, acc[4 * v + 2]);
+          acc[4 * v + 3] = fmaf(wv, a4.w, acc[4 * v + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kCT; ++c) red[(ks * kCT + c) * kNT + nl] = acc[c];
+  __syncthreads();
+  for (int e = tid; e < kCT * kNT; e += kGemmThreads) {
+    const int c = e / kNT, jl = e - c * kNT;
+    const int jj = blockIdx.x * kNT + jl;
+    if (c >= ncols || jj >= J) continue;
+    float sum = 0.0f;
+#pragma unroll
+    for (int s2 = 0; s2 < kKS; ++s2) sum += red[(s2 * kCT + c) * kNT + jl];
+    const int64_t row = r0 + c;
+    if (MODE == MODE_FWD) {
+      const int net = net0;
+      const float z = sum + __ldg(a.w + (int64_t)net * a.nd.P + a.nd.b_off[layer] + jj);
+      const int64_t o = ((int64_t)net * a.rows_cap + row) * J + jj;
+      a.H[layer][o] = act_dyn(z, a.nd.act);
+      a.G[layer][o] = act_grad_dyn(z, a.nd.act);
+    } else if (MODE == MODE_BWD_HID) {
+      const int64_t o = ((int64_t)net0 * a.rows_cap + row) * J + jj;
+      a.G[layer - 1][o] = sum * a.G[layer - 1][o];
+    } else {
+      // stage-input cotangent complete: Runge-Kutta adjoint bookkeeping (oracle/nde_adjoint.py)
+      const int64_t o = (col0 + c) * a.S3 + jj;
+      const float xbar = sum + a.XPHYS[o];
+      const float lam = a.LAM[o];
+      const float xsum = (stage == a.stages - 1 ? 0.0f : a.XSUM[o]) + xbar;
+      if (stage > 0) {
+        a.KBAR[o] = a.rk_b[stage - 1] * lam + a.rk_a[stage - 1] * xbar;
+        a.XSUM[o] = xsum;
+      } else {
+        float ln = lam + xsum;
+        if (n % a.save_every == 0) {
+          // dL/dx_n of the profile loss at this save point (loss.jl:1-9; NDE_training.jl:290-317)
+          const int nz = a.P.nz, v = jj / nz, cz = jj - v * nz;
+          const int snap = n / a.save_every;
+          const float* xs = a.XN + ((int64_t)n * a.B + col0 + c) * a.S3 + v * nz;
+          const float* tg = a.target + (((col0 + c) * a.n_save + snap) * (int64_t)a.S3) + v * nz;
+          const float inv_p = 1.0f / ((float)nz * (float)a.n_save * (float)a.B_total);
+          const float inv_g = 1.0f / ((float)(nz + 1) * (float)a.n_save * (float)a.B_total);
+          const float d0 = xs[cz] - tg[cz];
+          float add = a.loss_w[v] * 2.0f * d0 * inv_p;
+          const float sc = a.loss_w[3 + v] * 2.0f * a.P.nzf * inv_g;
+          if (sc != 0.0f) {
+            if (cz > 0) add += sc * ((d0 - (xs[cz - 1] - tg[cz - 1])) * a.P.nzf);
+            if (cz < nz - 1) add -= sc * (((xs[cz + 1] - tg[cz + 1]) - d0) * a.P.nzf);
+          }
+          ln += add;
+        }
+        a.LAM[o] = ln;
+        a.KBAR[o] = a.rk_b[a.stages - 1] * ln;
+      }
+    }
+  }
+}
+
+// ---- last Dense layer + physics + Runge-Kutta update: one CTA per column -----------------------------------
+__global__ void __launch_bounds__(1024) final_fwd_kernel(const __grid_constant__ Args a, int stage, int dn) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int nz = a.P.nz, S3 = a.S3, nout = a.nout, L = a.L;
+  const int nh = a.nd.sizes[L - 1];          // width of the last hidden layer
+  const int OP = (3 * nout + 31) / 32 * 32;  // padded number of outputs
+  const int KSL = nthr / OP;                 // reduction slices
+  float* hs = sm;                            // [3][nh]
+  float* ypart = hs + 3 * nh;                // [KSL][OP]
+  float* xs = ypart + KSL * OP;              // [S3]
+  float* Fs = xs + S3;                       // [3][nz+1]
+  const int64_t col = blockIdx.x;
+  const int n = a.cur->n + dn;
+  const int q = rec_index(a, n, stage);
+  const int64_t row = (int64_t)q * a.B + col;
+
+  for (int e = tid; e < 3 * nh; e += nthr) {
+    const int net = e / nh, k = e - net * nh;
+    hs[e] = a.H[L - 2][((int64_t)net * a.rows_cap + row) * nh + k];
+  }
+  for (int i = tid; i < S3; i += nthr) xs[i] = a.X[row * S3 + i];
+  __syncthreads();
+  {
+    const int o = tid % OP, ksl = tid / OP;
+    float part = 0.0f;
+    if (ksl < KSL && o < 3 * nout) {
+      const int net = o / nout, j = o - net * nout;
+      const float* W = a.w + (int64_t)net * a.nd.P + a.nd.w_off[L - 1];
+      const float* hh = hs + net * nh;
+#pragma unroll 4
+      for (int k = ksl; k < nh; k += KSL) part = fmaf(hh[k], __ldg(W + (size_t)k * nout + j), part);
+    }
+    if (ksl < KSL) ypart[ksl * OP + o] = part;
+  }
+  __syncthreads();
+  if (tid < 3 * nout) {
+    const int net = tid / nout, j = tid - net * nout;
+    float y = 0.0f;
+    for (int s2 = 0; s2 < KSL; ++s2) y += ypart[s2 * OP + tid];
+    y += __ldg(a.w + (int64_t)net * a.nd.P + a.nd.b_off[L - 1] + j);
+    ypart[tid] = y;  // slice 0 now holds the outputs
+  }
+  __syncthreads();
+  const float* bc = a.bc + col * OPZ_BC_STRIDE;
+  const float tn = a.t0 + (float)n * a.h;
+  const float ts = tn + a.rk_c[stage] * a.h;
+  const DevParams& P = a.P;
+  if (tid <= nz) {  // one thread per face
+    const int f = tid;
+    float Fu, Fv, FT;
+    if (f == 0) { Fu = bc[0] - P.off[0]; Fv = bc[2] - P.off[1]; FT = bc[4] - P.off[2]; }
+    else if (f == nz) { Fu = bc[1] - P.off[0]; Fv = bc[3] - P.off[1]; FT = wT_top_value(P, bc, ts); }
+    else {
+      Fu = ypart[f - 1]; Fv = ypart[nout + f - 1]; FT = ypart[2 * nout + f - 1];
+      if (P.flags & OPZ_FLAG_MPP) {
+        const float gu = (xs[f] - xs[f - 1]) * P.nzf;
+        const float gv = (xs[nz + f] - xs[nz + f - 1]) * P.nzf;
+        const float gT = (xs[2 * nz + f] - xs[2 * nz + f - 1]) * P.nzf;
+        const float Ri = richardson(P, gu, gv, gT);
+        const float nu = nu_of_ri(P, Ri);
+        const float nuT = nuT_of(P, nu, gu, gT);
+        Fu -= P.c_u * nu * gu;
+        Fv -= P.c_v * nu * gv;
+        FT -= P.c_T * nuT * gT;
+      }
+    }
+    Fs[f] = Fu; Fs[(nz + 1) + f] = Fv; Fs[2 * (nz + 1) + f] = FT;
+  }
+  __syncthreads();
+  if (tid < S3) {
+    const int v = tid / nz, c = tid - v * nz;
+    const float* F = Fs + v * (nz + 1);
+    float k;
+    if (v == 0) k = P.A_u * ((F[c + 1] - F[c]) * P.nzf) + P.cor_u * (P.s_v * xs[nz + c] + P.mu_v);
+    else if (v == 1) k = P.A_v * ((F[c + 1] - F[c]) * P.nzf) - P.cor_v * (P.s_u * xs[c] + P.mu_u);
+    else k = P.A_T * ((F[c + 1] - F[c]) * P.nzf);
+    const int64_t o = col * S3 + tid;
+    const float xn = a.XN[((int64_t)n * a.B + col) * S3 + tid];
+    const float hh = a.h;
+    float xnext;
+    bool last = (stage == a.stages - 1);
+    if (a.scheme == OPZ_RK4) {
+      if (stage == 0) { a.KACC[o] = k; xnext = xn + (hh * 0.5f) * k; }
+      else if (stage == 1) { a.KACC[o] = a.KACC[o] + 2.0f * k; xnext = xn + (hh * 0.5f) * k; }
+      else if (stage == 2) { a.KACC[o] = a.KACC[o] + 2.0f * k; xnext = xn + hh * k; }
+      else xnext = xn + (hh / 6.0f) * (a.KACC[o] + k);
+    } else if (a.scheme == OPZ_RK2) {
+      if (stage == 0) { a.KACC[o] = k; xnext = xn + hh * k; }
+      else xnext = xn + (hh * 0.5f) * (a.KACC[o] + k);
+    } else {
+      xnext = xn + hh * k;
+    }
+    if (last) a.XN[((int64_t)(n + 1) * a.B + col) * S3 + tid] = xnext;
+    int qn;
+    if (a.record) qn = q + 1 < a.rcap ? q + 1 : -1;
+    else qn = last ? 0 : stage + 1;
+    if (qn >= 0) a.X[((int64_t)qn * a.B + col) * S3 + tid] = xnext;
+  }
+}
+
+// ---- physics VJP + transpose of the last Dense layer: one CTA per column --------------------------------
+__global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__ Args a, int stage, int dn) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int nz = a.P.nz, S3 = a.S3, nout = a.nout, L = a.L;
+  const int nh = a.nd.sizes[L - 1];
+  float* xs = sm;              // [S3]
+  float* kb = xs + S3;         // [S3]
+  float* dy = kb + S3;         // [3][nout]
+  float* gb = dy + 3 * nout;   // [3][nz+1] cotangents of the face gradients
+  const int64_t col = blockIdx.x;
+  const int n = a.cur->n + dn;
+  const int q = rec_index(a, n, stage);
+  const int64_t row = (int64_t)q * a.B + col;
+  const DevParams& P = a.P;
+  for (int i = tid; i < S3; i += nthr) {
+    xs[i] = a.X[row * S3 + i];
+    kb[i] = a.KBAR[col * S3 + i];
+  }
+  __syncthreads();
+  if (tid <= nz) {
+    const int f = tid;
+    float gbu = 0.0f, gbv = 0.0f, gbT = 0.0f;
+    if (f > 0 && f < nz) {
+      const float Fbu = P.A_u * P.nzf * (kb[f - 1] - kb[f]);
+      const float Fbv = P.A_v * P.nzf * (kb[nz + f - 1] - kb[nz + f]);
+      const float FbT = P.A_T * P.nzf * (kb[2 * nz + f - 1] - kb[2 * nz + f]);
+      dy[f - 1] = Fbu; dy[nout + f - 1] = Fbv; dy[2 * nout + f - 1] = FbT;
+      a.DY[((int64_t)0 * a.rows_cap + row) * nout + f - 1] = Fbu;
+      a.DY[((int64_t)1 * a.rows_cap + row) * nout + f - 1] = Fbv;
+      a.DY[((int64_t)2 * a.rows_cap + row) * nout + f - 1] = FbT;
+      if (P.flags & OPZ_FLAG_MPP) {
+        const float gu = (xs[f] - xs[f - 1]) * P.nzf;
+        const float gv = (xs[nz + f] - xs[nz + f - 1]) * P.nzf;
+        const float gT = (xs[2 * nz + f] - xs[2 * nz + f - 1]) * P.nzf;
+        const float ea = P.s_u * (gu + P.eps), eb = P.s_v * (gv + P.eps);
+        const float S2 = ea * ea + eb * eb;
+        const float Ri = P.cBz * (gT + P.eps) / S2;
+        const float th = tanhf((Ri - P.Ric) / P.dRi);
+        const float nu = P.nu0 + P.nu_m * ((1.0f - th) / 2.0f);
+        bool keep = true;
+        float nuT = nu / P.Pr;
+        if (P.flags & OPZ_FLAG_CA) {
+          const float sel = (P.flags & OPZ_FLAG_CA_SELECT_DUDZ) ? gu : gT;
+          keep = sel > 0.0f;
+          if (!keep) nuT = P.kappa;
+        }
+        const float nubar = -P.c_u * gu * Fbu - P.c_v * gv * Fbv - (keep ? P.c_T * gT * FbT / P.Pr : 0.0f);
+        const float Ribar = nubar * (-P.nu_m / (2.0f * P.dRi) * (1.0f - th * th));
+        const float dRi_dgT = P.cBz / S2;
+        const bool ok = isfinite(Ri) && isfinite(dRi_dgT);
+        gbu = -P.c_u * nu * Fbu + (ok ? Ribar * (-Ri * 2.0f * P.s_u * ea / S2) : 0.0f);
+        gbv = -P.c_v * nu * Fbv + (ok ? Ribar * (-Ri * 2.0f * P.s_v * eb / S2) : 0.0f);
+        gbT = -P.c_T * nuT * FbT + (ok ? Ribar * dRi_dgT : 0.0f);
+      }
+    }
+    gb[f] = gbu; gb[(nz + 1) + f] = gbv; gb[2 * (nz + 1) + f] = gbT;
+  }
+  __syncthreads();
+  if (tid < S3) {
+    const int v = tid / nz, c = tid - v * nz;
+    const float* g = gb + v * (nz + 1);
+    float xb = P.nzf * (g[c] - g[c + 1]);  // cell c is the upper cell of face c and the lower cell of face c+1
+    if (v == 0) xb -= P.cor_v * P.s_u * kb[nz + c];
+    else if (v == 1) xb += P.cor_u * P.s_v * kb[c];
+    a.XPHYS[col * S3 + tid] = xb;
+  }
+  // dz_{L-2} = (W_L dy) * act'(z_{L-2})   (in place over the act' record)
+  for (int e = tid; e < 3 * nh; e += nthr) {
+    const int net = e / nh, k = e - net * nh;
+    const float* W = a.w + (int64_t)net * a.nd.P + a.nd.w_off[L - 1] + (size_t)k * nout;
+    const float* d = dy + net * nout;
+    float s = 0.0f;
+    for (int j = 0; j < nout; ++j) s = fmaf(__ldg(W + j), d[j], s);
+    const int64_t o = ((int64_t)net * a.rows_cap + row) * nh + k;
+    a.G[L - 2][o] = s * a.G[L - 2][o];
+  }
+}
+
+// ---- lambda_N and the first tendency cotangent ----------------------------------------------------------
+__global__ void init_lambda_kernel(const __grid_constant__ Args a) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B * a.S3) return;
+  const int64_t col = e / a.S3;
+  const int jj = (int)(e - col * a.S3);
+  const int n = a.n_steps;
+  const int nz = a.P.nz, v = jj / nz, cz = jj - v * nz;
+  const int snap = n / a.save_every;
+  const float* xs = a.XN + ((int64_t)n * a.B + col) * a.S3 + v * nz;
+  const float* tg = a.target + ((col * a.n_save + snap) * (int64_t)a.S3) + v * nz;
+  const float inv_p = 1.0f / ((float)nz * (float)a.n_save * (float)a.B_total);
+  const float inv_g = 1.0f / ((float)(nz + 1) * (float)a.n_save * (float)a.B_total);
+  const float d0 = xs[cz] - tg[cz];
+  float add = a.loss_w[v] * 2.0f * d0 * inv_p;
+  const float sc = a.loss_w[3 + v] * 2.0f * a.P.nzf * inv_g;
+  if (sc != 0.0f) {
+    if (cz > 0) add += sc * ((d0 - (xs[cz - 1] - tg[cz - 1])) * a.P.nzf);
+    if (cz < nz - 1) add -= sc * (((xs[cz + 1] - tg[cz + 1]) - d0) * a.P.nzf);
+  }
+  a.LAM[e] = add;
+  a.KBAR[e] = a.rk_b[a.stages - 1] * add;
+}
+
+// ---- loss --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) loss_partial_kernel(const __grid_constant__ Args a) {
+  __shared__ double red[6][128];
+  const int64_t col = blockIdx.x;
+  const int nz = a.P.nz;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = threadIdx.x; e < a.n_save * a.S3; e += blockDim.x) {
+    const int snap = e / a.S3, i = e - snap * a.S3;
+    const int v = i / nz, cz = i - v * nz;
+    const int64_t n = (int64_t)snap * a.save_every;
+    const float* xs = a.XN + (n * a.B + col) * a.S3 + v * nz;
+    const float* tg = a.target + ((col * a.n_save + snap) * (int64_t)a.S3) + v * nz;
+    const float d0 = xs[cz] - tg[cz];
+    s[v] += (double)d0 * d0;
+    if (cz > 0) {
+      const float dg = (d0 - (xs[cz - 1] - tg[cz - 1])) * a.P.nzf;
+      s[3 + v] += (double)dg * dg;
+    }
+  }
+  for (int c = 0; c < 6; ++c) red[c][threadIdx.x] = s[c];
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) t += red[threadIdx.x][i];
+    a.loss_part[col * 6 + threadIdx.x] = t;
+  }
+}
+
+__global__ void loss_final_kernel(const __grid_constant__ Args a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t c = 0; c < a.B; ++c)
+    for (int k = 0; k < 6; ++k) s[k] += a.loss_part[c * 6 + k];
+  const double nz = a.P.nz;
+  double tot = 0;
+  for (int k = 0; k < 6; ++k) {
+    const double den = (k < 3 ? nz : nz + 1.0) * (double)a.n_save * (double)a.B_total;
+    const double v = (double)a.loss_w[k] * s[k] / den;
+    a.loss_out[1 + k] = (float)v;
+    tot += v;
+  }
+  a.loss_out[0] = (float)tot;
+}
+
+// ---- weight-gradient reduction GEMM: dW[k][n] += sum_r A[r][k] D[r][n] ---------------------------------------
+constexpr int kTK = 64, kTN = 64, kRC = 16;
+__global__ void __launch_bounds__(256) dw_kernel(const float* __restrict__ A, int64_t a_net, int lda,
+                                                 const float* __restrict__ D, int64_t d_net, int ldd, int K, int N,
+                                                 int64_t R, int split, float* __restrict__ gW, float* __restrict__ gb,
+                                                 int64_t g_net) {
+  __shared__ __align__(16) float As[kRC][kTK];
+  __shared__ __align__(16) float Ds[kRC][kTN];
+  const int tid = threadIdx.x;
+  const int tk = tid / 16, tn = tid % 16;
+  const int net = blockIdx.z / split, sp = blockIdx.z % split;
+  const int k0 = blockIdx.x * kTK, n0 = blockIdx.y * kTN;
+  const int64_t per = (R + split - 1) / split;
+  const int64_t rbeg = per * sp, rend = min(R, per * (sp + 1));
+  A += net * a_net;
+  D += net * d_net;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_bias = (blockIdx.x == 0 && tk == 0);
+  for (int64_t r0 = rbeg; r0 < rend; r0 += kRC) {
+#pragma unroll
+    for (int i = 0; i < (kRC * kTK) / 256; ++i) {
+      const int e = tid + i * 256;
+      const int rr = e / kTK, kk = e % kTK;
+      const int64_t r = r0 + rr;
+      As[rr][kk] = (r < rend && k0 + kk < K) ? A[r * lda + k0 + kk] : 0.0f;
+      Ds[rr][kk] = (r < rend && n0 + kk < N) ? D[r * ldd + n0 + kk] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kRC; ++rr) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[rr][tk * 4]);
+      const float4 d4 = *reinterpret_cast<const float4*>(&Ds[rr][tn * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], dv[j], acc[i][j]);
+      if (do_bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bacc[j] += dv[j];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + tk * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tn * 4 + j;
+      if (nn < N) atomicAdd(gW + net * g_net + (size_t)k * N + nn, acc[i][j]);
+    }
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tn * 4 + j;
+      if (nn < N) atomicAdd(gb + net * g_net + nn, bacc[j]);
+    }
+  }
+}
+
+// W (K x N, element (k,n) at k*N+n) -> WT (element (n,k) at n*K+k)
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int K, int N) {
+  __shared__ float t[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    t[r][threadIdx.x] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N && k < K) WT[(size_t)n * K + k] = t[threadIdx.x][r];
+  }
+}
+
+}  // namespace bptt
+
+// ---- host orchestration ----------------------------------------------------------------------------------------
+namespace {
+
+struct GraphPair {
+  cudaGraphExec_t exec = nullptr;
+  int steps = 0;
+  int64_t kernels = 0;
+};
+
+void destroy(GraphPair& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  g.exec = nullptr;
+}
+
+// The instantiated graphs depend on every by-value kernel argument; a training loop repeats the same
+// call (same scratch buffers, same shapes), so they are cached on the context and rebuilt on any change.
+struct BpttCache {
+  bptt::Args key;
+  int U = 0;
+  bool valid = false;
+  GraphPair fwd_rec_U, fwd_rec_1, fwd_ring_U, fwd_ring_1, bwd_U, bwd_1;
+  void clear() {
+    destroy(fwd_rec_U); destroy(fwd_rec_1); destroy(fwd_ring_U); destroy(fwd_ring_1); destroy(bwd_U); destroy(bwd_1);
+    valid = false;
+  }
+};
+
+}  // namespace
+
+void bptt_release(opz_ctx* ctx) {
+  BpttCache* bc = static_cast<BpttCache*>(ctx->bptt_cache);
+  if (bc) { bc->clear(); delete bc; }
+  ctx->bptt_cache = nullptr;
+  if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
+  ctx->capture_stream = nullptr;
+}
+
+int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
+  using namespace bptt;
+  const NetDesc& nd = m->nd;
+  const int L = nd.n_layers;
+  const int nz = m->nz, S3 = 3 * nz, nout = nz - 1;
+  const int64_t B = c.r.B;
+  const size_t P3 = 3 * (size_t)nd.P;
+  cudaStream_t st = ctx->stream;
+  if (L < 2) { set_error("opz_loss_grad: the nets need at least one hidden layer"); return OPZ_EUNSUP; }
+  if (c.r.P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {
+    set_error("opz_loss_grad: smooth_NN / smooth_Ri are not differentiated yet");
+    return OPZ_EUNSUP;
+  }
+  OPZ_CUDA(cudaMemsetAsync(c.grad_out, 0, sizeof(float) * P3, st));
+  OPZ_CUDA(cudaMemsetAsync(c.loss_out, 0, sizeof(float) * 7, st));
+  if (B == 0) return OPZ_OK;
+
+  const int stages = c.r.scheme == OPZ_RK4 ? 4 : (c.r.scheme == OPZ_RK2 ? 2 : 1);
+  const int n_steps = c.r.n_steps;
+
+  // ---- memory plan ----
+  size_t rec_floats = S3 + 3 * (size_t)nout;  // per (column, right-hand side)
+  int max_in = S3;
+  for (int l = 0; l < L - 1; ++l) { rec_floats += 6 * (size_t)nd.sizes[l + 1]; max_in = std::max(max_in, nd.sizes[l + 1]); }
+  size_t budget = (size_t)24 << 30;
+  if (const char* e = getenv("OPZ_BPTT_RECORD_BYTES")) budget = (size_t)atoll(e);
+  size_t free_b = 0, total_b = 0;
+  OPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  free_b += ctx->scratch_bytes[4] + ctx->scratch_bytes[5];  // our own grow-only buffers can be reused
+  const size_t xn_bytes = sizeof(float) * (size_t)(n_steps + 1) * B * S3;
+  if (xn_bytes + ((size_t)1 << 30) > free_b) {
+    set_error("opz_loss_grad: state checkpoints of " + std::to_string(xn_bytes) + " bytes do not fit device memory");
+    return OPZ_ENOMEM;
+  }
+  budget = std::min(budget, (free_b - xn_bytes) / 2);
+  const size_t step_bytes = sizeof(float) * rec_floats * (size_t)B * stages;
+  int64_t seg_steps = (int64_t)(budget / step_bytes);
+  if (seg_steps < 1) { set_error("opz_loss_grad: one time step of records does not fit the memory budget"); return OPZ_ENOMEM; }
+  if (seg_steps > n_steps) seg_steps = n_steps;
+  const bool single = (seg_steps >= n_steps);
+  const int rcap = (int)std::max<int64_t>(seg_steps * stages, stages);
+  const int64_t rows_cap = (int64_t)rcap * B;
+
+  float *XN, *REC, *SMALL;
+  int rc;
+  if ((rc = ensure_scratch(ctx, 4, xn_bytes, (void**)&XN))) return rc;
+  if ((rc = ensure_scratch(ctx, 5, sizeof(float) * rec_floats * (size_t)rows_cap, (void**)&REC))) return rc;
+  size_t wT_net = 0;
+  int64_t wT_off[kMaxLayers] = {0};
+  for (int l = 0; l < L - 1; ++l) { wT_off[l] = (int64_t)wT_net; wT_net += (size_t)nd.sizes[l] * nd.sizes[l + 1]; }
+  const size_t small_floats = 5 * (size_t)B * S3 + 3 * wT_net + 64 + (size_t)B * 12 /* 6 doubles */;
+  if ((rc = ensure_scratch(ctx, 6, sizeof(float) * small_floats, (void**)&SMALL))) return rc;
+
+  Args a;
+  std::memset(&a, 0, sizeof(a));  // the struct doubles as the graph-cache key (padding included)
+  a.P = c.r.P;
+  a.nd = nd;
+  a.w = m->w_dev;
+  a.bc = c.r.bc;
+  a.target = c.target;
+  a.XN = XN;
+  {
+    float* p = REC;
+    a.X = p; p += (size_t)rows_cap * S3;
+    for (int l = 0; l < L - 1; ++l) {
+      a.H[l] = p; p += 3 * (size_t)rows_cap * nd.sizes[l + 1];
+      a.G[l] = p; p += 3 * (size_t)rows_cap * nd.sizes[l + 1];
+    }
+    a.DY = p;
+  }
+  {
+    float* p = SMALL;
+    a.loss_part = reinterpret_cast<double*>(p); p += (size_t)B * 12;
+    a.KACC = p; p += (size_t)B * S3;
+    a.LAM = p; p += (size_t)B * S3;
+    a.KBAR = p; p += (size_t)B * S3;
+    a.XSUM = p; p += (size_t)B * S3;
+    a.XPHYS = p; p += (size_t)B * S3;
+    a.cur = reinterpret_cast<Cursor*>(p); p += 64;
+    a.wT = p;
+  }
+  float* wT_dev = const_cast<float*>(a.wT);
+  Cursor* cur_dev = const_cast<Cursor*>(a.cur);
+  for (int l = 0; l < kMaxLayers; ++l) a.wT_off[l] = wT_off[l];
+  a.wT_net = (int64_t)wT_net;
+  a.loss_out = c.loss_out;
+  a.grad = c.grad_out;
+  a.B = B; a.B_total = c.B_total; a.rows_cap = rows_cap;
+  a.S3 = S3; a.nout = nout; a.L = L;
+  a.scheme = c.r.scheme; a.stages = stages;
+  a.n_steps = n_steps; a.save_every = c.r.save_every; a.n_save = c.r.n_save;
+  a.rcap = rcap;
+  a.h = c.r.dt; a.t0 = c.r.t0;
+  {
+    const float h = c.r.dt;
+    if (c.r.scheme == OPZ_RK4) {
+      const float b[4] = {h / 6.0f, h / 3.0f, h / 3.0f, h / 6.0f}, aa[4] = {h * 0.5f, h * 0.5f, h, 0.f}, cc[4] = {0.f, 0.5f, 0.5f, 1.0f};
+      for (int i = 0; i < 4; ++i) { a.rk_b[i] = b[i]; a.rk_a[i] = aa[i]; a.rk_c[i] = cc[i]; }
+    } else if (c.r.scheme == OPZ_RK2) {
+      a.rk_b[0] = a.rk_b[1] = h * 0.5f; a.rk_a[0] = h; a.rk_c[0] = 0.f; a.rk_c[1] = 1.0f;
+    } else {
+      a.rk_b[0] = h; a.rk_c[0] = 0.f;
+    }
+  }
+  for (int i = 0; i < 6; ++i) a.loss_w[i] = c.loss_w[i];
+
+  // ---- transposed weight copies for the backward GEMMs ----
+  for (int net = 0; net < 3; ++net)
+    for (int l = 0; l < L - 1; ++l) {
+      const int K = nd.sizes[l], N = nd.sizes[l + 1];
+      dim3 g((K + 31) / 32, (N + 31) / 32), b(32, 8);
+      transpose_kernel<<<g, b, 0, st>>>(m->w_dev + (size_t)net * nd.P + nd.w_off[l], wT_dev + (size_t)net * wT_net + wT_off[l], K, N);
+      ctx->launches += 1;
+    }
+  OPZ_CUDA(cudaGetLastError());
+
+  // ---- launch configuration ----
+  const int n_ct = (int)((B + kCT - 1) / kCT);
+  const size_t gemm_smem = sizeof(float) * ((size_t)max_in * kCT + (size_t)kKS * kCT * kNT);
+  if ((int)gemm_smem > ctx->smem_optin) { set_error("opz_loss_grad: layer too wide for the GEMM tile"); return OPZ_EUNSUP; }
+  OPZ_CUDA(cudaFuncSetAttribute(skinny_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+  OPZ_CUDA(cudaFuncSetAttribute(skinny_kernel<MODE_BWD_HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+  OPZ_CUDA(cudaFuncSetAttribute(skinny_kernel<MODE_BWD_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+  const int OP = (3 * nout + 31) / 32 * 32;
+  int ff_threads = std::max(OP, std::min(1024, OP * 4));
+  ff_threads = std::max(ff_threads, (S3 + 31) / 32 * 32);
+  if (ff_threads > 1024) { set_error("opz_loss_grad: nz too large"); return OPZ_EUNSUP; }
+  const int nh = nd.sizes[L - 1];
+  const size_t ff_smem = sizeof(float) * ((size_t)3 * nh + (size_t)(ff_threads / OP) * OP + S3 + 3 * (size_t)(nz + 1));
+  const size_t fb_smem = sizeof(float) * ((size_t)2 * S3 + 3 * (size_t)nout + 3 * (size_t)(nz + 1));
+  OPZ_CUDA(cudaFuncSetAttribute(final_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem));
+  const int fb_threads = std::min(1024, std::max(256, (S3 + 31) / 32 * 32));
+
+  int64_t step_kernels_fwd = 0, step_kernels_bwd = 0;
+  auto enqueue_fwd_step = [&](const Args& aa, int dn, cudaStream_t s) {
+    for (int sg = 0; sg < stages; ++sg) {
+      for (int l = 0; l < L - 1; ++l) {
+        dim3 g((nd.sizes[l + 1] + kNT - 1) / kNT, n_ct, 3);
+        skinny_kernel<MODE_FWD><<<g, kGemmThreads, gemm_smem, s>>>(aa, l, sg, dn);
+      }
+      final_fwd_kernel<<<(unsigned)B, ff_threads, ff_smem, s>>>(aa, sg, dn);
+    }
+  };
+  step_kernels_fwd = (int64_t)stages * L;
+  auto enqueue_bwd_step = [&](const Args& aa, int dn, cudaStream_t s) {
+    for (int sg = stages - 1; sg >= 0; --sg) {
+      first_bwd_kernel<<<(unsigned)B, fb_threads, fb_smem, s>>>(aa, sg, dn);
+      for (int l = L - 2; l >= 1; --l) {
+        dim3 g((nd.sizes[l] + kNT - 1) / kNT, n_ct, 3);
+        skinny_kernel<MODE_BWD_HID><<<g, kGemmThreads, gemm_smem, s>>>(aa, l, sg, dn);
+      }
+      dim3 g((S3 + kNT - 1) / kNT, n_ct, 1);
+      skinny_kernel<MODE_BWD_IN><<<g, kGemmThreads, gemm_smem, s>>>(aa, 0, sg, dn);
+    }
+  };
+  step_kernels_bwd = (int64_t)stages * L;
+
+  // ---- graphs: U unrolled steps + cursor bump, captured on a private stream ----
+  if (!ctx->capture_stream) OPZ_CUDA(cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = ctx->capture_stream;
+  auto build = [&](bool forward, const Args& aa, int U, GraphPair& out) -> int {
+    cudaGraph_t graph = nullptr;
+    OPZ_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    for (int u = 0; u < U; ++u) {
+      if (forward) enqueue_fwd_step(aa, u, cs);
+      else enqueue_bwd_step(aa, -u, cs);
+    }
+    bump_cursor_kernel<<<1, 1, 0, cs>>>(cur_dev, forward ? U : -U);
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&out.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+    out.steps = U;
+    out.kernels = (forward ? step_kernels_fwd : step_kernels_bwd) * U + 1;
+    return OPZ_OK;
+  };
+  int U = 16;
+  if (const char* e = getenv("OPZ_BPTT_GRAPH_STEPS")) U = std::max(1, atoi(e));
+  U = std::min(U, std::max(1, n_steps));
+  BpttCache* cache = static_cast<BpttCache*>(ctx->bptt_cache);
+  if (!cache) { cache = new BpttCache(); ctx->bptt_cache = cache; }
+  GraphPair &gf_rec_U = cache->fwd_rec_U, &gf_rec_1 = cache->fwd_rec_1, &gf_ring_U = cache->fwd_ring_U,
+            &gf_ring_1 = cache->fwd_ring_1, &gb_U = cache->bwd_U, &gb_1 = cache->bwd_1;
+  auto cleanup = [&]() { cudaStreamSynchronize(st); cache->clear(); };
+  Args a_rec = a; a_rec.record = 1;
+  Args a_ring = a; a_ring.record = 0;
+  if (n_steps > 0 && !(cache->valid && cache->U == U && std::memcmp(&cache->key, &a, sizeof(Args)) == 0)) {
+    OPZ_CUDA(cudaStreamSynchronize(st));  // graphs of an earlier call may still be in flight
+    cache->clear();
+    if ((rc = build(true, a_rec, U, gf_rec_U)) || (rc = build(true, a_rec, 1, gf_rec_1)) ||
+        (rc = build(false, a_rec, U, gb_U)) || (rc = build(false, a_rec, 1, gb_1))) { cleanup(); return rc; }
+    if (!single && ((rc = build(true, a_ring, U, gf_ring_U)) || (rc = build(true, a_ring, 1, gf_ring_1)))) { cleanup(); return rc; }
+    std::memcpy(&cache->key, &a, sizeof(Args));
+    cache->U = U;
+    cache->valid = true;
+  }
+  auto run_steps = [&](GraphPair& gU, GraphPair& g1, int count) -> int {
+    while (count > 0) {
+      GraphPair& g = count >= gU.steps ? gU : g1;
+      cudaError_t e = cudaGraphLaunch(g.exec, st);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+      ctx->launches += g.kernels;
+      count -= g.steps;
+    }
+    return OPZ_OK;
+  };
+  auto set_cursor = [&](int n, int seg_n0) {
+    set_cursor_kernel<<<1, 1, 0, st>>>(cur_dev, n, seg_n0);
+    ctx->launches += 1;
+  };
+
+  // ---- forward sweep ----
+  OPZ_CUDA(cudaMemcpyAsync(XN, c.r.x0, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
+  OPZ_CUDA(cudaMemcpyAsync(a.X, c.r.x0, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
+  set_cursor(0, 0);
+  if (single) rc = run_steps(gf_rec_U, gf_rec_1, n_steps);
+  else rc = run_steps(gf_ring_U, gf_ring_1, n_steps);
+  if (rc) { cleanup(); return rc; }
+
+  // ---- loss ----
+  loss_partial_kernel<<<(unsigned)B, 128, 0, st>>>(a);
+  loss_final_kernel<<<1, 32, 0, st>>>(a);
+  init_lambda_kernel<<<(unsigned)((B * S3 + 255) / 256), 256, 0, st>>>(a);
+  ctx->launches += 3;
+
+  // ---- backward sweep, segment by segment ----
+  auto dw_all = [&](int64_t rows) -> int {
+    for (int l = 0; l < L; ++l) {
+      const int K = nd.sizes[l], N = nd.sizes[l + 1];
+      const float* Aop = l == 0 ? a.X : a.H[l - 1];
+      const int64_t a_net = l == 0 ? 0 : rows_cap * (int64_t)K;
+      const float* Dop = l == L - 1 ? a.DY : a.G[l];
+      const int64_t d_net = rows_cap * (int64_t)N;
+      const int tiles = ((K + kTK - 1) / kTK) * ((N + kTN - 1) / kTN) * 3;
+      int split = (4 * ctx->sm_count + tiles - 1) / tiles;
+      split = (int)std::max<int64_t>(1, std::min<int64_t>(split, rows / 256));
+      dim3 g((K + kTK - 1) / kTK, (N + kTN - 1) / kTN, 3 * split);
+      dw_kernel<<<g, 256, 0, st>>>(Aop, a_net, K, Dop, d_net, N, K, N, rows, split, c.grad_out + nd.w_off[l],
+                                   c.grad_out + nd.b_off[l], nd.P);
+      ctx->launches += 1;
+    }
+    OPZ_CUDA(cudaGetLastError());
+    return OPZ_OK;
+  };
+  for (int64_t seg_end = n_steps; seg_end > 0;) {
+    const int64_t seg_n0 = std::max<int64_t>(0, seg_end - seg_steps);
+    const int len = (int)(seg_end - seg_n0);
+    if (!single) {  // recompute this segment's forward with records
+      OPZ_CUDA(cudaMemcpyAsync(a.X, XN + (size_t)seg_n0 * B * S3, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
+      set_cursor((int)seg_n0, (int)seg_n0);
+      if ((rc = run_steps(gf_rec_U, gf_rec_1, len))) { cleanup(); return rc; }
+    }
+    set_cursor((int)seg_end - 1, (int)seg_n0);
+    if ((rc = run_steps(gb_U, gb_1, len))) { cleanup(); return rc; }
+    if ((rc = dw_all((int64_t)len * stages * B))) { cleanup(); return rc; }
+    seg_end = seg_n0;
+  }
+  OPZ_CUDA(cudaGetLastError());
+  return OPZ_OK;
+}
+
+}  // namespace opz

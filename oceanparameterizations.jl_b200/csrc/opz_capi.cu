@@ -99,6 +99,7 @@ int opz_ctx_destroy(opz_ctx* ctx) {
   if (!ctx) return OPZ_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  bptt_release(ctx);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

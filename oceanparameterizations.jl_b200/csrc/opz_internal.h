@@ -15,6 +15,10 @@ struct opz_ctx {
   // grow-only device scratch (staging of host buffers; BPTT checkpoints)
   void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // BPTT path (opz_bptt.cu): private stream for graph capture (the adopted stream may be the legacy
+  // default stream, which cannot be captured) and the cached graph executables
+  cudaStream_t capture_stream = nullptr;
+  void* bptt_cache = nullptr;
 };
 
 struct opz_model {
@@ -70,6 +74,7 @@ struct LossGradCall {
   float* grad_out;        // device [3P]
 };
 int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c);
+void bptt_release(opz_ctx* ctx);
 
 // tcgen05 tensor-core path (opz_tc.cu)
 int tc_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights

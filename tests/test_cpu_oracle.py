@@ -196,3 +196,44 @@ def test_autograd_twin_matches_oracle_and_finite_differences():
         fp[idx] += 1e-6
         fm[idx] -= 1e-6
         assert (L(fp) - L(fm)) / 2e-6 == pytest.approx(g[idx], rel=1e-5)
+
+
+@pytest.mark.parametrize("flags,scheme,sizes,act", [
+    (O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0, O.SCHEME_RK4, (96, 50, 20, 31), O.ACT_MISH),
+    (O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0, O.SCHEME_RK4, (96, 64, 31), O.ACT_RELU),
+    (O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_DIURNAL, O.SCHEME_RK2, (96, 40, 30, 31), O.ACT_SWISH),
+    (0, O.SCHEME_EULER, (96, 40, 30, 20, 31), O.ACT_TANH),
+])
+def test_hand_adjoint_matches_autograd_twin(flags, scheme, sizes, act):
+    """oracle/nde_adjoint.py (the recurrences the CUDA BPTT kernels implement) against torch.autograd."""
+    from oracle import nde_adjoint as A
+    from oracle import nde_oracle_torch as OT
+    p = O.Params(flags=flags)
+    B = 5
+    x0, bc = O.synthetic_columns(B, p, dtype=np.float64, diurnal=True)
+    x0 = x0 + 0.05 * np.random.default_rng(1).normal(size=x0.shape)
+    m = O.make_model(sizes, act, seed=1, out_scale=0.1, dtype=np.float64)
+    dt, n_steps, se = 30.0 / p.tau, 12, 4
+    tgt = O.rollout(x0, bc, O.make_model(sizes, act, seed=2, out_scale=0.1, dtype=np.float64), p, scheme, dt, n_steps, se)
+    lw = [1, 0.7, 1.3, 5e-3, 4e-3, 6e-3]
+    L1, c1, g1 = OT.loss_and_grad(x0, bc, m, p, scheme, dt, n_steps, se, tgt, lw, B_total=7)
+    L2, c2, g2 = A.loss_and_grad(x0, bc, m, p, scheme, dt, n_steps, se, tgt, lw, B_total=7)
+    assert L2 == pytest.approx(L1, rel=1e-12)
+    assert np.allclose(c1, c2, rtol=1e-12, atol=0)
+    assert np.linalg.norm(g1 - g2) <= 1e-12 * np.linalg.norm(g1)
+
+
+def test_bptt_fixture_pins_the_adjoint(golden_dir):
+    """The committed gradient fixture (generated by the autograd twin) against the hand adjoint in float64
+    and float32: the latter is the noise floor the FP32 CUDA path is judged against."""
+    from oracle import nde_adjoint as A
+    g = np.load(f"{golden_dir}/bptt_config4_small.npz")
+    p = O.Params(tau=float(g["tau"]), flags=int(g["flags"]))
+    m = O.make_model((96, 400, 400, 31), O.ACT_RELU, seed=int(g["seed"]), out_scale=float(g["out_scale"]))
+    args = (g["x0"], g["bc"], m, p, O.SCHEME_RK4, float(g["dt_nd"]), int(g["n_steps"]), int(g["save_every"]), g["target"], g["loss_w"])
+    t64, _, g64 = A.loss_and_grad(*args, dtype=np.float64)
+    assert t64 == pytest.approx(float(g["total"]), rel=1e-9)
+    assert np.linalg.norm(g64 - g["grad"]) <= 1e-6 * np.linalg.norm(g["grad"])
+    t32, _, g32 = A.loss_and_grad(*args, dtype=np.float32)
+    assert t32 == pytest.approx(float(g["total"]), rel=1e-4)
+    assert np.linalg.norm(g32 - g["grad"]) <= 1e-3 * np.linalg.norm(g["grad"])

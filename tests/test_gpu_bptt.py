@@ -1,0 +1,176 @@
+"""GPU parity of opz_loss_grad (loss + exact discrete-adjoint gradient, FP32) against the float64
+autograd twin (oracle/nde_oracle_torch.py) and the committed gradient fixture.  Everything goes
+through the C ABI.  Tolerance (north_star): gradients within 1e-3 relative (L2)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import product_model, product_params
+
+pytestmark = pytest.mark.gpu
+
+TOL_GRAD = 1e-3
+TOL_LOSS = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx(opz):
+    return opz.default_context()
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _case(oracle, flags, sizes, act, B, n_steps, save_every, seed=1, tau=172800.0, dt_s=30.0, diurnal=False, jitter=0.02):
+    p = oracle.Params(flags=flags, tau=tau)
+    x0, bc = oracle.synthetic_columns(B, p, diurnal=diurnal)
+    rng = np.random.default_rng(seed)
+    x0 = (x0 + jitter * rng.normal(size=x0.shape)).astype(np.float32)
+    m = oracle.make_model(sizes, act, seed=seed, out_scale=0.1)
+    m_true = oracle.make_model(sizes, act, seed=seed + 100, out_scale=0.1)
+    dt = dt_s / p.tau
+    return p, x0, bc, m, m_true, dt
+
+
+@pytest.mark.parametrize("name,flags,sizes,act,scheme,B", [
+    ("training_small_mish_rk4", "train", (96, 50, 20, 31), 3, 2, 5),
+    ("inference_ca_relu_rk4", "infer", (96, 400, 400, 31), 1, 2, 18),
+    ("two_layer_swish_heun_diurnal", "diurnal", (96, 400, 31), 4, 1, 7),
+    ("four_layer_tanh_euler_nn_only", "none", (96, 40, 30, 20, 31), 2, 0, 3),
+    ("leakyrelu_ragged_two_column_tiles", "train", (96, 64, 48, 31), 5, 2, 37),
+])
+def test_loss_grad_matches_autograd_twin(opz, oracle, ctx, name, flags, sizes, act, scheme, B):
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    fl = {"train": O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0,
+          "infer": O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0,
+          "diurnal": O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_DIURNAL,
+          "none": 0}[flags]
+    n_steps, save_every = 12, 4
+    p, x0, bc, m, m_true, dt = _case(O, fl, sizes, act, B, n_steps, save_every, diurnal=(flags == "diurnal"))
+    target = O.rollout(x0, bc, m_true, p, scheme, dt, n_steps, save_every)
+    lw = np.array([1.0, 0.7, 1.3, 5e-3, 4e-3, 6e-3], dtype=np.float32)
+    model = product_model(opz, m)
+    n0 = ctx.launch_count
+    total, comps, grad = opz.loss_grad(model, product_params(opz, p), x0, bc, target, lw, scheme, dt, n_steps, save_every,
+                                       B_total=B + 2)
+    assert ctx.launch_count > n0
+    tr, cr, gr = OT.loss_and_grad(x0, bc, m, p, scheme, dt, n_steps, save_every, target, lw, B_total=B + 2)
+    assert np.isfinite(grad).all()
+    assert abs(total - tr) <= TOL_LOSS * abs(tr), (name, total, tr)
+    assert np.allclose(comps, cr, rtol=2e-4, atol=1e-4 * abs(tr)), (name, comps, cr)
+    assert _rel_l2(grad, gr) < TOL_GRAD, (name, _rel_l2(grad, gr))
+    # per net and per layer block as well: a wrong small block must not hide behind a large one
+    P = m.P
+    off = 0
+    for i in range(len(sizes) - 1):
+        for n_el in (sizes[i] * sizes[i + 1], sizes[i + 1]):
+            for net in range(3):
+                sl = slice(net * P + off, net * P + off + n_el)
+                if np.linalg.norm(gr[sl]) > 1e-12 * np.linalg.norm(gr):
+                    assert _rel_l2(grad[sl], gr[sl]) < 5e-3, (name, "layer", i, "net", net, _rel_l2(grad[sl], gr[sl]))
+            off += n_el
+    model.close()
+
+
+def test_config4_fixture(opz, oracle, golden_dir, ctx):
+    """Shortened BASELINE configs[3] step (18 cases, construct_NN) against the committed float64 fixture."""
+    g = np.load(os.path.join(golden_dir, "bptt_config4_small.npz"))
+    O = oracle
+    p = O.Params(tau=float(g["tau"]), flags=int(g["flags"]))
+    m = O.make_model((96, 400, 400, 31), O.ACT_RELU, seed=int(g["seed"]), out_scale=float(g["out_scale"]))
+    model = product_model(opz, m)
+    total, comps, grad = opz.loss_grad(model, product_params(opz, p), g["x0"], g["bc"], g["target"], g["loss_w"],
+                                       opz.SCHEME_RK4, float(g["dt_nd"]), int(g["n_steps"]), int(g["save_every"]))
+    assert abs(total - float(g["total"])) <= TOL_LOSS * float(g["total"])
+    assert _rel_l2(grad, g["grad"]) < TOL_GRAD, _rel_l2(grad, g["grad"])
+    model.close()
+
+
+def test_segmented_recompute_equals_single_segment(opz, oracle, ctx, monkeypatch):
+    O = oracle
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    n_steps, save_every, B = 21, 7, 6
+    p, x0, bc, m, m_true, dt = _case(O, fl, (96, 50, 20, 31), 3, B, n_steps, save_every, seed=4)
+    target = O.rollout(x0, bc, m_true, p, 2, dt, n_steps, save_every)
+    lw = np.array([1, 1, 1, 0, 0, 0], dtype=np.float32)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    t1, c1, g1 = opz.loss_grad(model, pp, x0, bc, target, lw, 2, dt, n_steps, save_every)
+    # budget for 5 time steps of records -> segments of 5, 5, 5, 5, 1 steps, forward sweep without records
+    rec_floats = 96 + 3 * 31 + 6 * (50 + 20)
+    monkeypatch.setenv("OPZ_BPTT_RECORD_BYTES", str(4 * rec_floats * B * 4 * 5 + 64))
+    monkeypatch.setenv("OPZ_BPTT_GRAPH_STEPS", "3")
+    t2, c2, g2 = opz.loss_grad(model, pp, x0, bc, target, lw, 2, dt, n_steps, save_every)
+    assert t1 == pytest.approx(t2, rel=1e-6)
+    assert _rel_l2(g2, g1) < 1e-5
+    model.close()
+
+
+def test_gradient_is_additive_over_column_shards(opz, oracle, ctx):
+    """The multi-GPU contract: each rank passes its shard with B_total = global batch; the all-reduce is a sum."""
+    O = oracle
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    n_steps, save_every, B = 8, 4, 18
+    p, x0, bc, m, m_true, dt = _case(O, fl, (96, 50, 20, 31), 3, B, n_steps, save_every, seed=6)
+    target = O.rollout(x0, bc, m_true, p, 2, dt, n_steps, save_every)
+    lw = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    t, c, g = opz.loss_grad(model, pp, x0, bc, target, lw, 2, dt, n_steps, save_every)
+    ts, gs = 0.0, np.zeros_like(g)
+    for lo, hi in ((0, 7), (7, 7), (7, 18)):  # one empty shard
+        ti, ci, gi = opz.loss_grad(model, pp, x0[lo:hi], bc[lo:hi], target[lo:hi], lw, 2, dt, n_steps, save_every, B_total=B)
+        ts += ti
+        gs += gi
+    assert ts == pytest.approx(t, rel=1e-5)
+    assert _rel_l2(gs, g) < 1e-5
+    model.close()
+
+
+def test_gradient_descends_the_loss(opz, oracle, ctx):
+    """A few ADAM steps through the reference-shaped host loop reduce the profile loss."""
+    O = oracle
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    n_steps, save_every, B = 16, 4, 6
+    p, x0, bc, m, m_true, dt = _case(O, fl, (96, 50, 20, 31), 3, B, n_steps, save_every, seed=8)
+    target = O.rollout(x0, bc, m_true, p, 2, dt, n_steps, save_every)
+    lw = np.array([1, 1, 1, 0, 0, 0], dtype=np.float32)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    w = model.get_weights()
+    opt = opz.ADAM(1e-3)
+    losses = []
+    for _ in range(6):
+        model.set_weights(w)
+        t, _, g = opz.loss_grad(model, pp, x0, bc, target, lw, 2, dt, n_steps, save_every)
+        losses.append(t)
+        w = opt.apply(w, g)
+    assert losses[-1] < losses[0]
+    model.close()
+
+
+def test_loss_grad_rejects_unsupported(opz, oracle, ctx):
+    O = oracle
+    m = O.make_model((96, 31), 0, seed=0)
+    model = product_model(opz, m)
+    p = O.Params()
+    x0, bc = O.synthetic_columns(2, p)
+    tgt = np.zeros((2, 2, 96), dtype=np.float32)
+    lw = np.ones(6, dtype=np.float32)
+    with pytest.raises(opz.OpzError) as e:
+        opz.loss_grad(model, product_params(opz, p), x0, bc, tgt, lw, 2, 1e-4, 2, 2)
+    assert e.value.code == opz.OPZ_EUNSUP
+    model.close()
+    m2 = O.make_model((96, 50, 31), 1, seed=0)
+    model2 = product_model(opz, m2)
+    p2 = O.Params(flags=O.FLAG_MPP | O.FLAG_SMOOTH_NN)
+    with pytest.raises(opz.OpzError) as e:
+        opz.loss_grad(model2, product_params(opz, p2), x0, bc, tgt, lw, 2, 1e-4, 2, 2)
+    assert e.value.code == opz.OPZ_EUNSUP
+    with pytest.raises(opz.OpzError):  # n_steps not a multiple of save_every
+        opz.loss_grad(model2, product_params(opz, p), x0, bc, np.zeros((2, 2, 96), np.float32), lw, 2, 1e-4, 3, 2)
+    model2.close()
