@@ -153,6 +153,79 @@ def config_dict(args, columns_per_gpu):
     }
 
 
+BPTT_CASES = 18
+BPTT_DT_SECONDS = 60.0
+BPTT_SAVE_EVERY = 90   # 5400 s between training snapshots = `1:9:1153` of the 600 s data (train_NDE_args.jl:195)
+BPTT_STEPS = 11520     # 8 days
+
+
+def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
+    """BPTT grad-steps/s: loss + exact discrete-adjoint gradient over the 18 synthetic forcing cases
+    (construct_NN, training-flavour RHS: mPP with eps, zero_weights boundary form, RK4 dt = 60 s, 8 days,
+    129 snapshots, profile + gradient loss), cases sharded over the ranks, gradient + loss all-reduced (sum)."""
+    from helpers import product_model, product_params
+    from oracle import nde_oracle as O  # synthetic inputs only
+    p = O.Params(tau=TAU, flags=O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0)
+    x0, bc = O.synthetic_columns(BPTT_CASES, p)
+    m = O.make_model(SIZES, O.ACT_RELU, seed=0, out_scale=0.1)
+    model = product_model(opz, m, ctx=ctx)
+    pp = product_params(opz, p)
+    dt = BPTT_DT_SECONDS / p.tau
+    n_save = BPTT_STEPS // BPTT_SAVE_EVERY + 1
+    # targets: the initial profiles relaxed towards a mixed state (the LES data is not available offline);
+    # their values do not change the work done
+    target = np.repeat(x0[:, None, :], n_save, axis=1).astype(np.float32)
+    lo, hi = opz.shard_range(BPTT_CASES, rank, world)
+    nb = hi - lo
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xd = torch.from_numpy(x0[lo:hi].copy()).to(dev) if nb else torch.zeros((1, 96), device=dev)
+    bd = torch.from_numpy(bc[lo:hi].copy()).to(dev) if nb else torch.zeros((1, 8), device=dev)
+    td = torch.from_numpy(target[lo:hi].copy()).to(dev) if nb else torch.zeros((1, n_save, 96), device=dev)
+    P3 = 3 * model.P
+    buf = torch.zeros(P3 + 8, device=dev)
+    lw = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+
+    def step():
+        opz.loss_grad_dev(model, pp, xd.data_ptr(), bd.data_ptr(), nb, BPTT_CASES, td.data_ptr(), lw, opz.SCHEME_RK4, dt,
+                          BPTT_STEPS, BPTT_SAVE_EVERY, buf.data_ptr() + 4 * P3, buf.data_ptr())
+        if dist is not None:
+            dist.all_reduce(buf)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step()  # warm-up: allocates the record buffers and builds the graphs
+    barrier()
+    n0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.bptt_steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / args.bptt_steps
+    launches = (ctx.launch_count - n0) // args.bptt_steps
+    if dist is not None:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+    loss = float(buf[P3].item())
+    gnorm = float(buf[:P3].norm().item())
+    model.close()
+    # algorithmic FLOPs (SURVEY 8d): forward sweep + backward (dX and dW) = 3 x stages x F_rhs per column-step
+    flops = 3.0 * STAGES * FLOP_PER_RHS * BPTT_CASES * BPTT_STEPS
+    return {"metric": "BPTT grad-steps/sec", "value": 1e3 / ms, "unit": "grad-steps/s", "ms_per_grad_step": ms,
+            "scaling": "strong", "cases": BPTT_CASES, "cases_this_rank": nb, "timesteps": BPTT_STEPS, "scheme": "RK4",
+            "dt_seconds": BPTT_DT_SECONDS, "snapshots": n_save, "precision": "fp32", "timed_steps": args.bptt_steps,
+            "gpu_launches_per_step": int(launches), "loss": loss, "grad_norm": gnorm,
+            "finite": bool(np.isfinite(loss) and np.isfinite(gnorm)),
+            "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+            "collective": "none (1 GPU)" if dist is None else f"NCCL all-reduce(sum) of {P3 + 8} fp32 per step",
+            "note": "latency-bound: 18 columns x 46080 sequential right-hand sides; see DESIGN.md section 6"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +238,8 @@ def main():
     ap.add_argument("--ref-columns", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bptt", action="store_true", help="skip the BPTT grad-steps/s leg")
+    ap.add_argument("--bptt-steps", type=int, default=2, help="timed gradient steps of the BPTT leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -264,6 +339,11 @@ def main():
         e2e_ms = (time.perf_counter() - t) * 1e3 / e_steps
         e2e = {"ms": e2e_ms, "h2d": int(x0.nbytes + bc.nbytes), "d2h": int(x0.nbytes)}
 
+    # ---- BPTT leg: BASELINE configs[3], 18 cases sharded over the ranks, one NCCL all-reduce per step ----
+    bptt = None
+    if not args.no_bptt:
+        bptt = run_bptt(args, opz, ctx, torch, dist, rank, world, stream)
+
     # ---- max over ranks ----
     t_ms = total_ms
     e_ms = e2e["ms"] if e2e else 0.0
@@ -299,6 +379,8 @@ def main():
     if e2e:
         line["e2e"] = {"value": colsteps_per_step / (e_ms * 1e-3), "unit": "column-timesteps/s",
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e_ms}
+    if bptt:
+        line["bptt"] = bptt
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as CO
         cores = CO.max_threads()

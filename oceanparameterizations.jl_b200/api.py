@@ -436,6 +436,18 @@ def loss_grad(model: NDEModel, params: L.OpzParams, x0, bc, target, loss_w, sche
     return float(loss_out[0]), loss_out[1:].copy(), grad
 
 
+def loss_grad_dev(model: NDEModel, params: L.OpzParams, x0_ptr: int, bc_ptr: int, B: int, B_total: int, target_ptr: int,
+                  loss_w, scheme: int, dt_nd: float, n_steps: int, save_every: int, loss_out_ptr: int, grad_out_ptr: int, *,
+                  t0: float = 0.0, precision: int = L.PREC_FP32) -> None:
+    """Device-pointer variant of loss_grad: loss_out[7] and grad_out[3P] are DEVICE buffers (e.g. one torch
+    tensor that the caller then all-reduces over NCCL); enqueues on the context's stream and returns."""
+    lw = _f32(loss_w, (6,))
+    L.check(L.lib.opz_loss_grad_dev(model.ctx._h, model._h, C.byref(params), C.c_void_p(x0_ptr), C.c_void_p(bc_ptr), int(B),
+                                    int(B_total), scheme, float(dt_nd), float(t0), int(n_steps), int(save_every),
+                                    C.c_void_p(target_ptr), _fptr(lw), precision, C.c_void_p(loss_out_ptr),
+                                    C.c_void_p(grad_out_ptr)))
+
+
 def mlp_forward(model: NDEModel, which_net: int, x, precision: int = L.PREC_FP32) -> np.ndarray:
     x = _f32(x)
     y = np.empty((x.shape[0], model.Nz - 1), dtype=np.float32)

@@ -25,6 +25,7 @@
 //
 // The recurrences are the ones restated and checked against autograd in oracle/nde_adjoint.py.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -38,6 +39,9 @@ constexpr int kNT = 16;        // units per CTA
 constexpr int kKS = 16;        // split of the reduction dimension inside a CTA
 constexpr int kGemmThreads = kNT * kKS;
 constexpr int kMaxStages = 4;
+constexpr int kWR = 32;                  // weight registers per thread and chunk
+constexpr int kFW = 40;                  // last-layer weight registers per thread (final_fwd_kernel)
+constexpr int kChunk = kWR * kKS;      // inputs per staged chunk (512)
 
 struct Cursor {
   int n;        // base time step of the graph launch in flight
@@ -96,62 +100,86 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_kernel(const __grid_const
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
   const int nl = tid % kNT, ks = tid / kNT;
-  const int n = a.cur->n + dn;
-  const int q = rec_index(a, n, stage);
-  const int64_t col0 = (int64_t)blockIdx.y * kCT;
-  const int ncols = (int)min((int64_t)kCT, a.B - col0);
-  const int64_t r0 = (int64_t)q * a.B + col0;
   const int net0 = (MODE == MODE_BWD_IN) ? 0 : blockIdx.z;
   const int nsum = (MODE == MODE_BWD_IN) ? 3 : 1;
-
   int I, J;
   if (MODE == MODE_FWD) { I = a.nd.sizes[layer]; J = a.nd.sizes[layer + 1]; }
   else if (MODE == MODE_BWD_HID) { I = a.nd.sizes[layer + 1]; J = a.nd.sizes[layer]; }   // dz_layer -> dz_{layer-1}
   else { I = a.nd.sizes[1]; J = a.S3; }
-  float* As = sm;                 // [I][kCT]
-  float* red = sm + (size_t)I * kCT;  // [kKS][kCT][kNT]
+  const int Ic_max = min(I, kChunk);
+  float* As = sm;                          // [min(I, kChunk)][kCT]
+  float* red = sm + (size_t)Ic_max * kCT;  // [kKS][kCT][kNT]
   const int j = blockIdx.x * kNT + nl;
 
   float acc[kCT];
 #pragma unroll
   for (int c = 0; c < kCT; ++c) acc[c] = 0.0f;
 
+  // The weights do not depend on the step: their loads are issued first so that their L2 latency
+  // overlaps the cursor read and the staging of the activations.
+  float wreg[kWR];
+  auto weights_of = [&](int net) -> const float* {
+    if (MODE == MODE_FWD) return a.w + (int64_t)net * a.nd.P + a.nd.w_off[layer];
+    return a.wT + (int64_t)net * a.wT_net + a.wT_off[MODE == MODE_BWD_HID ? layer : 0];
+  };
+  auto fetch_w = [&](int net, int i0) {
+    const float* M = weights_of(net);
+#pragma unroll
+    for (int r = 0; r < kWR; ++r) {
+      const int i = i0 + ks + r * kKS;
+      wreg[r] = (i < I && j < J) ? __ldg(M + (size_t)i * J + j) : 0.0f;
+    }
+  };
+  fetch_w(net0, 0);
+
+  const int n = a.cur->n + dn;
+  const int q = rec_index(a, n, stage);
+  const int64_t col0 = (int64_t)blockIdx.y * kCT;
+  const int ncols = (int)min((int64_t)kCT, a.B - col0);
+  const int64_t r0 = (int64_t)q * a.B + col0;
+
+  bool first = true;
   for (int ns = 0; ns < nsum; ++ns) {
     const int net = net0 + ns;
     const float* A;
     int lda;
-    const float* M;
     if (MODE == MODE_FWD) {
       if (layer == 0) { A = a.X + r0 * a.S3; lda = a.S3; }
       else { lda = a.nd.sizes[layer]; A = a.H[layer - 1] + ((int64_t)net * a.rows_cap + r0) * lda; }
-      M = a.w + (int64_t)net * a.nd.P + a.nd.w_off[layer];
     } else if (MODE == MODE_BWD_HID) {
       lda = I;
       A = a.G[layer] + ((int64_t)net * a.rows_cap + r0) * lda;
-      M = a.wT + (int64_t)net * a.wT_net + a.wT_off[layer];
     } else {
       lda = I;
       A = a.G[0] + ((int64_t)net * a.rows_cap + r0) * lda;
-      M = a.wT + (int64_t)net * a.wT_net + a.wT_off[0];
     }
-    if (ns > 0) __syncthreads();
-    for (int e = tid; e < I * kCT; e += kGemmThreads) {
-      const int c = e / I, i = e - c * I;
-      As[i * kCT + c] = c < ncols ? A[(int64_t)c * lda + i] : 0.0f;
-    }
-    __syncthreads();
-    if (j < J) {
-#pragma unroll 5
-      for (int i = ks; i < I; i += kKS) {
-        const float wv = __ldg(M + (size_t)i * J + j);
-        const float4* ap = reinterpret_cast<const float4*>(As + i * kCT);
+    for (int i0 = 0; i0 < I; i0 += kChunk) {
+      const int Ic = min(kChunk, I - i0);
+      if (!first) {
+        __syncthreads();  // the previous chunk's As has been consumed
+        fetch_w(net, i0);
+      }
+      first = false;
+#pragma unroll 8
+      for (int e = tid; e < Ic * kCT; e += kGemmThreads) {
+        const int c = e / Ic, i = e - c * Ic;
+        As[i * kCT + c] = c < ncols ? A[(int64_t)c * lda + i0 + i] : 0.0f;
+      }
+      __syncthreads();
 #pragma unroll
-        for (int v = 0; v < kCT / 4; ++v) {
-          const float4 a4 = ap[v];
-          acc[4 * v + 0] = fmaf(wv, a4.x, acc[4 * v + 0]);
-          acc[4 * v + 1] = fmaf(wv, a4.y, acc[4 * v + 1]);
-          acc[4 * v + 2] = fmaf(wv, a4.z, acc[4 * v + 2]);
-          acc[4 * v + 3] = fmaf(wv, a4.w, acc[4 * v + 3]);
+      for (int r = 0; r < kWR; ++r) {
+        const int il = ks + r * kKS;
+        if (il < Ic) {
+          const float wv = wreg[r];
+          const float4* ap = reinterpret_cast<const float4*>(As + il * kCT);
+#pragma unroll
+          for (int v = 0; v < kCT / 4; ++v) {
+            const float4 a4 = ap[v];
+            acc[4 * v + 0] = fmaf(wv, a4.x, acc[4 * v + 0]);
+            acc[4 * v + 1] = fmaf(wv, a4.y, acc[4 * v + 1]);
+            acc[4 * v + 2] = fmaf(wv, a4.z, acc[4 * v + 2]);
+            acc[4 * v + 3] = fmaf(wv, a4.w, acc[4 * v + 3]);
+          }
         }
       }
     }
@@ -224,10 +252,22 @@ __global__ void __launch_bounds__(1024) final_fwd_kernel(const __grid_constant__
   float* xs = ypart + KSL * OP;              // [S3]
   float* Fs = xs + S3;                       // [3][nz+1]
   const int64_t col = blockIdx.x;
+  // last-layer weights first (independent of the step), then the cursor and the activations
+  const int o = tid % OP, ksl = tid / OP;
+  const bool live = ksl < KSL && o < 3 * nout;
+  const int onet = live ? o / nout : 0, oj = live ? o - onet * nout : 0;
+  const float* Wl = a.w + (int64_t)onet * a.nd.P + a.nd.w_off[L - 1] + oj;
+  float wreg[kFW];
+#pragma unroll
+  for (int r = 0; r < kFW; ++r) {
+    const int k = ksl + r * KSL;
+    wreg[r] = (live && k < nh) ? __ldg(Wl + (size_t)k * nout) : 0.0f;
+  }
   const int n = a.cur->n + dn;
   const int q = rec_index(a, n, stage);
   const int64_t row = (int64_t)q * a.B + col;
 
+#pragma unroll 4
   for (int e = tid; e < 3 * nh; e += nthr) {
     const int net = e / nh, k = e - net * nh;
     hs[e] = a.H[L - 2][((int64_t)net * a.rows_cap + row) * nh + k];
@@ -235,15 +275,14 @@ __global__ void __launch_bounds__(1024) final_fwd_kernel(const __grid_constant__
   for (int i = tid; i < S3; i += nthr) xs[i] = a.X[row * S3 + i];
   __syncthreads();
   {
-    const int o = tid % OP, ksl = tid / OP;
     float part = 0.0f;
-    if (ksl < KSL && o < 3 * nout) {
-      const int net = o / nout, j = o - net * nout;
-      const float* W = a.w + (int64_t)net * a.nd.P + a.nd.w_off[L - 1];
-      const float* hh = hs + net * nh;
-#pragma unroll 4
-      for (int k = ksl; k < nh; k += KSL) part = fmaf(hh[k], __ldg(W + (size_t)k * nout + j), part);
+    const float* hh = hs + onet * nh;
+#pragma unroll
+    for (int r = 0; r < kFW; ++r) {
+      const int k = ksl + r * KSL;
+      if (k < nh) part = fmaf(hh[k], wreg[r], part);
     }
+    for (int k = ksl + kFW * KSL; live && k < nh; k += KSL) part = fmaf(hh[k], __ldg(Wl + (size_t)k * nout), part);
     if (ksl < KSL) ypart[ksl * OP + o] = part;
   }
   __syncthreads();
@@ -379,15 +418,34 @@ __global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__
     else if (v == 1) xb += P.cor_u * P.s_v * kb[c];
     a.XPHYS[col * S3 + tid] = xb;
   }
-  // dz_{L-2} = (W_L dy) * act'(z_{L-2})   (in place over the act' record)
-  for (int e = tid; e < 3 * nh; e += nthr) {
-    const int net = e / nh, k = e - net * nh;
-    const float* W = a.w + (int64_t)net * a.nd.P + a.nd.w_off[L - 1] + (size_t)k * nout;
-    const float* d = dy + net * nout;
-    float s = 0.0f;
-    for (int j = 0; j < nout; ++j) s = fmaf(__ldg(W + j), d[j], s);
-    const int64_t o = ((int64_t)net * a.rows_cap + row) * nh + k;
-    a.G[L - 2][o] = s * a.G[L - 2][o];
+  // dz_{L-2} = (W_L dy) * act'(z_{L-2})   (in place over the act' record): one warp per weight row,
+  // lanes along the nout contiguous outputs, shuffle reduction
+  {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    for (int e0 = warp; e0 < 3 * nh; e0 += nwarp * 4) {
+      float s[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nwarp;
+        s[u] = 0.0f;
+        if (e < 3 * nh) {
+          const int net = e / nh, k = e - net * nh;
+          const float* W = a.w + (int64_t)net * a.nd.P + a.nd.w_off[L - 1] + (size_t)k * nout;
+          for (int j = lane; j < nout; j += 32) s[u] = fmaf(__ldg(W + j), dy[net * nout + j], s[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], sh);
+        const int e = e0 + u * nwarp;
+        if (lane == 0 && e < 3 * nh) {
+          const int net = e / nh, k = e - net * nh;
+          const int64_t o = ((int64_t)net * a.rows_cap + row) * nh + k;
+          a.G[L - 2][o] = s[u] * a.G[L - 2][o];
+        }
+      }
+    }
   }
 }
 
@@ -700,20 +758,20 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
 
   // ---- launch configuration ----
   const int n_ct = (int)((B + kCT - 1) / kCT);
-  const size_t gemm_smem = sizeof(float) * ((size_t)max_in * kCT + (size_t)kKS * kCT * kNT);
+  const size_t gemm_smem = sizeof(float) * ((size_t)std::min(max_in, kChunk) * kCT + (size_t)kKS * kCT * kNT);
   if ((int)gemm_smem > ctx->smem_optin) { set_error("opz_loss_grad: layer too wide for the GEMM tile"); return OPZ_EUNSUP; }
   OPZ_CUDA(cudaFuncSetAttribute(skinny_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
   OPZ_CUDA(cudaFuncSetAttribute(skinny_kernel<MODE_BWD_HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
   OPZ_CUDA(cudaFuncSetAttribute(skinny_kernel<MODE_BWD_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
   const int OP = (3 * nout + 31) / 32 * 32;
-  int ff_threads = std::max(OP, std::min(1024, OP * 4));
+  int ff_threads = std::max(OP, (1024 / OP) * OP);
   ff_threads = std::max(ff_threads, (S3 + 31) / 32 * 32);
   if (ff_threads > 1024) { set_error("opz_loss_grad: nz too large"); return OPZ_EUNSUP; }
   const int nh = nd.sizes[L - 1];
   const size_t ff_smem = sizeof(float) * ((size_t)3 * nh + (size_t)(ff_threads / OP) * OP + S3 + 3 * (size_t)(nz + 1));
   const size_t fb_smem = sizeof(float) * ((size_t)2 * S3 + 3 * (size_t)nout + 3 * (size_t)(nz + 1));
   OPZ_CUDA(cudaFuncSetAttribute(final_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem));
-  const int fb_threads = std::min(1024, std::max(256, (S3 + 31) / 32 * 32));
+  const int fb_threads = 1024;
 
   int64_t step_kernels_fwd = 0, step_kernels_bwd = 0;
   auto enqueue_fwd_step = [&](const Args& aa, int dn, cudaStream_t s) {
@@ -794,6 +852,10 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
     ctx->launches += 1;
   };
 
+  const bool prof = getenv("OPZ_BPTT_PROFILE") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (prof) for (auto& e : ev) cudaEventCreate(&e);
+  if (prof) cudaEventRecord(ev[0], st);
   // ---- forward sweep ----
   OPZ_CUDA(cudaMemcpyAsync(XN, c.r.x0, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
   OPZ_CUDA(cudaMemcpyAsync(a.X, c.r.x0, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
@@ -802,6 +864,7 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   else rc = run_steps(gf_ring_U, gf_ring_1, n_steps);
   if (rc) { cleanup(); return rc; }
 
+  if (prof) cudaEventRecord(ev[1], st);
   // ---- loss ----
   loss_partial_kernel<<<(unsigned)B, 128, 0, st>>>(a);
   loss_final_kernel<<<1, 32, 0, st>>>(a);
@@ -841,6 +904,16 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
     seg_end = seg_n0;
   }
   OPZ_CUDA(cudaGetLastError());
+  if (prof) {
+    cudaEventRecord(ev[3], st);
+    cudaEventSynchronize(ev[3]);
+    float f = 0, t = 0;
+    cudaEventElapsedTime(&f, ev[0], ev[1]);
+    cudaEventElapsedTime(&t, ev[0], ev[3]);
+    fprintf(stderr, "opz bptt profile: forward sweep %.2f ms, loss + backward + dW %.2f ms, segments %s, records %.2f GB\n", f,
+            t - f, single ? "1" : ">1", (double)(sizeof(float) * rec_floats * (size_t)rows_cap) / 1e9);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   return OPZ_OK;
 }
 

@@ -297,7 +297,8 @@ int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, con
   int rc = check_common(ctx, m, p);
   if (rc) return rc;
   if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
-  if (!x0 || !bc || !target || !loss_w || !loss_out || !grad_out) { set_error("null buffer"); return OPZ_EINVAL; }
+  // a rank that owns no columns (B == 0) still calls in and gets zeros for the all-reduce
+  if ((B > 0 && (!x0 || !bc || !target)) || !loss_w || !loss_out || !grad_out) { set_error("null buffer"); return OPZ_EINVAL; }
   if (save_every <= 0) { set_error("opz_loss_grad needs save_every > 0"); return OPZ_EINVAL; }
   if (B_total < B || B_total < 1) { set_error("B_total must be >= B and >= 1"); return OPZ_EINVAL; }
   if (precision != OPZ_PREC_FP32) { set_error("opz_loss_grad: only OPZ_PREC_FP32 so far"); return OPZ_EUNSUP; }
