@@ -601,6 +601,8 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
   }
 }
 
+#include "opz_bptt_cluster.cuh"
+
 }  // namespace bptt
 
 // ---- host orchestration ----------------------------------------------------------------------------------------
@@ -639,6 +641,90 @@ void bptt_release(opz_ctx* ctx) {
   if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
   ctx->capture_stream = nullptr;
 }
+
+namespace {
+
+// Shared-memory plan of the cluster kernel for CG columns per cluster; returns false if it cannot run.
+bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CG, bptt::cl::Layout& lay) {
+  using namespace bptt;
+  const int L = nd.n_layers, S3 = 3 * nz, nout = nz - 1, NO3 = 3 * nout;
+  std::memset(&lay, 0, sizeof(lay));
+  if (S3 * CG > cl::kThreads || NO3 * CG > cl::kThreads) return false;
+  int off = 0, ulmax = 0;
+  auto take = [&](int n) { const int o = off; off += (n + 3) / 4 * 4; return o; };
+  for (int l = 0; l < L - 1; ++l) {
+    const int UL = (nd.sizes[l + 1] + cl::kCS - 1) / cl::kCS;
+    if (3 * UL * CG > cl::kThreads) return false;
+    lay.UL[l] = UL;
+    ulmax = std::max(ulmax, UL);
+    lay.W[l] = take(3 * nd.sizes[l] * UL);
+    lay.bias[l] = take(3 * UL);
+    if (l <= L - 3) lay.hfull[l] = take(3 * nd.sizes[l + 1] * CG);
+  }
+  lay.W[L - 1] = take(3 * lay.UL[L - 2] * nout);
+  lay.bias[L - 1] = take(NO3);
+  lay.hs = take(3 * ulmax * CG);
+  lay.dzs = take(3 * ulmax * CG);
+  lay.part = take(cl::kThreads * CG);
+  lay.y = take(std::max(NO3, S3) * CG);
+  lay.dy = take(NO3 * CG);
+  lay.xn = take(S3 * CG); lay.xs = take(S3 * CG); lay.kacc = take(S3 * CG); lay.lam = take(S3 * CG);
+  lay.kbar = take(S3 * CG); lay.xsum = take(S3 * CG); lay.xphys = take(S3 * CG);
+  lay.Fs = take(3 * (nz + 1) * CG);
+  lay.recv_big_size = cl::kCS * 3 * ulmax * CG;
+  lay.recv_big = take(lay.recv_big_size * (L >= 4 ? 2 : 1));
+  lay.SL = (std::max(NO3, S3) * CG + cl::kCS - 1) / cl::kCS;
+  lay.recv_small = take(cl::kCS * lay.SL);
+  lay.rbase = take(cl::kCS);
+  lay.total = off;
+  return (size_t)off * sizeof(float) <= (size_t)ctx->smem_optin;
+}
+
+template <int CG>
+int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int64_t groups, int* max_active) {
+  using namespace bptt;
+  auto kern = cl::sweep_kernel<CG>;
+  const size_t smem = (size_t)lay.total * sizeof(float);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return OPZ_EUNSUP;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(std::max<int64_t>(groups, 1) * cl::kCS));
+  cfg.blockDim = dim3(cl::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl::kCS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    (void)cudaGetLastError();
+    return OPZ_EUNSUP;
+  }
+  *max_active = n;
+  if (groups == 0) return OPZ_OK;  // query only
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lay);
+  if (e != cudaSuccess) return cuda_fail(e, "cluster sweep launch");
+  ctx->launches += 1;
+  return OPZ_OK;
+}
+
+int dispatch_cluster(int CG, opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int64_t groups, int* max_active) {
+  switch (CG) {
+    case 1: return launch_cluster<1>(ctx, a, lay, groups, max_active);
+    case 2: return launch_cluster<2>(ctx, a, lay, groups, max_active);
+    case 3: return launch_cluster<3>(ctx, a, lay, groups, max_active);
+    default: return launch_cluster<4>(ctx, a, lay, groups, max_active);
+  }
+}
+
+}  // namespace
 
 int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   using namespace bptt;
@@ -746,6 +832,78 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   }
   for (int i = 0; i < 6; ++i) a.loss_w[i] = c.loss_w[i];
 
+  // weight gradient: one reduction GEMM per layer over all recorded right-hand sides
+  auto dw_all = [&](int64_t rows) -> int {
+    for (int l = 0; l < L; ++l) {
+      const int K = nd.sizes[l], N = nd.sizes[l + 1];
+      const float* Aop = l == 0 ? a.X : a.H[l - 1];
+      const int64_t a_net = l == 0 ? 0 : rows_cap * (int64_t)K;
+      const float* Dop = l == L - 1 ? a.DY : a.G[l];
+      const int64_t d_net = rows_cap * (int64_t)N;
+      const int tiles = ((K + kTK - 1) / kTK) * ((N + kTN - 1) / kTN) * 3;
+      int split = (4 * ctx->sm_count + tiles - 1) / tiles;
+      split = (int)std::max<int64_t>(1, std::min<int64_t>(split, rows / 256));
+      dim3 g((K + kTK - 1) / kTK, (N + kTN - 1) / kTN, 3 * split);
+      dw_kernel<<<g, 256, 0, st>>>(Aop, a_net, K, Dop, d_net, N, K, N, rows, split, c.grad_out + nd.w_off[l],
+                                   c.grad_out + nd.b_off[l], nd.P);
+      ctx->launches += 1;
+    }
+    OPZ_CUDA(cudaGetLastError());
+    return OPZ_OK;
+  };
+  const bool prof = getenv("OPZ_BPTT_PROFILE") != nullptr;
+
+  // ---- cluster path: the whole sweep of a column group inside one 16-CTA cluster (weights in shared memory) ----
+  if (single && n_steps > 0 && !getenv("OPZ_BPTT_NO_CLUSTER")) {
+    cl::Layout lay;
+    int CG = 0, max_active = 0;
+    // fewest columns per cluster that still lets all groups run concurrently; else the widest that fits
+    for (int cg = 1; cg <= 4; ++cg) {
+      cl::Layout tmp;
+      int ma = 0;
+      if (!plan_cluster(ctx, nd, nz, cg, tmp)) continue;
+      if (dispatch_cluster(cg, ctx, a, tmp, 0, &ma) != OPZ_OK) continue;
+      CG = cg; lay = tmp; max_active = ma;
+      if ((B + cg - 1) / cg <= ma) break;
+    }
+    if (const char* e = getenv("OPZ_BPTT_CLUSTER_COLUMNS")) {
+      const int cg = atoi(e);
+      cl::Layout tmp;
+      int ma = 0;
+      if (cg >= 1 && cg <= 4 && plan_cluster(ctx, nd, nz, cg, tmp) && dispatch_cluster(cg, ctx, a, tmp, 0, &ma) == OPZ_OK) {
+        CG = cg; lay = tmp; max_active = ma;
+      }
+    }
+    if (CG > 0) {
+      cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+      if (prof) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
+      OPZ_CUDA(cudaMemcpyAsync(XN, c.r.x0, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
+      Args ac = a;
+      ac.record = 1;
+      { int dbg = 0; if (const char* e = getenv("OPZ_BPTT_DEBUG")) dbg = atoi(e); cudaMemcpyToSymbolAsync(cl::g_dbg, &dbg, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
+      const int64_t groups = (B + CG - 1) / CG;
+      int ma = 0;
+      if ((rc = dispatch_cluster(CG, ctx, ac, lay, groups, &ma))) return rc;
+      if (prof) cudaEventRecord(ev[1], st);
+      loss_partial_kernel<<<(unsigned)B, 128, 0, st>>>(a);
+      loss_final_kernel<<<1, 32, 0, st>>>(a);
+      ctx->launches += 2;
+      if ((rc = dw_all((int64_t)n_steps * stages * B))) return rc;
+      if (prof) {
+        cudaEventRecord(ev[2], st);
+        cudaEventSynchronize(ev[2]);
+        float f = 0, g = 0;
+        cudaEventElapsedTime(&f, ev[0], ev[1]);
+        cudaEventElapsedTime(&g, ev[1], ev[2]);
+        fprintf(stderr, "opz bptt profile (cluster path): sweep %.2f ms (%d columns/cluster, %lld clusters, %d resident), "
+                "loss + dW %.2f ms, shared memory %.1f KB, records %.2f GB\n", f, CG, (long long)groups, max_active, g,
+                lay.total * 4 / 1024.0, (double)(sizeof(float) * rec_floats * (size_t)rows_cap) / 1e9);
+        for (auto& e : ev) cudaEventDestroy(e);
+      }
+      return OPZ_OK;
+    }
+  }
+
   // ---- transposed weight copies for the backward GEMMs ----
   for (int net = 0; net < 3; ++net)
     for (int l = 0; l < L - 1; ++l) {
@@ -852,7 +1010,6 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
     ctx->launches += 1;
   };
 
-  const bool prof = getenv("OPZ_BPTT_PROFILE") != nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (prof) for (auto& e : ev) cudaEventCreate(&e);
   if (prof) cudaEventRecord(ev[0], st);
@@ -872,24 +1029,6 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   ctx->launches += 3;
 
   // ---- backward sweep, segment by segment ----
-  auto dw_all = [&](int64_t rows) -> int {
-    for (int l = 0; l < L; ++l) {
-      const int K = nd.sizes[l], N = nd.sizes[l + 1];
-      const float* Aop = l == 0 ? a.X : a.H[l - 1];
-      const int64_t a_net = l == 0 ? 0 : rows_cap * (int64_t)K;
-      const float* Dop = l == L - 1 ? a.DY : a.G[l];
-      const int64_t d_net = rows_cap * (int64_t)N;
-      const int tiles = ((K + kTK - 1) / kTK) * ((N + kTN - 1) / kTN) * 3;
-      int split = (4 * ctx->sm_count + tiles - 1) / tiles;
-      split = (int)std::max<int64_t>(1, std::min<int64_t>(split, rows / 256));
-      dim3 g((K + kTK - 1) / kTK, (N + kTN - 1) / kTN, 3 * split);
-      dw_kernel<<<g, 256, 0, st>>>(Aop, a_net, K, Dop, d_net, N, K, N, rows, split, c.grad_out + nd.w_off[l],
-                                   c.grad_out + nd.b_off[l], nd.P);
-      ctx->launches += 1;
-    }
-    OPZ_CUDA(cudaGetLastError());
-    return OPZ_OK;
-  };
   for (int64_t seg_end = n_steps; seg_end > 0;) {
     const int64_t seg_n0 = std::max<int64_t>(0, seg_end - seg_steps);
     const int len = (int)(seg_end - seg_n0);

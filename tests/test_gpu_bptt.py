@@ -110,6 +110,32 @@ def test_segmented_recompute_equals_single_segment(opz, oracle, ctx, monkeypatch
     model.close()
 
 
+def test_cluster_and_graph_paths_agree(opz, oracle, ctx, monkeypatch):
+    """The 16-CTA cluster sweep (weights resident in shared memory) and the layer-parallel CUDA-graph path
+    compute the same loss and gradient (different summation orders only)."""
+    O = oracle
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    n_steps, save_every = 12, 4
+    lw = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+    for sizes, act, B in (((96, 400, 400, 31), 1, 18), ((96, 50, 20, 31), 3, 7), ((96, 64, 31), 4, 3), ((96, 40, 30, 20, 31), 2, 9)):
+        p, x0, bc, m, m_true, dt = _case(O, fl, sizes, act, B, n_steps, save_every, seed=9)
+        target = O.rollout(x0, bc, m_true, p, 2, dt, n_steps, save_every)
+        model = product_model(opz, m)
+        pp = product_params(opz, p)
+        res = {}
+        for name, env in (("cluster", {}), ("graph", {"OPZ_BPTT_NO_CLUSTER": "1"}), ("cluster4", {"OPZ_BPTT_CLUSTER_COLUMNS": "4"}),
+                          ("cluster1", {"OPZ_BPTT_CLUSTER_COLUMNS": "1"})):
+            for k in ("OPZ_BPTT_NO_CLUSTER", "OPZ_BPTT_CLUSTER_COLUMNS"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            res[name] = opz.loss_grad(model, pp, x0, bc, target, lw, 2, dt, n_steps, save_every)
+        for name in ("graph", "cluster4", "cluster1"):
+            assert res[name][0] == pytest.approx(res["cluster"][0], rel=1e-5), (sizes, name)
+            assert _rel_l2(res[name][2], res["cluster"][2]) < 2e-4, (sizes, name, _rel_l2(res[name][2], res["cluster"][2]))
+        model.close()
+
+
 def test_gradient_is_additive_over_column_shards(opz, oracle, ctx):
     """The multi-GPU contract: each rank passes its shard with B_total = global batch; the all-reduce is a sum."""
     O = oracle
