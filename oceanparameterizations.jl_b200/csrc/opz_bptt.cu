@@ -644,46 +644,48 @@ void bptt_release(opz_ctx* ctx) {
 
 namespace {
 
-// Shared-memory plan of the cluster kernel for CG columns per cluster; returns false if it cannot run.
-bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CG, bptt::cl::Layout& lay) {
+// Shared-memory plan of the cluster kernel for CP column slots per cluster; returns false if it cannot run.
+bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, bptt::cl::Layout& lay) {
   using namespace bptt;
   const int L = nd.n_layers, S3 = 3 * nz, nout = nz - 1, NO3 = 3 * nout;
   std::memset(&lay, 0, sizeof(lay));
-  if (S3 * CG > cl::kThreads || NO3 * CG > cl::kThreads) return false;
+  if (S3 * CP > cl::kThreads || NO3 * CP > cl::kThreads) return false;
   int off = 0, ulmax = 0;
   auto take = [&](int n) { const int o = off; off += (n + 3) / 4 * 4; return o; };
   for (int l = 0; l < L - 1; ++l) {
     const int UL = (nd.sizes[l + 1] + cl::kCS - 1) / cl::kCS;
-    if (3 * UL * CG > cl::kThreads) return false;
+    if (3 * UL * CP > cl::kThreads) return false;
     lay.UL[l] = UL;
     ulmax = std::max(ulmax, UL);
     lay.W[l] = take(3 * nd.sizes[l] * UL);
     lay.bias[l] = take(3 * UL);
-    if (l <= L - 3) lay.hfull[l] = take(3 * nd.sizes[l + 1] * CG);
+    lay.gs[l] = take(3 * UL * CP);
+    if (l <= L - 3) lay.hfull[l] = take(3 * nd.sizes[l + 1] * CP);
   }
   lay.W[L - 1] = take(3 * lay.UL[L - 2] * nout);
   lay.bias[L - 1] = take(NO3);
-  lay.hs = take(3 * ulmax * CG);
-  lay.dzs = take(3 * ulmax * CG);
-  lay.part = take(cl::kThreads * CG);
-  lay.y = take(std::max(NO3, S3) * CG);
-  lay.dy = take(NO3 * CG);
-  lay.xn = take(S3 * CG); lay.xs = take(S3 * CG); lay.kacc = take(S3 * CG); lay.lam = take(S3 * CG);
-  lay.kbar = take(S3 * CG); lay.xsum = take(S3 * CG); lay.xphys = take(S3 * CG);
-  lay.Fs = take(3 * (nz + 1) * CG);
-  lay.recv_big_size = cl::kCS * 3 * ulmax * CG;
+  lay.hs = take(3 * ulmax * CP);
+  lay.dzs = take(3 * ulmax * CP);
+  lay.part = take(cl::kThreads * CP);
+  lay.y = take(std::max(NO3, S3) * CP);
+  lay.dy = take(NO3 * CP);
+  lay.xn = take(S3 * CP); lay.xs = take(S3 * CP); lay.kacc = take(S3 * CP); lay.lam = take(S3 * CP);
+  lay.kbar = take(S3 * CP); lay.xsum = take(S3 * CP); lay.xphys = take(S3 * CP);
+  lay.Fs = take(3 * (nz + 1) * CP);
+  lay.recv_big_size = cl::kCS * 3 * ulmax * CP;
   lay.recv_big = take(lay.recv_big_size * (L >= 4 ? 2 : 1));
-  lay.SL = (std::max(NO3, S3) * CG + cl::kCS - 1) / cl::kCS;
+  lay.SL = (std::max(NO3, S3) * CP + cl::kCS - 1) / cl::kCS;
   lay.recv_small = take(cl::kCS * lay.SL);
   lay.rbase = take(cl::kCS);
   lay.total = off;
   return (size_t)off * sizeof(float) <= (size_t)ctx->smem_optin;
 }
 
-template <int CG>
-int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int64_t groups, int* max_active) {
+// groups == 0: only queries how many clusters can be resident at once
+template <int CP>
+int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int cg, int64_t groups, int* max_active) {
   using namespace bptt;
-  auto kern = cl::sweep_kernel<CG>;
+  auto kern = cl::sweep_kernel<CP>;
   const size_t smem = (size_t)lay.total * sizeof(float);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -708,19 +710,20 @@ int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& la
     return OPZ_EUNSUP;
   }
   *max_active = n;
-  if (groups == 0) return OPZ_OK;  // query only
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lay);
+  if (groups == 0) return OPZ_OK;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, lay, cg);
   if (e != cudaSuccess) return cuda_fail(e, "cluster sweep launch");
   ctx->launches += 1;
   return OPZ_OK;
 }
 
-int dispatch_cluster(int CG, opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int64_t groups, int* max_active) {
-  switch (CG) {
-    case 1: return launch_cluster<1>(ctx, a, lay, groups, max_active);
-    case 2: return launch_cluster<2>(ctx, a, lay, groups, max_active);
-    case 3: return launch_cluster<3>(ctx, a, lay, groups, max_active);
-    default: return launch_cluster<4>(ctx, a, lay, groups, max_active);
+int slots_for(int cg) { return cg <= 1 ? 1 : (cg <= 2 ? 2 : 4); }
+
+int dispatch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int cg, int64_t groups, int* max_active) {
+  switch (slots_for(cg)) {
+    case 1: return launch_cluster<1>(ctx, a, lay, cg, groups, max_active);
+    case 2: return launch_cluster<2>(ctx, a, lay, cg, groups, max_active);
+    default: return launch_cluster<4>(ctx, a, lay, cg, groups, max_active);
   }
 }
 
@@ -858,21 +861,19 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
     cl::Layout lay;
     int CG = 0, max_active = 0;
     // fewest columns per cluster that still lets all groups run concurrently; else the widest that fits
-    for (int cg = 1; cg <= 4; ++cg) {
+    auto try_cg = [&](int cg) -> bool {
       cl::Layout tmp;
       int ma = 0;
-      if (!plan_cluster(ctx, nd, nz, cg, tmp)) continue;
-      if (dispatch_cluster(cg, ctx, a, tmp, 0, &ma) != OPZ_OK) continue;
+      if (!plan_cluster(ctx, nd, nz, slots_for(cg), tmp)) return false;
+      if (dispatch_cluster(ctx, a, tmp, cg, 0, &ma) != OPZ_OK) return false;
       CG = cg; lay = tmp; max_active = ma;
-      if ((B + cg - 1) / cg <= ma) break;
-    }
+      return true;
+    };
+    for (int cg = 1; cg <= 4; ++cg)
+      if (try_cg(cg) && (B + cg - 1) / cg <= max_active) break;
     if (const char* e = getenv("OPZ_BPTT_CLUSTER_COLUMNS")) {
       const int cg = atoi(e);
-      cl::Layout tmp;
-      int ma = 0;
-      if (cg >= 1 && cg <= 4 && plan_cluster(ctx, nd, nz, cg, tmp) && dispatch_cluster(cg, ctx, a, tmp, 0, &ma) == OPZ_OK) {
-        CG = cg; lay = tmp; max_active = ma;
-      }
+      if (cg >= 1 && cg <= 4) try_cg(cg);
     }
     if (CG > 0) {
       cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -880,10 +881,9 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
       OPZ_CUDA(cudaMemcpyAsync(XN, c.r.x0, sizeof(float) * B * S3, cudaMemcpyDeviceToDevice, st));
       Args ac = a;
       ac.record = 1;
-      { int dbg = 0; if (const char* e = getenv("OPZ_BPTT_DEBUG")) dbg = atoi(e); cudaMemcpyToSymbolAsync(cl::g_dbg, &dbg, sizeof(int), 0, cudaMemcpyHostToDevice, st); }
       const int64_t groups = (B + CG - 1) / CG;
       int ma = 0;
-      if ((rc = dispatch_cluster(CG, ctx, ac, lay, groups, &ma))) return rc;
+      if ((rc = dispatch_cluster(ctx, ac, lay, CG, groups, &ma))) return rc;
       if (prof) cudaEventRecord(ev[1], st);
       loss_partial_kernel<<<(unsigned)B, 128, 0, st>>>(a);
       loss_final_kernel<<<1, 32, 0, st>>>(a);
@@ -899,6 +899,14 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
                 "loss + dW %.2f ms, shared memory %.1f KB, records %.2f GB\n", f, CG, (long long)groups, max_active, g,
                 lay.total * 4 / 1024.0, (double)(sizeof(float) * rec_floats * (size_t)rows_cap) / 1e9);
         for (auto& e : ev) cudaEventDestroy(e);
+        unsigned long long ph[24];
+        cudaMemcpyFromSymbol(ph, cl::g_phase_cycles, sizeof(ph));
+        const char* names[24] = {"fwd slice matvec", "fwd epilogue+gather", "fwd last-layer partial", "fwd y all-reduce", "fwd physics faces",
+                                 "fwd cells+RK", "", "", "bwd land+prefetch", "bwd physics VJP", "bwd dz last", "bwd dh partial+send",
+                                 "bwd reduce-scatter wait", "bwd dz hidden", "bwd dx partial", "bwd dx all-reduce", "bwd RK adjoint"};
+        const double per = 1.0 / ((double)n_steps * stages);
+        for (int i = 0; i < 17; ++i)
+          if (ph[i]) fprintf(stderr, "    phase %-26s %8.0f cycles / right-hand side\n", names[i], ph[i] * per);
       }
       return OPZ_OK;
     }

@@ -1,5 +1,5 @@
 // opz_bptt_cluster.cuh — the whole BPTT sweep of one group of columns inside ONE thread-block cluster.
-// Included by opz_bptt.cu (namespace opz::bptt; uses Args, rec-free indexing q = n*stages + s).
+// Included by opz_bptt.cu (namespace opz::bptt; uses Args; record index q = n*stages + s).
 //
 // 16 CTAs form a cluster; CTA r keeps, for the WHOLE rollout, its 1/16 slice of every Dense layer of
 // the three nets resident in shared memory in FP32 (construct_NN: 2.54 MB over 16 SMs = 158 KB each),
@@ -12,28 +12,36 @@
 //     backward  physics VJP replicated; dz of the last hidden layer is slice-local;
 //               dh_{l-1} = W_l^T dz_l: slice-local partial over ALL inputs -> reduce-scatter to the owners;
 //               first layer: partial input cotangent -> two-phase all-reduce -> RK adjoint, replicated.
-// Clusters are independent (a group of <= CG columns each), so there is no grid-wide synchronisation
+// Clusters are independent (a group of <= CP columns each), so there is no grid-wide synchronisation
 // and no co-scheduling requirement.  Stage inputs, h_l and act'(z_l) -> dz_l are recorded in HBM for the
 // weight-gradient reduction GEMMs (dw_kernel), exactly as in the graph path.
+//
+// Latency notes (the sweep is a chain of ~6 exchanges per right-hand side): activations are laid out
+// [feature][CP] with CP = 1, 2 or 4 column slots so that one broadcast LDS.32/64/128 feeds CP FMAs;
+// record stores to HBM are issued between barrier.cluster.arrive and .wait so that no barrier's release
+// has to drain them; the backward sweep prefetches the next right-hand side's records one step ahead;
+// the CTA that writes the replicated records rotates with the record index.
 #pragma once
 
 namespace cl {
 
 constexpr int kCS = 16;         // CTAs per cluster
 constexpr int kThreads = 512;
+constexpr int kMaxKSL = 8;      // split of a slice's reduction dimension over threads
 
 struct Layout {                 // float offsets into dynamic shared memory (identical in every CTA)
   int W[kMaxLayers];            // hidden l: [3][K_l][UL_l] ; last: [3][UL_{L-2}][nout]
   int bias[kMaxLayers];         // hidden l: [3][UL_l]      ; last: [3][nout]
   int UL[kMaxLayers];           // units per CTA of hidden layer l
-  int hfull[kMaxLayers];        // gathered activations of hidden layer l <= L-3: [3][N_l][CG]
-  int hs, dzs;                  // own slice of the last hidden layer / of the current dz: [3][ULmax][CG]
-  int part;                     // split-K partials: kThreads * CG
-  int y;                        // [max(3 nout, S3)][CG]: NN outputs (fwd), dy then the summed input cotangent (bwd)
-  int dy;                       // [3 nout][CG]
-  int xn, xs, kacc, lam, kbar, xsum, xphys;  // [S3][CG]
-  int Fs;                       // [3][nz+1][CG]
-  int recv_big, recv_big_size;  // [kCS][3 ULmax][CG] (x2 when L >= 4)
+  int hfull[kMaxLayers];        // gathered activations of hidden layer l <= L-3: [3][N_l][CP]
+  int gs[kMaxLayers];           // this CTA's act'(z_l) slice of the right-hand side being back-propagated: [3][UL_l][CP]
+  int hs, dzs;                  // own slice of the last hidden layer / of the current dz: [3][ULmax][CP]
+  int part;                     // split-K partials: kThreads * CP
+  int y;                        // [max(3 nout, S3)][CP]: NN outputs (fwd), summed input cotangent (bwd)
+  int dy;                       // [3 nout][CP]
+  int xn, xs, kacc, lam, kbar, xsum, xphys;  // [S3][CP]
+  int Fs;                       // [3][nz+1][CP]
+  int recv_big, recv_big_size;  // [kCS][3 ULmax][CP] (x2 when L >= 4)
   int recv_small;               // [kCS][SL]
   int SL;
   int rbase;                    // 16 x uint32: shared::cluster base address of every rank
@@ -50,24 +58,45 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ int g_dbg;
 __device__ __forceinline__ void st_remote(uint32_t addr, float v) {
-  if (g_dbg & 4) return;
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  if (g_dbg & 2) { __syncthreads(); return; }
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+
+// acc[0..CP) += w * p[0..CP)  with one broadcast vector load
+template <int CP>
+__device__ __forceinline__ void fma_cols(float (&acc)[CP], float w, const float* p) {
+  if constexpr (CP == 1) {
+    acc[0] = fmaf(w, p[0], acc[0]);
+  } else if constexpr (CP == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
+  } else {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
+    acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+  }
 }
 
-template <int CG>
-__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constant__ Args a, const __grid_constant__ Layout lay) {
+// per-phase cycle counters of CTA 0 (thread 0), dumped by the host when OPZ_BPTT_PROFILE is set
+__device__ unsigned long long g_phase_cycles[24];
+#define OPZ_PH(i)                                                     \
+  do {                                                                \
+    if (timing) { const long long now_ = clock64(); ph[i] += now_ - tlast; tlast = now_; } \
+  } while (0)
+
+template <int CP>
+__global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constant__ Args a, const __grid_constant__ Layout lay, int cg) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x;
+  const int tc = t % CP, tq = t / CP;   // column slot / item index of the "one thread per (item, column)" phases
   const int rank = (int)cluster_rank();
   const int64_t group = blockIdx.x / kCS;
-  const int64_t col0 = group * CG;
-  const int ncol = (int)min((int64_t)CG, a.B - col0);
+  const int64_t col0 = group * cg;
+  const int ncol = (int)min((int64_t)cg, a.B - col0);
+  const bool col_ok = tc < ncol;
   const DevParams& P = a.P;
   const int nz = P.nz, S3 = a.S3, nout = a.nout, L = a.L, stages = a.stages;
   const int NO3 = 3 * nout;
@@ -88,6 +117,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
   float* recv_small = sm + lay.recv_small;
   uint32_t* rbase = reinterpret_cast<uint32_t*>(sm + lay.rbase);
   const uint32_t my_base = (uint32_t)__cvta_generic_to_shared(sm);
+  const bool timing = (blockIdx.x == 1 && t == 0);
+  long long ph[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) ph[i] = 0;
+  long long tlast = clock64();
 
   // ---- one-time setup: remote bases, weight slices, initial state ----
   if (t < kCS) rbase[t] = map_to_rank(my_base, (uint32_t)t);
@@ -114,29 +148,31 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     float* bsl = sm + lay.bias[l];
     for (int e = t; e < NO3; e += kThreads) bsl[e] = a.w[(int64_t)(e / nout) * a.nd.P + a.nd.b_off[l] + e % nout];
   }
-  for (int e = t; e < S3 * CG; e += kThreads) {
-    const int i = e / CG, c = e % CG;
-    const float v = c < ncol ? a.XN[(col0 + c) * S3 + i] : 0.0f;  // XN[0] was filled by the host
-    xn[e] = v;
-    xs[e] = v;
+  if (t < S3 * CP) {
+    const float v = col_ok ? a.XN[(col0 + tc) * S3 + tq] : 0.0f;  // XN[0] was filled by the host
+    xn[t] = v;
+    xs[t] = v;
   }
   cluster_sync_all();  // rbase of every CTA is mapped; nobody writes remotely before everyone is here
 
-  // two-phase all-reduce of `count` values held as per-CTA partials in registers of threads t < count:
-  // reduce-scatter to owner = e % 16, the owner adds `bias_of(e)` and broadcasts into dst[e] of every CTA
-  auto all_reduce = [&](float value, int count, float* dst, const float* bias_by_elem) {
+  // two-phase all-reduce of `count` (<= kThreads) per-CTA partials held by threads t < count:
+  // reduce-scatter to owner = e % 16; the owner adds bias[e / CP] and broadcasts into dst[e] of every CTA.
+  // `between()` runs between the first arrive and wait (HBM record stores go there).
+  auto all_reduce = [&](float value, int count, float* dst, const float* bias_by_item, auto&& between) {
     if (t < count) {
       const int owner = t % kCS, slot = t / kCS;
       st_remote(rbase[owner] + 4u * (uint32_t)(lay.recv_small + rank * lay.SL + slot), value);
     }
-    cluster_sync_all();
+    cluster_arrive();
+    between();
+    cluster_wait();
     if (t < lay.SL) {
       const int e = t * kCS + rank;
       if (e < count) {
         float s = 0.0f;
 #pragma unroll
         for (int src = 0; src < kCS; ++src) s += recv_small[src * lay.SL + t];
-        if (bias_by_elem) s += bias_by_elem[e / CG];
+        if (bias_by_item) s += bias_by_item[e / CP];
         const uint32_t off = 4u * (uint32_t)((int)(dst - sm) + e);
 #pragma unroll
         for (int d = 0; d < kCS; ++d) st_remote(rbase[d] + off, s);
@@ -145,34 +181,31 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     cluster_sync_all();
   };
 
-  // hidden layer l, forward, for this CTA's slice; input activations `in` laid out [net][K][CG]
-  // (net_stride 0 for the shared state input).  Leaves z in registers of threads t < 3 UL CG.
+  // hidden layer l, forward, this CTA's slice; `in` is laid out [net][K][CP] (net_stride 0 for the shared
+  // state input).  Returns z for threads t < 3 UL CP (item p = t / CP = net*UL + u, column slot t % CP).
   auto slice_forward = [&](int l, const float* in, int net_stride) -> float {
     const int K = a.nd.sizes[l], UL = lay.UL[l], NP = 3 * UL;
-    const int KSL = max(1, min(kThreads / NP, K));
+    const int KSL = max(1, min(min(kThreads / NP, K), kMaxKSL));
     const float* W = sm + lay.W[l];
     if (t < NP * KSL) {
       const int p = t % NP, ks = t / NP, net = p / UL, u = p - net * UL;
-      float acc[CG];
+      float acc[CP];
 #pragma unroll
-      for (int c = 0; c < CG; ++c) acc[c] = 0.0f;
+      for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
       const float* Wp = W + (size_t)net * K * UL + u;
       const float* ip = in + (size_t)net * net_stride;
-#pragma unroll 4
-      for (int k = ks; k < K; k += KSL) {
-        const float wv = Wp[k * UL];
+#pragma unroll 8
+      for (int k = ks; k < K; k += KSL) fma_cols<CP>(acc, Wp[k * UL], ip + k * CP);
 #pragma unroll
-        for (int c = 0; c < CG; ++c) acc[c] = fmaf(wv, ip[k * CG + c], acc[c]);
-      }
-#pragma unroll
-      for (int c = 0; c < CG; ++c) part[(ks * NP + p) * CG + c] = acc[c];
+      for (int c = 0; c < CP; ++c) part[(ks * NP + p) * CP + c] = acc[c];
     }
     __syncthreads();
     float z = 0.0f;
-    if (t < NP * CG) {
-      const int p = t / CG;
-      for (int ks = 0; ks < KSL; ++ks) z += part[ks * NP * CG + t];
-      z += (sm + lay.bias[l])[p];
+    if (t < NP * CP) {
+#pragma unroll
+      for (int ks = 0; ks < kMaxKSL; ++ks)
+        if (ks < KSL) z += part[ks * NP * CP + t];
+      z += (sm + lay.bias[l])[tq];
     }
     return z;
   };
@@ -183,66 +216,66 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     for (int s = 0; s < stages; ++s) {
       const int q = n * stages + s;
       const int64_t row0 = (int64_t)q * a.B + col0;
-      if (rank == 0) {
-        for (int e = t; e < S3 * CG; e += kThreads) {
-          const int i = e / CG, c = e % CG;
-          if (c < ncol) a.X[(row0 + c) * S3 + i] = xs[e];
-        }
-      }
+      const bool recorder = (rank == (q & (kCS - 1)));   // the replicated records are written by one CTA, in rotation
       for (int l = 0; l < L - 1; ++l) {
         const int N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
-        const float z = slice_forward(l, l == 0 ? xs : sm + lay.hfull[l - 1], l == 0 ? 0 : a.nd.sizes[l] * CG);
-        if (t < 3 * UL * CG) {
-          const int p = t / CG, c = t % CG, net = p / UL, u = p - net * UL;
-          if (u0 + u < N) {
-            const float hv = act_dyn(z, a.nd.act);
-            if (c < ncol && !(g_dbg & 1)) {
-              const int64_t o = ((int64_t)net * a.rows_cap + row0 + c) * N + u0 + u;
-              a.H[l][o] = hv;
-              a.G[l][o] = act_grad_dyn(z, a.nd.act);
-            }
-            if (l < L - 2) {
-              const uint32_t off = 4u * (uint32_t)(lay.hfull[l] + (net * N + u0 + u) * CG + c);
+        const float z = slice_forward(l, l == 0 ? xs : sm + lay.hfull[l - 1], l == 0 ? 0 : a.nd.sizes[l] * CP);
+        OPZ_PH(0);
+        const bool mine = t < 3 * UL * CP;
+        const int net = mine ? tq / UL : 0, u = tq - net * UL;
+        const bool live = mine && (u0 + u < N);
+        const float hv = act_dyn(z, a.nd.act);
+        if (l < L - 2) {
+          if (live) {
+            const uint32_t off = 4u * (uint32_t)(lay.hfull[l] + (net * N + u0 + u) * CP + tc);
 #pragma unroll
-              for (int d = 0; d < kCS; ++d) st_remote(rbase[d] + off, hv);
-            } else {
-              hs[t] = hv;
-            }
-          } else if (l == L - 2) {
-            hs[t] = 0.0f;
+            for (int d = 0; d < kCS; ++d) st_remote(rbase[d] + off, hv);
           }
+          cluster_arrive();
+        } else if (mine) {
+          hs[t] = live ? hv : 0.0f;
         }
-        if (l < L - 2) cluster_sync_all();
+        // HBM records (consumed by the backward sweep and the weight-gradient GEMMs)
+        if (live && col_ok) {
+          const int64_t o = ((int64_t)net * a.rows_cap + row0 + tc) * N + u0 + u;
+          a.H[l][o] = hv;
+          a.G[l][o] = act_grad_dyn(z, a.nd.act);
+        }
+        if (l == 0 && recorder && t < S3 * CP && col_ok) a.X[(row0 + tc) * S3 + tq] = xs[t];
+        if (l < L - 2) cluster_wait();
         else __syncthreads();
+        OPZ_PH(1);
       }
       // last layer: split-K over this CTA's slice of the last hidden layer, then all-reduce
       {
         const int UL = lay.UL[L - 2];
         const float* W = sm + lay.W[L - 1];
         float yp = 0.0f;
-        if (t < NO3 * CG) {
-          const int o = t / CG, c = t % CG, net = o / nout, j = o - net * nout;
+        if (t < NO3 * CP) {
+          const int net = tq / nout, j = tq - net * nout;
           const float* Wp = W + (size_t)net * UL * nout + j;
-          const float* hp = hs + net * UL * CG + c;
+          const float* hp = hs + net * UL * CP + tc;
 #pragma unroll 5
-          for (int u = 0; u < UL; ++u) yp = fmaf(hp[u * CG], Wp[u * nout], yp);
+          for (int u = 0; u < UL; ++u) yp = fmaf(hp[u * CP], Wp[u * nout], yp);
         }
-        all_reduce(yp, NO3 * CG, yb, sm + lay.bias[L - 1]);
+        OPZ_PH(2);
+        all_reduce(yp, NO3 * CP, yb, sm + lay.bias[L - 1], [] {});
+        OPZ_PH(3);
       }
       // physics + Runge-Kutta update, replicated in every CTA (opz_device.cuh formulas, one thread per face / cell)
       const float ts = tn + a.rk_c[s] * a.h;
-      if (t < (nz + 1) * CG) {
-        const int f = t / CG, c = t % CG;
+      if (t < (nz + 1) * CP) {
+        const int f = tq, c = tc;
         const float* bc = a.bc + (col0 + min(c, ncol - 1)) * OPZ_BC_STRIDE;
         float Fu, Fv, FT;
         if (f == 0) { Fu = bc[0] - P.off[0]; Fv = bc[2] - P.off[1]; FT = bc[4] - P.off[2]; }
         else if (f == nz) { Fu = bc[1] - P.off[0]; Fv = bc[3] - P.off[1]; FT = wT_top_value(P, bc, ts); }
         else {
-          Fu = yb[(f - 1) * CG + c]; Fv = yb[(nout + f - 1) * CG + c]; FT = yb[(2 * nout + f - 1) * CG + c];
+          Fu = yb[(f - 1) * CP + c]; Fv = yb[(nout + f - 1) * CP + c]; FT = yb[(2 * nout + f - 1) * CP + c];
           if (P.flags & OPZ_FLAG_MPP) {
-            const float gu = (xs[f * CG + c] - xs[(f - 1) * CG + c]) * P.nzf;
-            const float gv = (xs[(nz + f) * CG + c] - xs[(nz + f - 1) * CG + c]) * P.nzf;
-            const float gT = (xs[(2 * nz + f) * CG + c] - xs[(2 * nz + f - 1) * CG + c]) * P.nzf;
+            const float gu = (xs[f * CP + c] - xs[(f - 1) * CP + c]) * P.nzf;
+            const float gv = (xs[(nz + f) * CP + c] - xs[(nz + f - 1) * CP + c]) * P.nzf;
+            const float gT = (xs[(2 * nz + f) * CP + c] - xs[(2 * nz + f - 1) * CP + c]) * P.nzf;
             const float Ri = richardson(P, gu, gv, gT);
             const float nu = nu_of_ri(P, Ri);
             const float nuT = nuT_of(P, nu, gu, gT);
@@ -251,19 +284,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
             FT -= P.c_T * nuT * gT;
           }
         }
-        Fs[f * CG + c] = Fu; Fs[((nz + 1) + f) * CG + c] = Fv; Fs[(2 * (nz + 1) + f) * CG + c] = FT;
+        Fs[f * CP + c] = Fu; Fs[((nz + 1) + f) * CP + c] = Fv; Fs[(2 * (nz + 1) + f) * CP + c] = FT;
       }
       __syncthreads();
-      if (t < S3 * CG) {
-        const int i = t / CG, c = t % CG, v = i / nz, cz = i - v * nz;
-        const float* F = Fs + v * (nz + 1) * CG + c;
+      OPZ_PH(4);
+      float xnext = 0.0f;
+      const bool last = (s == stages - 1);
+      if (t < S3 * CP) {
+        const int i = tq, c = tc, v = i / nz, cz = i - v * nz;
+        const float* F = Fs + v * (nz + 1) * CP + c;
         float k;
-        if (v == 0) k = P.A_u * ((F[(cz + 1) * CG] - F[cz * CG]) * P.nzf) + P.cor_u * (P.s_v * xs[(nz + cz) * CG + c] + P.mu_v);
-        else if (v == 1) k = P.A_v * ((F[(cz + 1) * CG] - F[cz * CG]) * P.nzf) - P.cor_v * (P.s_u * xs[cz * CG + c] + P.mu_u);
-        else k = P.A_T * ((F[(cz + 1) * CG] - F[cz * CG]) * P.nzf);
+        if (v == 0) k = P.A_u * ((F[(cz + 1) * CP] - F[cz * CP]) * P.nzf) + P.cor_u * (P.s_v * xs[(nz + cz) * CP + c] + P.mu_v);
+        else if (v == 1) k = P.A_v * ((F[(cz + 1) * CP] - F[cz * CP]) * P.nzf) - P.cor_v * (P.s_u * xs[cz * CP + c] + P.mu_u);
+        else k = P.A_T * ((F[(cz + 1) * CP] - F[cz * CP]) * P.nzf);
         const float x0v = xn[t], hh = a.h;
-        const bool last = (s == stages - 1);
-        float xnext;
         if (a.scheme == OPZ_RK4) {
           if (s == 0) { kacc[t] = k; xnext = x0v + (hh * 0.5f) * k; }
           else if (s == 1) { kacc[t] = kacc[t] + 2.0f * k; xnext = x0v + (hh * 0.5f) * k; }
@@ -275,18 +309,21 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
         } else {
           xnext = x0v + hh * k;
         }
-        xs[t] = xnext;   // every thread touches only its own element of xs / xn here
+      }
+      __syncthreads();  // the Coriolis terms read OTHER cells of xs: nobody overwrites xs before everybody has read it
+      if (t < S3 * CP) {
+        xs[t] = xnext;
         if (last) {
           xn[t] = xnext;
-          if (rank == 0 && c < ncol) a.XN[((int64_t)(n + 1) * a.B + col0 + c) * S3 + i] = xnext;
+          if (recorder && col_ok) a.XN[((int64_t)(n + 1) * a.B + col0 + tc) * S3 + tq] = xnext;
         }
       }
       __syncthreads();
+      OPZ_PH(5);
     }
   }
 
   // ================================ backward sweep ================================
-  // dL/dx_N and the first tendency cotangent (replicated)
   auto loss_cotangent = [&](int n, int i, int c) -> float {
     const int v = i / nz, cz = i - v * nz;
     const int snap = n / a.save_every;
@@ -303,56 +340,61 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     }
     return add;
   };
-  cluster_sync_all();  // rank 0's checkpoint stores are visible to the whole cluster
-  if (t < S3 * CG) {
-    const int i = t / CG, c = t % CG;
-    const float l0 = c < ncol ? loss_cotangent(a.n_steps, i, c) : 0.0f;
+  // records of right-hand side q needed by its back-propagation: this CTA's act'(z_l) slices and the stage input
+  float g_next[kMaxLayers - 1], x_next = 0.0f;
+  auto prefetch = [&](int q) {
+    const int64_t row0 = (int64_t)q * a.B + col0;
+#pragma unroll
+    for (int l = 0; l < kMaxLayers - 1; ++l) {
+      g_next[l] = 0.0f;
+      if (l < L - 1 && q >= 0) {
+        const int N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
+        if (t < 3 * UL * CP) {
+          const int net = tq / UL, u = tq - net * UL;
+          if (u0 + u < N && col_ok) g_next[l] = __ldcg(a.G[l] + ((int64_t)net * a.rows_cap + row0 + tc) * N + u0 + u);
+        }
+      }
+    }
+    x_next = (q >= 0 && t < S3 * CP && col_ok) ? __ldcg(a.X + (row0 + tc) * S3 + tq) : 0.0f;
+  };
+  cluster_sync_all();  // the recorders' checkpoint / record stores are visible to the whole cluster
+  if (t < S3 * CP) {
+    const float l0 = col_ok ? loss_cotangent(a.n_steps, tq, tc) : 0.0f;
     lam[t] = l0;
     kbar[t] = a.rk_b[stages - 1] * l0;
   }
+  prefetch(a.n_steps * stages - 1);
   __syncthreads();
 
   int rs_parity = 0;
-  for (int n = (g_dbg & 8) ? -1 : a.n_steps - 1; n >= 0; --n) {
+  for (int n = a.n_steps - 1; n >= 0; --n) {
     for (int s = stages - 1; s >= 0; --s) {
       const int q = n * stages + s;
       const int64_t row0 = (int64_t)q * a.B + col0;
-      // prefetch this CTA's act'(z_l) slices (written by this CTA during the forward sweep)
-      float greg[kMaxLayers];
+      const bool recorder = (rank == (q & (kCS - 1)));
+      // land the prefetched records in shared memory, then prefetch the next right-hand side's
 #pragma unroll
-      for (int l = 0; l < kMaxLayers; ++l) {
-        greg[l] = 0.0f;
-        if (l < L - 1) {
-          const int N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
-          if (t < 3 * UL * CG) {
-            const int p = t / CG, c = t % CG, net = p / UL, u = p - net * UL;
-            if (u0 + u < N && c < ncol) greg[l] = __ldcg(a.G[l] + ((int64_t)net * a.rows_cap + row0 + c) * N + u0 + u);
-          }
-        }
-      }
-      if (t < S3 * CG) {
-        const int i = t / CG, c = t % CG;
-        xs[t] = c < ncol ? __ldcg(a.X + (row0 + c) * S3 + i) : 0.0f;
-      }
+      for (int l = 0; l < kMaxLayers - 1; ++l)
+        if (l < L - 1 && t < 3 * lay.UL[l] * CP) (sm + lay.gs[l])[t] = g_next[l];
+      if (t < S3 * CP) xs[t] = x_next;
+      prefetch(q - 1);
       __syncthreads();
+      OPZ_PH(8);
       // ---- physics VJP (replicated) ----
-      if (t < (nz + 1) * CG) {
-        const int f = t / CG, c = t % CG;
+      float dy_u = 0.0f, dy_v = 0.0f, dy_T = 0.0f;
+      if (t < (nz + 1) * CP) {
+        const int f = tq, c = tc;
         float gbu = 0.0f, gbv = 0.0f, gbT = 0.0f;
         if (f > 0 && f < nz) {
-          const float Fbu = P.A_u * P.nzf * (kbar[(f - 1) * CG + c] - kbar[f * CG + c]);
-          const float Fbv = P.A_v * P.nzf * (kbar[(nz + f - 1) * CG + c] - kbar[(nz + f) * CG + c]);
-          const float FbT = P.A_T * P.nzf * (kbar[(2 * nz + f - 1) * CG + c] - kbar[(2 * nz + f) * CG + c]);
-          dy[(f - 1) * CG + c] = Fbu; dy[(nout + f - 1) * CG + c] = Fbv; dy[(2 * nout + f - 1) * CG + c] = FbT;
-          if (rank == 0 && c < ncol) {
-            a.DY[((int64_t)0 * a.rows_cap + row0 + c) * nout + f - 1] = Fbu;
-            a.DY[((int64_t)1 * a.rows_cap + row0 + c) * nout + f - 1] = Fbv;
-            a.DY[((int64_t)2 * a.rows_cap + row0 + c) * nout + f - 1] = FbT;
-          }
+          const float Fbu = P.A_u * P.nzf * (kbar[(f - 1) * CP + c] - kbar[f * CP + c]);
+          const float Fbv = P.A_v * P.nzf * (kbar[(nz + f - 1) * CP + c] - kbar[(nz + f) * CP + c]);
+          const float FbT = P.A_T * P.nzf * (kbar[(2 * nz + f - 1) * CP + c] - kbar[(2 * nz + f) * CP + c]);
+          dy[(f - 1) * CP + c] = Fbu; dy[(nout + f - 1) * CP + c] = Fbv; dy[(2 * nout + f - 1) * CP + c] = FbT;
+          dy_u = Fbu; dy_v = Fbv; dy_T = FbT;
           if (P.flags & OPZ_FLAG_MPP) {
-            const float gu = (xs[f * CG + c] - xs[(f - 1) * CG + c]) * P.nzf;
-            const float gv = (xs[(nz + f) * CG + c] - xs[(nz + f - 1) * CG + c]) * P.nzf;
-            const float gT = (xs[(2 * nz + f) * CG + c] - xs[(2 * nz + f - 1) * CG + c]) * P.nzf;
+            const float gu = (xs[f * CP + c] - xs[(f - 1) * CP + c]) * P.nzf;
+            const float gv = (xs[(nz + f) * CP + c] - xs[(nz + f - 1) * CP + c]) * P.nzf;
+            const float gT = (xs[(2 * nz + f) * CP + c] - xs[(2 * nz + f - 1) * CP + c]) * P.nzf;
             const float ea = P.s_u * (gu + P.eps), eb = P.s_v * (gv + P.eps);
             const float S2 = ea * ea + eb * eb;
             const float Ri = P.cBz * (gT + P.eps) / S2;
@@ -374,34 +416,42 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
             gbT = -P.c_T * nuT * FbT + (ok ? Ribar * dRi_dgT : 0.0f);
           }
         }
-        Fs[f * CG + c] = gbu; Fs[((nz + 1) + f) * CG + c] = gbv; Fs[(2 * (nz + 1) + f) * CG + c] = gbT;
+        Fs[f * CP + c] = gbu; Fs[((nz + 1) + f) * CP + c] = gbv; Fs[(2 * (nz + 1) + f) * CP + c] = gbT;
       }
       __syncthreads();
-      if (t < S3 * CG) {
-        const int i = t / CG, c = t % CG, v = i / nz, cz = i - v * nz;
-        const float* g = Fs + v * (nz + 1) * CG + c;
-        float xb = P.nzf * (g[cz * CG] - g[(cz + 1) * CG]);
-        if (v == 0) xb -= P.cor_v * P.s_u * kbar[(nz + cz) * CG + c];
-        else if (v == 1) xb += P.cor_u * P.s_v * kbar[cz * CG + c];
+      if (t < S3 * CP) {
+        const int i = tq, c = tc, v = i / nz, cz = i - v * nz;
+        const float* g = Fs + v * (nz + 1) * CP + c;
+        float xb = P.nzf * (g[cz * CP] - g[(cz + 1) * CP]);
+        if (v == 0) xb -= P.cor_v * P.s_u * kbar[(nz + cz) * CP + c];
+        else if (v == 1) xb += P.cor_u * P.s_v * kbar[cz * CP + c];
         xphys[t] = xb;
       }
+      OPZ_PH(9);
       // ---- dz of the last hidden layer: slice-local ----
+      float pend = 0.0f;          // dz value whose HBM record store is deferred past the next barrier arrive
+      int64_t pend_off = -1;
+      int pend_layer = 0;
       {
         const int l = L - 2, N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
         const float* W = sm + lay.W[L - 1];
-        if (t < 3 * UL * CG) {
-          const int p = t / CG, c = t % CG, net = p / UL, u = p - net * UL;
+        if (t < 3 * UL * CP) {
+          const int net = tq / UL, u = tq - net * UL;
           const float* Wp = W + (size_t)(net * UL + u) * nout;
-          const float* dp = dy + net * nout * CG + c;
+          const float* dp = dy + net * nout * CP + tc;
           float sacc = 0.0f;
-#pragma unroll 4
-          for (int j = 0; j < nout; ++j) sacc = fmaf(Wp[j], dp[j * CG], sacc);
-          const float dz = sacc * greg[l];
+#pragma unroll 8
+          for (int j = 0; j < nout; ++j) sacc = fmaf(Wp[j], dp[j * CP], sacc);
+          const float dz = sacc * (sm + lay.gs[l])[t];
           dzs[t] = dz;
-          if (u0 + u < N && c < ncol) a.G[l][((int64_t)net * a.rows_cap + row0 + c) * N + u0 + u] = dz;
+          if (u0 + u < N && col_ok) { pend = dz; pend_layer = l; pend_off = ((int64_t)net * a.rows_cap + row0 + tc) * N + u0 + u; }
         }
       }
+      auto flush = [&]() {
+        if (pend_off >= 0) { a.G[pend_layer][pend_off] = pend; pend_off = -1; }
+      };
       __syncthreads();
+      OPZ_PH(10);
       // ---- hidden layers: partial dh_{l-1} over all inputs of layer l -> reduce-scatter to the owners ----
       for (int l = L - 2; l >= 1; --l) {
         const int K = a.nd.sizes[l], UL = lay.UL[l];        // layer l: K inputs (= width of hidden l-1)
@@ -411,54 +461,62 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
         for (int it = t; it < 3 * K; it += kThreads) {
           const int net = it / K, k = it - net * K;
           const float* Wp = W + ((size_t)net * K + k) * UL;
-          const float* dp = dzs + net * UL * CG;
-          float acc[CG];
+          const float* dp = dzs + net * UL * CP;
+          float acc[CP];
 #pragma unroll
-          for (int c = 0; c < CG; ++c) acc[c] = 0.0f;
+          for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
 #pragma unroll 5
-          for (int u = 0; u < UL; ++u) {
-            const float wv = Wp[u];
-#pragma unroll
-            for (int c = 0; c < CG; ++c) acc[c] = fmaf(wv, dp[u * CG + c], acc[c]);
-          }
+          for (int u = 0; u < UL; ++u) fma_cols<CP>(acc, Wp[u], dp + u * CP);
           const int owner = k / ULp, kl = k - owner * ULp;
-          const uint32_t off = 4u * (uint32_t)((int)(rb - sm) + ((rank * 3 + net) * ULp + kl) * CG);
+          const uint32_t off = rbase[owner] + 4u * (uint32_t)((int)(rb - sm) + ((rank * 3 + net) * ULp + kl) * CP);
 #pragma unroll
-          for (int c = 0; c < CG; ++c) st_remote(rbase[owner] + off + 4u * c, acc[c]);
+          for (int c = 0; c < CP; ++c) st_remote(off + 4u * c, acc[c]);
         }
-        cluster_sync_all();
-        if (t < 3 * ULp * CG) {
-          const int p = t / CG, c = t % CG, net = p / ULp, u = p - net * ULp;
+        OPZ_PH(11);
+        cluster_arrive();
+        flush();
+        cluster_wait();
+        OPZ_PH(12);
+        if (t < 3 * ULp * CP) {
+          const int net = tq / ULp, u = tq - net * ULp;
           float sacc = 0.0f;
 #pragma unroll
-          for (int src = 0; src < kCS; ++src) sacc += rb[(src * 3 * ULp) * CG + t];
-          const float dz = sacc * greg[l - 1];
+          for (int src = 0; src < kCS; ++src) sacc += rb[(src * 3 * ULp) * CP + t];
+          const float dz = sacc * (sm + lay.gs[l - 1])[t];
           dzs[t] = dz;
           const int N = a.nd.sizes[l];
-          if (u0p + u < N && c < ncol) a.G[l - 1][((int64_t)net * a.rows_cap + row0 + c) * N + u0p + u] = dz;
+          if (u0p + u < N && col_ok) { pend = dz; pend_layer = l - 1; pend_off = ((int64_t)net * a.rows_cap + row0 + tc) * N + u0p + u; }
         }
         if (L >= 4) rs_parity ^= 1;
         __syncthreads();
+        OPZ_PH(13);
       }
       // ---- first layer: partial input cotangent over this CTA's units, all-reduce ----
       {
         const int UL = lay.UL[0];
         const float* W = sm + lay.W[0];
         float xp = 0.0f;
-        if (t < S3 * CG) {
-          const int i = t / CG, c = t % CG;
+        if (t < S3 * CP) {
           for (int net = 0; net < 3; ++net) {
-            const float* Wp = W + ((size_t)net * S3 + i) * UL;
-            const float* dp = dzs + net * UL * CG + c;
+            const float* Wp = W + ((size_t)net * S3 + tq) * UL;
+            const float* dp = dzs + net * UL * CP + tc;
 #pragma unroll 5
-            for (int u = 0; u < UL; ++u) xp = fmaf(Wp[u], dp[u * CG], xp);
+            for (int u = 0; u < UL; ++u) xp = fmaf(Wp[u], dp[u * CP], xp);
           }
         }
-        all_reduce(xp, S3 * CG, yb, nullptr);
+        OPZ_PH(14);
+        all_reduce(xp, S3 * CP, yb, nullptr, [&] {
+          flush();
+          if (recorder && t < (nz + 1) * CP && tq > 0 && tq < nz && col_ok) {
+            a.DY[((int64_t)0 * a.rows_cap + row0 + tc) * nout + tq - 1] = dy_u;
+            a.DY[((int64_t)1 * a.rows_cap + row0 + tc) * nout + tq - 1] = dy_v;
+            a.DY[((int64_t)2 * a.rows_cap + row0 + tc) * nout + tq - 1] = dy_T;
+          }
+        });
+        OPZ_PH(15);
       }
       // ---- Runge-Kutta adjoint bookkeeping (replicated) ----
-      if (t < S3 * CG) {
-        const int i = t / CG, c = t % CG;
+      if (t < S3 * CP) {
         const float xbar = yb[t] + xphys[t];
         const float lv = lam[t];
         const float xsv = (s == stages - 1 ? 0.0f : xsum[t]) + xbar;
@@ -467,14 +525,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           xsum[t] = xsv;
         } else {
           float ln = lv + xsv;
-          if (n % a.save_every == 0 && c < ncol) ln += loss_cotangent(n, i, c);
+          if (n % a.save_every == 0 && col_ok) ln += loss_cotangent(n, tq, tc);
           lam[t] = ln;
           kbar[t] = a.rk_b[stages - 1] * ln;
         }
       }
       __syncthreads();
+      OPZ_PH(16);
     }
   }
+  if (timing)
+    for (int i = 0; i < 24; ++i) g_phase_cycles[i] = (unsigned long long)ph[i];
   cluster_sync_all();  // no CTA exits while a peer may still address its shared memory
 }
 
