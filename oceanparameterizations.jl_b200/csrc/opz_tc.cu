@@ -28,6 +28,8 @@
 //
 // Replaces the batched form of NDE! / predict_flux! (wind_mixing/src/training_postprocessing.jl:105-153)
 // inside a fixed-step solve (solve_NDE_mutating, :55-159).
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -45,7 +47,7 @@ constexpr int kCW = 64;              // accumulator chunk width (TMEM columns)
 constexpr int kSlotBytes = 12288;    // 64 rows x 96 k x 2 B
 constexpr int kSlots = 6;
 constexpr int kMaxOps = 160;
-constexpr int kMaxKsteps = 6;         // k-steps per op (the issue loop is unrolled this far)
+constexpr int kMaxKsteps = 12;        // k-steps per weight stage
 constexpr int kMaxHidden = 400;      // HF region: 200 TMEM columns
 constexpr int kThreads = 192;
 
@@ -100,6 +102,7 @@ struct Plan {                     // host-side, cached on the model
   int ks_full[2] = {1, 1}, ks_tail[2] = {1, 1};  // k-steps per stage (64-row chunks / tail chunk)
   int act = 0;
   bool fp16 = false;              // operand format of the tape (IEEE half instead of bfloat16)
+  int ncta = 1;                   // 2: every weight block is stored as two row halves, one per CTA of a pair
   int bias_per_net = 0;           // floats
   size_t tape_bytes = 0;          // per right-hand side
   size_t tape_stride = 0;         // bytes between replicas
@@ -125,6 +128,7 @@ struct Args {
   uint32_t tape_bytes;
   uint32_t tape_stride;
   int n_copies;
+  int profile;
   Op ops[kMaxOps];
 };
 
@@ -145,6 +149,17 @@ __device__ __forceinline__ void bar_wait(uint64_t* bars, int id, uint32_t& mask)
   ptx::mbar_wait(bars + id, (mask >> id) & 1u);
   mask ^= 1u << id;
 }
+// Optional wait-time profile (OPZ_TC_PROFILE=1): cycles CTA 0's MMA warp and first epilogue warp spend
+// waiting on each class of barrier.  [0..7] MMA warp, [8..15] epilogue warp.
+__device__ unsigned long long g_tc_wait[16];
+enum { W_X = 0, W_DEMPTY = 1, W_H1 = 2, W_FULL = 3, W_H2FULL = 4, W_TOTAL = 5,
+       E_DFULL = 8, E_H2EMPTY = 9, E_YFULL = 10, E_PHYS = 11, E_TOTAL = 12, E_PUBLISH = 13 };
+__device__ __forceinline__ void bar_wait_t(uint64_t* bars, int id, uint32_t& mask, bool prof, long long* acc, int slot) {
+  if (!prof) { bar_wait(bars, id, mask); return; }
+  const long long t0 = clock64();
+  bar_wait(bars, id, mask);
+  acc[slot] += clock64() - t0;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // two FP32 values -> one 32-bit TMEM column of the A operand (low half = even k), activation applied
@@ -156,7 +171,12 @@ __device__ __forceinline__ uint32_t pack_act(float a, float b) {
   return FP16 ? ptx::pack_f16x2(a, b) : ptx::pack_bf16x2(a, b);
 }
 
-template <bool FP16, int ACT>
+// NCTA = 2: CTA pair (cta_group::2).  The two CTAs of a cluster own two adjacent column tiles; every tcgen05.mma is
+// issued once, by the leader, with M = 256: rows 0..127 are the leader's tile (A and D in its tensor memory), rows
+// 128..255 the peer's, and each CTA streams only HALF of every weight block into its own ring.  That halves the
+// MMA-issue work and the L2 -> SM weight traffic per SM.  Barriers the issuer waits on live in the leader CTA and are
+// arrived on remotely by the peer's warps; completions are multicast to both CTAs by tcgen05.commit.
+template <bool FP16, int ACT, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_xn = reinterpret_cast<float*>(smem + SmemLayout::off_xn);
@@ -171,24 +191,37 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
   const int64_t n_tiles = (a.B + kM - 1) / kM;
   const int stages = a.scheme == OPZ_RK4 ? 4 : (a.scheme == OPZ_RK2 ? 2 : 1);
   const int n_rhs = a.n_steps * stages;
+  const uint32_t rank = NCTA == 2 ? ptx::cluster_ctarank() : 0u;
+  // work items: one tile (NCTA = 1) or one pair of adjacent tiles (NCTA = 2) per cluster and iteration
+  const int64_t n_items = (n_tiles + NCTA - 1) / NCTA;
+  const int64_t item0 = blockIdx.x / NCTA, item_stride = gridDim.x / NCTA;
+  // arrive on a barrier the MMA issuer waits on: it lives in the leader CTA
+  const uint32_t leader_bars = NCTA == 2 ? ptx::mapa(ptx::smem_u32(bars), 0u) : 0u;
+  auto arrive_issuer = [&](int id) {
+    if (NCTA == 2 && rank != 0) ptx::mbar_arrive_remote(leader_bars + 8u * (uint32_t)id);
+    else ptx::mbar_arrive(bars + id);
+  };
 
   for (int i = threadIdx.x; i < 3 * a.bias_per_net; i += kThreads) s_bias[i] = a.bias[i];
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kSlots; ++s) { ptx::mbar_init(bars + B_FULL + s, 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(bars + B_DFULL + b, 1); ptx::mbar_init(bars + B_DEMPTY + b, 4); }
-      for (int c = 0; c < 7; ++c) ptx::mbar_init(bars + B_H1 + c, 4);
-      ptx::mbar_init(bars + B_H2FULL, 4);
+      // the leader's "full" barriers also take the peer's forwarded arrival; the peer's own count only its producer
+      for (int s = 0; s < kSlots; ++s) { ptx::mbar_init(bars + B_FULL + s, rank == 0 ? NCTA : 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(bars + B_DFULL + b, 1); ptx::mbar_init(bars + B_DEMPTY + b, 4 * NCTA); }
+      for (int c = 0; c < 7; ++c) ptx::mbar_init(bars + B_H1 + c, 4 * NCTA);
+      ptx::mbar_init(bars + B_H2FULL, 4 * NCTA);
       ptx::mbar_init(bars + B_H2EMPTY, 1);
       ptx::mbar_init(bars + B_YFULL, 1);
-      ptx::mbar_init(bars + B_XFULL, 4);
+      ptx::mbar_init(bars + B_XFULL, 4 * NCTA);
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<512>(tmem_slot);
+    if (NCTA == 2) ptx::tmem_alloc2<512>(tmem_slot);
+    else ptx::tmem_alloc<512>(tmem_slot);
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -197,20 +230,34 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
     if (lane == 0 && n_rhs > 0) {
       uint32_t mask = 0xFFFFFFFFu;  // "empty" barriers start in the released state
       int slot = 0;
-      const uint8_t* tape0 = a.tape + (size_t)(blockIdx.x % a.n_copies) * a.tape_stride;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint8_t* tape0 = a.tape + (size_t)((blockIdx.x / NCTA) % a.n_copies) * a.tape_stride;
+      for (int64_t item = item0; item < n_items; item += item_stride) {
         for (int r = 0; r < n_rhs; ++r) {
           const uint8_t* src = tape0;
           for (int i = 0; i < a.n_ops; ++i) {
-            const uint32_t bytes = a.ops[i].bytes;
+            const uint32_t bytes = a.ops[i].bytes / NCTA;   // this CTA's half of the weight block
             bar_wait(bars, B_EMPTY + slot, mask);
             ptx::mbar_arrive_expect_tx(bars + B_FULL + slot, bytes);
-            ptx::bulk_g2s(s_ring + (size_t)slot * kSlotBytes, src, bytes, bars + B_FULL + slot);
-            src += bytes;
+            ptx::bulk_g2s(s_ring + (size_t)slot * kSlotBytes, src + rank * bytes, bytes, bars + B_FULL + slot);
+            src += a.ops[i].bytes;
             slot = slot + 1 == kSlots ? 0 : slot + 1;
           }
         }
       }
+    }
+    __syncwarp();
+  } else if (warp == 1 && NCTA == 2 && rank != 0) {
+    // ================= peer CTA: forward "my half of the weight block has landed" to the leader =================
+    if (lane == 0 && n_rhs > 0) {
+      uint32_t mask = 0;
+      int slot = 0;
+      for (int64_t item = item0; item < n_items; item += item_stride)
+        for (int r = 0; r < n_rhs; ++r)
+          for (int i = 0; i < a.n_ops; ++i) {
+            bar_wait(bars, B_FULL + slot, mask);
+            ptx::mbar_arrive_remote(leader_bars + 8u * (uint32_t)(B_FULL + slot));
+            slot = slot + 1 == kSlots ? 0 : slot + 1;
+          }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -222,40 +269,63 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
       // released state for the barriers this warp waits on as "empty": D-drained
       uint32_t mask = (1u << (B_DEMPTY + 0)) | (1u << (B_DEMPTY + 1));
       uint32_t slot = 0, g = 0;
+      const bool prof = a.profile && blockIdx.x == 0;
+      long long wacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long t_begin = clock64();
       const uint32_t ring_u32 = ptx::smem_u32(s_ring);
-      const uint32_t idesc0 = ptx::idesc_f16kind(kM, 0, FP16);
+      const uint32_t idesc0 = ptx::idesc_f16kind(kM * NCTA, 0, FP16);
       const int L = a.L;
       // one weight stage: wait for its bytes, issue ks MMAs D (+)= A[k] * B[k]^T, release the slot
+      // The readiness of the NEXT slot is tested before this stage's MMAs are issued, so that the ~100-cycle
+      // try_wait latency hides behind the (pipe-paced) MMA issue; the MMAs are issued from a rolled loop so
+      // that the first one leaves as soon as its two operand addresses exist.
+      bool pre_ok = false;
       auto stage = [&](uint32_t d, uint32_t a_col, uint32_t rows, int ks, bool acc_first) {
-        bar_wait(bars, B_FULL + slot, mask);
+        const long long tw0 = prof ? clock64() : 0;
+        if (pre_ok) mask ^= 1u << (B_FULL + slot);
+        else bar_wait(bars, B_FULL + slot, mask);
+        const uint32_t nslot = slot + 1 == kSlots ? 0 : slot + 1;
+        pre_ok = ptx::mbar_try_wait(bars + B_FULL + nslot, (mask >> (B_FULL + nslot)) & 1u);
         ptx::tc_fence_after();
-        const uint64_t bd0 = ptx::smem_desc(ring_u32 + slot * kSlotBytes, rows * 16u, 128);
+        if (prof) wacc[W_FULL] += clock64() - tw0;  // orders the MMAs after the epilogue warps' tcgen05.st seen through the barriers waited on above
+        // each CTA holds rows / NCTA rows of the block: [k/8][rows / NCTA][8]
+        uint64_t bd = ptx::smem_desc(ring_u32 + slot * kSlotBytes, (rows / NCTA) * 16u, 128);
         const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
+        const long long ti0 = prof ? clock64() : 0;
         if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kMaxKsteps; ++k)
-            if (k < ks) ptx::mma_ts(tmem + d, tmem + a_col + (uint32_t)k * 8u, bd0 + (uint64_t)((uint32_t)k * 2u * rows), idesc, acc_first || k > 0);
-          ptx::tc_commit(bars + B_EMPTY + slot);
+          uint32_t at = tmem + a_col;
+          if (NCTA == 2) ptx::mma_ts2(tmem + d, at, bd, idesc, acc_first);
+          else ptx::mma_ts(tmem + d, at, bd, idesc, acc_first);
+#pragma unroll 1
+          for (int k = 1; k < ks; ++k) {
+            at += 8u;
+            bd += (uint64_t)(2u * rows / NCTA);
+            if (NCTA == 2) ptx::mma_ts2(tmem + d, at, bd, idesc, true);
+            else ptx::mma_ts(tmem + d, at, bd, idesc, true);
+          }
+          if (NCTA == 2) ptx::tc_commit2(bars + B_EMPTY + slot);
+          else ptx::tc_commit(bars + B_EMPTY + slot);
         }
         __syncwarp();
-        slot = slot + 1 == kSlots ? 0 : slot + 1;
+        if (prof) { wacc[6] += clock64() - ti0; wacc[7] += ks; }
+        slot = nslot;
       };
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t item = item0; item < n_items; item += item_stride) {
 #pragma unroll 1
         for (int r = 0; r < n_rhs; ++r) {
           bool have_pend = false;
           uint32_t pend_net = 0, pend_c = 0, pend_rows = 0;
           // output-layer MMAs for one H2c chunk: Y_net (+)= H2c * W_out[:, chunk]^T
           auto out_op = [&](bool final_op) {
-            bar_wait(bars, B_H2FULL, mask);
+            bar_wait_t(bars, B_H2FULL, mask, prof, wacc, W_H2FULL);
             stage(kColY + 32u * pend_net, kColH2, 32u, (int)(pend_rows >> 4), pend_c > 0);
             if (ptx::elect_one()) {
-              ptx::tc_commit(bars + B_H2EMPTY);
-              if (final_op) ptx::tc_commit(bars + B_YFULL);
+              if (NCTA == 2) { ptx::tc_commit2(bars + B_H2EMPTY); if (final_op) ptx::tc_commit2(bars + B_YFULL); }
+              else { ptx::tc_commit(bars + B_H2EMPTY); if (final_op) ptx::tc_commit(bars + B_YFULL); }
             }
             __syncwarp();
           };
-          bar_wait(bars, B_XFULL, mask);
+          bar_wait_t(bars, B_XFULL, mask, prof, wacc, W_X);
 #pragma unroll 1
           for (int net = 0; net < 3; ++net) {
 #pragma unroll 1
@@ -271,17 +341,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
                 const int ks_per = (rows == (uint32_t)kCW) ? a.ks_full[j] : a.ks_tail[j];
                 const uint32_t buf = g & 1u;
                 ++g;
-                bar_wait(bars, B_DEMPTY + buf, mask);
+                bar_wait_t(bars, B_DEMPTY + buf, mask, prof, wacc, W_DEMPTY);
 #pragma unroll 1
                 for (int k0 = 0; k0 < kin; k0 += ks_per) {
                   const int ks = min(ks_per, kin - k0);
                   if (j > 0) {  // HF chunks covering inputs [0, 16 (k0 + ks)) must have been written
                     const int need = ((k0 + ks) * 16 + kCW - 1) / kCW;
-                    while (h1_waited < need) { bar_wait(bars, B_H1 + h1_waited, mask); ++h1_waited; }
+                    while (h1_waited < need) { bar_wait_t(bars, B_H1 + h1_waited, mask, prof, wacc, W_H1); ++h1_waited; }
                   }
                   stage(kColD0 + buf * kCW, a_base + (uint32_t)k0 * 8u, rows, ks, k0 > 0);
                 }
-                if (ptx::elect_one()) ptx::tc_commit(bars + B_DFULL + buf);
+                if (ptx::elect_one()) {
+                  if (NCTA == 2) ptx::tc_commit2(bars + B_DFULL + buf);
+                  else ptx::tc_commit(bars + B_DFULL + buf);
+                }
                 __syncwarp();
                 // the output-layer MMAs of the PREVIOUS fused chunk go after this chunk's MMAs
                 if (have_pend) { out_op(false); have_pend = false; }
@@ -291,6 +364,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
           }
           out_op(true);
         }
+      }
+      if (prof && lane == 0) {
+        wacc[W_TOTAL] = clock64() - t_begin;
+        for (int i = 0; i < 8; ++i) g_tc_wait[i] = (unsigned long long)wacc[i];
       }
     }
   } else {
@@ -302,8 +379,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
     uint32_t mask = 1u << B_H2EMPTY;  // released state
     uint32_t g = 0;
     const float h = a.dt;
+    const bool prof = a.profile && blockIdx.x == 0 && warp == 2;
+    long long eacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t item = item0; item < n_items; item += item_stride) {
+      const int64_t tile = item * NCTA + rank;   // may be one past the last tile for the peer: a padding tile, never stored
       const int64_t col0 = tile * kM;
       const int64_t col = col0 + m;
       // ---- load the initial profiles (coalesced through the padded state array) ----
@@ -339,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bars + B_XFULL);
+        if (lane == 0) arrive_issuer(B_XFULL);
       };
 #pragma unroll 4
       for (int i = 0; i < kS; ++i) s_xs[i * kM + m] = s_xn[i * kLd + m];
@@ -362,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
                 const uint32_t buf = g & 1u;
                 ++g;
                 const int ncols = min(kCW, hp - c * kCW);
-                bar_wait(bars, B_DFULL + buf, mask);
+                bar_wait_t(bars, B_DFULL + buf, mask, prof, eacc, E_DFULL - 8);
                 ptx::tc_fence_after();
                 const uint32_t src = tmem + lane_addr + kColD0 + buf * kCW;
                 const uint32_t dst = tmem + lane_addr + (fused ? kColH2 : kColHF + (uint32_t)c * (kCW / 2));
@@ -384,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
                   }
                 }
                 if (fused) {  // the output-layer MMAs of the previous chunk must have consumed H2c
-                  bar_wait(bars, B_H2EMPTY, mask);
+                  bar_wait_t(bars, B_H2EMPTY, mask, prof, eacc, E_H2EMPTY - 8);
                   ptx::tc_fence_after();
                 }
 #pragma unroll
@@ -394,16 +475,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                  ptx::mbar_arrive(bars + B_DEMPTY + buf);
-                  ptx::mbar_arrive(bars + (fused ? B_H2FULL : B_H1 + c));
+                  arrive_issuer(B_DEMPTY + buf);
+                  arrive_issuer(fused ? B_H2FULL : B_H1 + c);
                 }
               }
               boff += hp;
             }
           }
           // ---- NN outputs -> physics -> Runge-Kutta update ----
-          bar_wait(bars, B_YFULL, mask);
+          bar_wait_t(bars, B_YFULL, mask, prof, eacc, E_YFULL - 8);
           ptx::tc_fence_after();
+          const long long t_phys = prof ? clock64() : 0;
           float y[3][32];
           {
             int boff = 0;
@@ -442,16 +524,26 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
             if (last) s_xn[on] = xv;
           };
           column_rhs<kNz, false, true>(a.P, bc, ts, X, Y, K, NoFlux());
+          const long long t_pub = prof ? clock64() : 0;
           if (rhs_idx + 1 < n_rhs) publish_x();  // also tells the MMA warp that Y has been consumed
+          if (prof) { eacc[E_PHYS - 8] += t_pub - t_phys; eacc[E_PUBLISH - 8] += clock64() - t_pub; }
         }
         if (a.save_every > 0 && (n + 1) % a.save_every == 0) save((n + 1) / a.save_every);
       }
       if (a.save_every <= 0) save(0);
     }
+    if (prof && lane == 0) {
+      eacc[E_TOTAL - 8] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) g_tc_wait[8 + i] = (unsigned long long)eacc[i];
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
+  if (NCTA == 2) ptx::cluster_sync();  // the peer's tensor / shared memory stay valid until both CTAs are done
+  else __syncthreads();
+  if (warp == 1) {
+    if (NCTA == 2) ptx::tmem_dealloc2<512>(tmem);
+    else ptx::tmem_dealloc<512>(tmem);
+  }
 }
 
 // ---- host: weight tape + op program ---------------------------------------------------------------
@@ -486,22 +578,26 @@ static uint16_t bf16_rne(float f) {
 // Appends the no-swizzle K-major block of W (Flux layout: element (k_in, n_out) at w[k*nout + n]) for
 // output rows [r0, r0+rows) and inputs [k0, k0 + 16*ksteps):  [k/8][row][k%8] BF16, zero padded.
 static void append_block(std::vector<uint16_t>& tape, bool fp16, const float* w, int nin, int nout, int r0, int rows,
-                         int k0, int ksteps) {
-  const size_t base = tape.size();
-  tape.resize(base + (size_t)rows * ksteps * 16, 0);
-  for (int kk = 0; kk < ksteps * 16; ++kk) {
-    const int k = k0 + kk;
-    if (k >= nin) continue;
-    for (int r = 0; r < rows; ++r) {
-      const int n = r0 + r;
-      if (n >= nout) continue;
-      const float v = w[(size_t)k * nout + n];
-      tape[base + ((size_t)(kk / 8) * rows + r) * 8 + (kk % 8)] = fp16 ? f16_rne(v) : bf16_rne(v);
+                         int k0, int ksteps, int ncta) {
+  // ncta = 2: two consecutive images of rows / 2 rows each (the leader's half first)
+  const int hrows = rows / ncta;
+  for (int half = 0; half < ncta; ++half) {
+    const size_t base = tape.size();
+    tape.resize(base + (size_t)hrows * ksteps * 16, 0);
+    for (int kk = 0; kk < ksteps * 16; ++kk) {
+      const int k = k0 + kk;
+      if (k >= nin) continue;
+      for (int r = 0; r < hrows; ++r) {
+        const int n = r0 + half * hrows + r;
+        if (n >= nout) continue;
+        const float v = w[(size_t)k * nout + n];
+        tape[base + ((size_t)(kk / 8) * hrows + r) * 8 + (kk % 8)] = fp16 ? f16_rne(v) : bf16_rne(v);
+      }
     }
   }
 }
 
-static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, Plan& pl, std::vector<uint16_t>& tape,
+static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, int ncta, Plan& pl, std::vector<uint16_t>& tape,
                       std::vector<float>& bias) {
   const NetDesc& nd = m->nd;
   const int L = nd.n_layers;
@@ -510,6 +606,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   pl.L = L;
   pl.act = nd.act;
   pl.fp16 = fp16;
+  pl.ncta = ncta;
   int bias_per_net = 0;
   for (int j = 0; j < L - 1; ++j) {
     pl.hpad[j] = (nd.sizes[j + 1] + 15) / 16 * 16;
@@ -538,7 +635,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
     op.n = 32;
     op.ksteps = (uint8_t)(p.cols / 16);  // <= 4
     op.flags = F_WAIT_H2 | F_D_IS_Y | F_COMMIT_H2E | (p.c > 0 ? F_ACC : 0) | (final_op ? F_COMMIT_Y : 0);
-    append_block(tape, fp16, wn + nd.w_off[L - 1], nd.sizes[L - 1], nd.sizes[L], 0, 32, p.c * kCW, op.ksteps);
+    append_block(tape, fp16, wn + nd.w_off[L - 1], nd.sizes[L - 1], nd.sizes[L], 0, 32, p.c * kCW, op.ksteps, ncta);
     push(op);
   };
   for (int net = 0; net < 3; ++net) {
@@ -556,7 +653,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
       const int hp = pl.hpad[j];
       for (int c = 0; c * kCW < hp; ++c) {
         const int rows = std::min(kCW, hp - c * kCW);
-        const int max_ks = std::min(kMaxKsteps, kSlotBytes / (rows * 32));
+        const int max_ks = std::min(kMaxKsteps, kSlotBytes / ((rows / ncta) * 32));
         const int n_stage = (ksteps_total + max_ks - 1) / max_ks;
         const int ks_per = (ksteps_total + n_stage - 1) / n_stage;
         if (net == 0) (rows == kCW ? pl.ks_full[j] : pl.ks_tail[j]) = ks_per;
@@ -574,7 +671,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
             if (c == 0 && k == 0) op.flags |= F_H1_RESET;
             op.h1_need = (uint8_t)(((k + ks) * 16 + kCW - 1) / kCW);  // HF chunks covering inputs [0, 16(k+ks))
           }
-          append_block(tape, fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW, rows, k * 16, ks);
+          append_block(tape, fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW, rows, k * 16, ks, ncta);
           push(op);
         }
         // the output-layer MMAs of the PREVIOUS fused chunk go after this chunk's MMAs, so the tensor
@@ -604,7 +701,9 @@ int tc_model_prepare(opz_model* m, int precision) {
   if (!pl) { pl = new Plan(); m->tc_plan = pl; }
   std::vector<uint16_t> tape;
   std::vector<float> bias;
-  int rc = build_plan(m, w, fp16, *pl, tape, bias);
+  int ncta = 1;  // OPZ_TC_PAIR=1 selects the CTA-pair (cta_group::2) variant
+  if (const char* e = getenv("OPZ_TC_PAIR")) ncta = atoi(e) ? 2 : 1;
+  int rc = build_plan(m, w, fp16, ncta, *pl, tape, bias);
   if (rc) return rc;
   int copies = 1;
   if (const char* e = getenv("OPZ_TC_TAPE_COPIES")) copies = atoi(e);
@@ -662,23 +761,54 @@ int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int preci
   a.tape_bytes = (uint32_t)pl->tape_bytes;
   a.tape_stride = (uint32_t)pl->tape_stride;
   a.n_copies = pl->n_copies;
+  a.profile = getenv("OPZ_TC_PROFILE") != nullptr;
   std::memcpy(a.ops, pl->ops, sizeof(Op) * pl->n_ops);
   const size_t smem = SmemLayout::bytes(pl->bias_per_net);
   if ((int)smem > ctx->smem_optin) { set_error("tensor-core path: shared memory budget exceeded"); return OPZ_EUNSUP; }
   using KernelT = void (*)(const Args);
-  static const KernelT table[2][6] = {
-      {rollout_tc_kernel<false, 0>, rollout_tc_kernel<false, 1>, rollout_tc_kernel<false, 2>, rollout_tc_kernel<false, 3>,
-       rollout_tc_kernel<false, 4>, rollout_tc_kernel<false, 5>},
-      {rollout_tc_kernel<true, 0>, rollout_tc_kernel<true, 1>, rollout_tc_kernel<true, 2>, rollout_tc_kernel<true, 3>,
-       rollout_tc_kernel<true, 4>, rollout_tc_kernel<true, 5>}};
-  const KernelT kern = table[fp16 ? 1 : 0][pl->act];
+#define OPZ_TC_ROW(F, N) {rollout_tc_kernel<F, 0, N>, rollout_tc_kernel<F, 1, N>, rollout_tc_kernel<F, 2, N>, \
+                          rollout_tc_kernel<F, 3, N>, rollout_tc_kernel<F, 4, N>, rollout_tc_kernel<F, 5, N>}
+  static const KernelT table[2][2][6] = {{OPZ_TC_ROW(false, 1), OPZ_TC_ROW(true, 1)}, {OPZ_TC_ROW(false, 2), OPZ_TC_ROW(true, 2)}};
+#undef OPZ_TC_ROW
+  const int ncta = pl->ncta;
+  const KernelT kern = table[ncta - 1][fp16 ? 1 : 0][pl->act];
   OPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (c.B + kM - 1) / kM;
-  int64_t grid = n_tiles < (int64_t)ctx->sm_count ? n_tiles : (int64_t)ctx->sm_count;
-  if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(a);
+  const int64_t n_items = (n_tiles + ncta - 1) / ncta;
+  int64_t grid = std::min<int64_t>(n_items, ctx->sm_count / ncta) * ncta;
+  if (grid < ncta) grid = ncta;
+  if (ncta == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OPZ_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  } else {
+    kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(a);
+  }
   OPZ_CUDA(cudaGetLastError());
   ctx->launches += 1;
+  if (a.profile) {
+    OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long w[16];
+    OPZ_CUDA(cudaMemcpyFromSymbol(w, g_tc_wait, sizeof(w)));
+    const int64_t my_tiles = (n_items + grid / ncta - 1) / (grid / ncta);
+    const int stages = c.scheme == OPZ_RK4 ? 4 : (c.scheme == OPZ_RK2 ? 2 : 1);
+    const double per = 1.0 / ((double)my_tiles * c.n_steps * stages);
+    fprintf(stderr, "opz tc profile (CTA 0, cycles per tile right-hand side): MMA warp total %.0f | wait X %.0f, D-empty %.0f, H1 %.0f, "
+            "weights %.0f, H2-full %.0f || epilogue warp total %.0f | wait D-full %.0f, H2-empty %.0f, Y-full %.0f, physics %.0f, publish %.0f\n",
+            w[W_TOTAL] * per, w[W_X] * per, w[W_DEMPTY] * per, w[W_H1] * per, w[W_FULL] * per, w[W_H2FULL] * per,
+            w[E_TOTAL] * per, w[E_DFULL] * per, w[E_H2EMPTY] * per, w[E_YFULL] * per, w[E_PHYS] * per, w[E_PUBLISH] * per);
+    fprintf(stderr, "    MMA issue blocks (elect .. commit .. syncwarp): %.0f cycles per tile right-hand side for %.0f MMAs\n", w[6] * per, w[7] * per);
+  }
   return OPZ_OK;
 }
 

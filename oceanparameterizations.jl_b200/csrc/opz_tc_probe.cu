@@ -139,3 +139,103 @@ extern "C" int opz_debug_umma(int N, int K, int mode, const uint16_t* A, const u
   cudaFree(da); cudaFree(db); cudaFree(dar); cudaFree(dd);
   return OPZ_OK;
 }
+
+// ---- issue-rate probe: how many cycles does one tcgen05.mma (M=128, N, K=16, kind::f16) cost when a single
+// thread issues `per_commit` of them back to back and then waits for the commit, `reps` times?
+namespace opz {
+__global__ void __launch_bounds__(192, 1) umma_rate_kernel(int N, int per_commit, int reps, int mode, int same_d, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x / 32;
+  if (warp == 0) {
+    if (threadIdx.x == 0) { ptx::mbar_init(bars, 1); ptx::mbar_init(bars + 1, 1); ptx::fence_barrier_init(); tmem_slot[1] = 0u; }
+    __syncwarp();
+    ptx::tmem_alloc<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = ptx::idesc_f16kind(128, N, true);
+    const uint32_t sb = ptx::smem_u32(smem), sa = ptx::smem_u32(smem + 48 * 1024);
+    uint32_t parity = 0;
+    long long t0 = 0, t1 = 0;
+    if (ptx::elect_one()) {
+      t0 = clock64();
+      long long t_issue = 0;
+      for (int r = 0; r < reps; ++r) {
+        const long long ti = clock64();
+        for (int i = 0; i < per_commit; ++i) {
+          const uint64_t bd = ptx::smem_desc(sb + (uint32_t)(i % 8) * 2u * (uint32_t)N * 16u, (uint32_t)N * 16u, 128);
+          const uint32_t d = tmem + ((same_d & 1) || same_d >= 10 ? 0u : (uint32_t)((i & 1) * N));
+          if ((mode & 1) == 0) ptx::mma_ss(d, ptx::smem_desc(sa + (uint32_t)(i % 8) * 4096u, 2048, 128), bd, idesc, i > 0);
+          else ptx::mma_ts(d, tmem + 256 + (uint32_t)(i % 16) * 8u, bd, idesc, i > 0);
+        }
+        if (same_d >= 10) {  // streaming variant: (same_d - 10) commits per batch, no completion wait inside
+          for (int cc = 0; cc < same_d - 10; ++cc) ptx::tc_commit(bars + 1);
+          t_issue += clock64() - ti;
+          continue;
+        }
+        ptx::tc_commit(bars);
+        t_issue += clock64() - ti;
+        ptx::mbar_wait(bars, parity);
+        parity ^= 1;
+      }
+      if (same_d >= 10) { ptx::tc_commit(bars); ptx::mbar_wait(bars, 0); }
+      t1 = clock64();
+      out[blockIdx.x] = t1 - t0;
+      out[gridDim.x + blockIdx.x] = t_issue;
+      *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = 1u;  // stop the load warps
+    }
+    __syncwarp();
+  } else if (warp >= 2 && (mode & 6)) {
+    // background TMEM traffic like the rollout kernel's epilogue: mode bit 1 = tcgen05.ld of 64 columns,
+    // bit 2 = tcgen05.st of 32 columns, on columns the MMAs do not touch
+    const uint32_t lane_addr = (uint32_t)((warp % 4) * 32) << 16;
+    volatile uint32_t* stop = reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
+    uint32_t sink = 0;
+    while (*stop == 0u) {
+      if (mode & 2) {
+        uint32_t r[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(tmem + lane_addr + 384 + g * 16, r[g]);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sink ^= r[g][3];
+      }
+      if (mode & 4) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = sink + j;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_st8(tmem + lane_addr + 448 + g * 8, pk);
+        ptx::tmem_wait_st();
+      }
+    }
+    if (sink == 0x12345u) out[0] = 0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem);
+}
+}  // namespace opz
+
+extern "C" int opz_debug_umma_rate(int N, int per_commit, int reps, int mode, int same_d, int grid, double* cycles_per_mma) {
+  long long* d;
+  OPZ_CUDA(cudaMalloc(&d, sizeof(long long) * 2 * grid));
+  const size_t smem = 96 * 1024 + 64;
+  OPZ_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_kernel<<<grid, 192, smem>>>(N, per_commit, reps, mode, same_d, d);
+  OPZ_CUDA(cudaGetLastError());
+  OPZ_CUDA(cudaDeviceSynchronize());
+  std::vector<long long> h(2 * grid);
+  OPZ_CUDA(cudaMemcpy(h.data(), d, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  long long mx = 0;
+  for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+  cycles_per_mma[0] = (double)mx / ((double)per_commit * reps);
+  cycles_per_mma[1] = (double)h[grid] / ((double)per_commit * reps);  // issue loop only (CTA 0)
+  return OPZ_OK;
+}
