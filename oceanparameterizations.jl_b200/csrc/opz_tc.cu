@@ -47,7 +47,7 @@ constexpr int kCW = 64;              // accumulator chunk width (TMEM columns)
 constexpr int kSlotBytes = 12288;    // 64 rows x 96 k x 2 B
 constexpr int kSlots = 6;
 constexpr int kMaxOps = 160;
-constexpr int kMaxKsteps = 12;        // k-steps per weight stage
+constexpr int kMaxKsteps = 6;         // k-steps per weight stage and CTA of the group (the issue sequence is unrolled this far)
 constexpr int kMaxHidden = 400;      // HF region: 200 TMEM columns
 constexpr int kThreads = 192;
 
@@ -276,39 +276,34 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
       const uint32_t idesc0 = ptx::idesc_f16kind(kM * NCTA, 0, FP16);
       const int L = a.L;
       // one weight stage: wait for its bytes, issue ks MMAs D (+)= A[k] * B[k]^T, release the slot
-      // The readiness of the NEXT slot is tested before this stage's MMAs are issued, so that the ~100-cycle
-      // try_wait latency hides behind the (pipe-paced) MMA issue; the MMAs are issued from a rolled loop so
-      // that the first one leaves as soon as its two operand addresses exist.
-      bool pre_ok = false;
+      // The MMAs are issued from a fully unrolled, predicated sequence: descriptor and address offsets are
+      // immediates, so consecutive tcgen05.mma leave back to back (a rolled loop with 64-bit descriptor
+      // arithmetic between the MMAs measured 1.6x slower end to end).
       auto stage = [&](uint32_t d, uint32_t a_col, uint32_t rows, int ks, bool acc_first) {
-        const long long tw0 = prof ? clock64() : 0;
-        if (pre_ok) mask ^= 1u << (B_FULL + slot);
-        else bar_wait(bars, B_FULL + slot, mask);
-        const uint32_t nslot = slot + 1 == kSlots ? 0 : slot + 1;
-        pre_ok = ptx::mbar_try_wait(bars + B_FULL + nslot, (mask >> (B_FULL + nslot)) & 1u);
-        ptx::tc_fence_after();
-        if (prof) wacc[W_FULL] += clock64() - tw0;  // orders the MMAs after the epilogue warps' tcgen05.st seen through the barriers waited on above
+        if (prof) {
+          const long long tw0 = clock64();
+          bar_wait(bars, B_FULL + slot, mask);
+          wacc[W_FULL] += clock64() - tw0;
+        } else {
+          bar_wait(bars, B_FULL + slot, mask);
+        }
+        ptx::tc_fence_after();  // orders the MMAs after the epilogue warps' tcgen05.st seen through the barriers waited on above
         // each CTA holds rows / NCTA rows of the block: [k/8][rows / NCTA][8]
-        uint64_t bd = ptx::smem_desc(ring_u32 + slot * kSlotBytes, (rows / NCTA) * 16u, 128);
+        const uint64_t bd0 = ptx::smem_desc(ring_u32 + slot * kSlotBytes, (rows / NCTA) * 16u, 128);
         const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
-        const long long ti0 = prof ? clock64() : 0;
+        const uint32_t kstride = 2u * rows / NCTA;  // descriptor units (16 B) per k-step
         if (ptx::elect_one()) {
-          uint32_t at = tmem + a_col;
-          if (NCTA == 2) ptx::mma_ts2(tmem + d, at, bd, idesc, acc_first);
-          else ptx::mma_ts(tmem + d, at, bd, idesc, acc_first);
-#pragma unroll 1
-          for (int k = 1; k < ks; ++k) {
-            at += 8u;
-            bd += (uint64_t)(2u * rows / NCTA);
-            if (NCTA == 2) ptx::mma_ts2(tmem + d, at, bd, idesc, true);
-            else ptx::mma_ts(tmem + d, at, bd, idesc, true);
-          }
+#pragma unroll
+          for (int k = 0; k < kMaxKsteps * NCTA; ++k)
+            if (k < ks) {
+              if (NCTA == 2) ptx::mma_ts2(tmem + d, tmem + a_col + (uint32_t)k * 8u, bd0 + (uint64_t)((uint32_t)k * kstride), idesc, acc_first || k > 0);
+              else ptx::mma_ts(tmem + d, tmem + a_col + (uint32_t)k * 8u, bd0 + (uint64_t)((uint32_t)k * kstride), idesc, acc_first || k > 0);
+            }
           if (NCTA == 2) ptx::tc_commit2(bars + B_EMPTY + slot);
           else ptx::tc_commit(bars + B_EMPTY + slot);
         }
         __syncwarp();
-        if (prof) { wacc[6] += clock64() - ti0; wacc[7] += ks; }
-        slot = nslot;
+        slot = slot + 1 == kSlots ? 0 : slot + 1;
       };
       for (int64_t item = item0; item < n_items; item += item_stride) {
 #pragma unroll 1
@@ -653,7 +648,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
       const int hp = pl.hpad[j];
       for (int c = 0; c * kCW < hp; ++c) {
         const int rows = std::min(kCW, hp - c * kCW);
-        const int max_ks = std::min(kMaxKsteps, kSlotBytes / ((rows / ncta) * 32));
+        const int max_ks = std::min(kMaxKsteps * ncta, kSlotBytes / ((rows / ncta) * 32));
         const int n_stage = (ksteps_total + max_ks - 1) / max_ks;
         const int ks_per = (ksteps_total + n_stage - 1) / n_stage;
         if (net == 0) (rows == kCW ? pl.ks_full[j] : pl.ks_tail[j]) = ks_per;
@@ -807,7 +802,6 @@ int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int preci
             "weights %.0f, H2-full %.0f || epilogue warp total %.0f | wait D-full %.0f, H2-empty %.0f, Y-full %.0f, physics %.0f, publish %.0f\n",
             w[W_TOTAL] * per, w[W_X] * per, w[W_DEMPTY] * per, w[W_H1] * per, w[W_FULL] * per, w[W_H2FULL] * per,
             w[E_TOTAL] * per, w[E_DFULL] * per, w[E_H2EMPTY] * per, w[E_YFULL] * per, w[E_PHYS] * per, w[E_PUBLISH] * per);
-    fprintf(stderr, "    MMA issue blocks (elect .. commit .. syncwarp): %.0f cycles per tile right-hand side for %.0f MMAs\n", w[6] * per, w[7] * per);
   }
   return OPZ_OK;
 }

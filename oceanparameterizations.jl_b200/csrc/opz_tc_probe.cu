@@ -169,12 +169,12 @@ __global__ void __launch_bounds__(192, 1) umma_rate_kernel(int N, int per_commit
         const long long ti = clock64();
         for (int i = 0; i < per_commit; ++i) {
           const uint64_t bd = ptx::smem_desc(sb + (uint32_t)(i % 8) * 2u * (uint32_t)N * 16u, (uint32_t)N * 16u, 128);
-          const uint32_t d = tmem + ((same_d & 1) || same_d >= 10 ? 0u : (uint32_t)((i & 1) * N));
+          const uint32_t d = tmem + (same_d >= 20 ? (uint32_t)((i & 1) * 128) : ((same_d & 1) || same_d >= 10 ? 0u : (uint32_t)((i & 1) * N)));  // >= 20: streaming, alternating accumulators
           if ((mode & 1) == 0) ptx::mma_ss(d, ptx::smem_desc(sa + (uint32_t)(i % 8) * 4096u, 2048, 128), bd, idesc, i > 0);
           else ptx::mma_ts(d, tmem + 256 + (uint32_t)(i % 16) * 8u, bd, idesc, i > 0);
         }
-        if (same_d >= 10) {  // streaming variant: (same_d - 10) commits per batch, no completion wait inside
-          for (int cc = 0; cc < same_d - 10; ++cc) ptx::tc_commit(bars + 1);
+        if (same_d >= 10) {  // streaming variant: (same_d % 10) commits per batch, no completion wait inside
+          for (int cc = 0; cc < same_d % 10; ++cc) ptx::tc_commit(bars + 1);
           t_issue += clock64() - ti;
           continue;
         }

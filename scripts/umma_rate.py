@@ -7,9 +7,10 @@ opz.default_context()
 fn = opz.lib.opz_debug_umma_rate
 fn.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_double)]
 fn.restype = C.c_int
-for N in (64, 128):
-    for per in (1, 3, 6, 12, 25):
-        for commits in (0, 1, 2):
-            out = (C.c_double * 2)()
-            opz.check(fn(N, per, 200, 1, 10 + commits, 1, out))
-            print(f"TS N={N:3d} MMAs/batch={per:3d} commits/batch={commits}: {out[1] * per:8.1f} cycles per batch in the issue loop ({out[1]:6.1f}/MMA; floor {128 * N / 256:.0f})", flush=True)
+for mode, mname in ((1, "TS"), (0, "SS")):
+    for N in (32, 64, 96, 128, 256):
+        for per in (6, 25, 100):
+            for sd, dname in ((10, "same D"), (20, "alternating D")):
+                out = (C.c_double * 2)()
+                opz.check(fn(N, per, 200, mode, sd + 1, 1, out))
+                print(f"{mname} N={N:3d} {dname:14s} MMAs/batch={per:3d}: total {out[0]:6.1f} cycles/MMA, issue loop {out[1]:6.1f}/MMA; floor {128 * N / 256:.0f}", flush=True)
