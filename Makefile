@@ -3,7 +3,7 @@ NVCC ?= nvcc
 PKG := oceanparameterizations.jl_b200
 CSRC := $(PKG)/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -Xptxas -v
-SRCS := $(CSRC)/opz_capi.cu $(CSRC)/opz_fp32.cu $(CSRC)/opz_bptt.cu $(CSRC)/opz_tc.cu $(CSRC)/opz_tc_probe.cu
+SRCS := $(CSRC)/opz_capi.cu $(CSRC)/opz_fp32.cu $(CSRC)/opz_bptt.cu $(CSRC)/opz_tc.cu $(CSRC)/opz_tc2.cu $(CSRC)/opz_tc_probe.cu
 OBJS := $(SRCS:.cu=.o)
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/opz.h
 

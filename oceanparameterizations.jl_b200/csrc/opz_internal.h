@@ -33,6 +33,9 @@ struct opz_model {
   bool tc_pack_valid = false;
   int tc_pack_precision = -1;    // OPZ_PREC_* the tape was packed for
   void* tc_plan = nullptr;       // opaque (opz_tc.cu)
+  void* tc2_pack = nullptr;      // second-generation kernel (opz_tc2.cu): stage-ordered tape + biases
+  size_t tc2_pack_bytes = 0;
+  void* tc2_plan = nullptr;
 };
 
 namespace opz {
@@ -80,5 +83,9 @@ void bptt_release(opz_ctx* ctx);
 int tc_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights
 void tc_model_release(opz_model* m);
 int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
+// second generation (opz_tc2.cu): CTA pairs, chunk-sized weight stages, level-parallel physics; tc_* dispatch to it
+int tc2_model_prepare(opz_model* m, int precision);
+void tc2_model_release(opz_model* m);
+int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
 
 }  // namespace opz

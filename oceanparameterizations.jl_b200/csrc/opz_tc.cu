@@ -685,8 +685,20 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
 
 }  // namespace tc
 
+// OPZ_TC_V1=1 keeps the first-generation kernel of this file; the default is opz_tc2.cu
+static bool use_v2() {
+  const char* e = getenv("OPZ_TC_V1");
+  return !(e && atoi(e) != 0);
+}
+
 int tc_model_prepare(opz_model* m, int precision) {
   using namespace tc;
+  if (use_v2()) {
+    const int rc2 = tc2_model_prepare(m, precision);
+    if (rc2) return rc2;
+    m->tc_pack_valid = true;
+    return OPZ_OK;
+  }
   const bool fp16 = precision == OPZ_PREC_FP16;
   OPZ_CUDA(cudaSetDevice(m->ctx->device));
   std::vector<float> w((size_t)3 * m->nd.P);
@@ -723,6 +735,7 @@ int tc_model_prepare(opz_model* m, int precision) {
 }
 
 void tc_model_release(opz_model* m) {
+  tc2_model_release(m);
   if (m->tc_pack) cudaFree(m->tc_pack);
   m->tc_pack = nullptr;
   m->tc_pack_bytes = 0;
@@ -741,6 +754,10 @@ int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int preci
   if (c.P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {
     set_error("tensor-core path: smooth_NN / smooth_Ri are only available with OPZ_PREC_FP32");
     return OPZ_EUNSUP;
+  }
+  if (use_v2()) {
+    if (!m->tc_pack_valid) { set_error("tensor-core path: model not prepared"); return OPZ_EINVAL; }
+    return tc2_rollout(ctx, m, c, precision);
   }
   const Plan* pl = static_cast<const Plan*>(m->tc_plan);
   if (!pl || !m->tc_pack_valid || pl->fp16 != fp16) { set_error("tensor-core path: model not prepared for this precision"); return OPZ_EINVAL; }

@@ -1,0 +1,854 @@
+// opz_tc2.cu — second-generation tcgen05 / TMEM rollout kernel: CTA pairs, chunk-sized weight stages,
+// eight (or sixteen) epilogue warps and level-parallel physics.
+//
+// What changed against opz_tc.cu (kept as the OPZ_TC_V1=1 fallback and as the measured baseline):
+//   * the wait profile of v1 showed the single MMA-issuing warp as the limiter: ~570 cycles of bookkeeping per
+//     6-MMA weight stage (147 stages per right-hand side) against 192 cycles of tensor work.  Here a weight stage
+//     is a WHOLE accumulator chunk (up to 25 k-steps + the 4 output-layer k-steps of the previous fused chunk),
+//     43 stages per right-hand side, each issued from one unrolled, immediate-offset sequence;
+//   * that needs 27.6 KB per stage, which only fits because the kernel always runs as a CTA PAIR
+//     (tcgen05 cta_group::2, M = 256): each CTA stages HALF of every weight block and the hardware shares the
+//     halves, so L2 -> SM weight traffic per SM halves too.  The ring is a byte FIFO (host-computed offsets and
+//     "stages that may stay in flight" per stage) rather than fixed slots;
+//   * 8 epilogue warps (two per TMEM lane quadrant, 32 accumulator columns each) instead of 4 halve the drain
+//     latency per chunk, and the physics runs LEVEL-PARALLEL: two threads per ocean column, 16 cells each, with
+//     the NN-independent part (gradients, Ri, diffusivities, Coriolis) evaluated BEFORE the last output-layer
+//     MMAs have landed;
+//   * hidden-layer biases are read through L1 (prefetched before the accumulator barrier) — the shared memory
+//     they used to occupy now belongs to the weight ring.
+//
+// TMEM map, operand formats, barrier protocol between MMA issuer and epilogue and the numerics are those of v1
+// (see opz_tc.cu); the physics evaluates the same FP32 expressions per face as opz_device.cuh::column_rhs<FAST>.
+//
+// Replaces the batched form of NDE! / predict_flux! (wind_mixing/src/training_postprocessing.jl:105-153)
+// inside a fixed-step solve (solve_NDE_mutating, :55-159).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "opz_internal.h"
+#include "opz_ptx.cuh"
+
+namespace opz {
+namespace tc2 {
+
+constexpr int kNz = 32;
+constexpr int kS = 3 * kNz;          // 96 state entries per column
+constexpr int kM = 128;              // columns per tile (one tile per CTA, two per pair)
+constexpr int kLd = kM + 1;          // padded leading dimension of s_xn (conflict-free transposing copies)
+constexpr int kCW = 64;              // accumulator chunk width (TMEM columns)
+constexpr int kMaxHidden = 400;      // HF region: 200 TMEM columns
+constexpr int kNB = 8;               // stage barrier pairs (stages in flight <= kNB - 1)
+constexpr int kMaxStages = 48;       // stages per right-hand side
+constexpr int kRingBytes = 82944;    // 3 x (32 rows x 400 k + 16 rows x 64 k) x 2 B
+constexpr int kMaxKs = 28;           // 7 HF chunks x 4 k-steps
+
+constexpr uint32_t kColD0 = 0, kColY = 128, kColX = 224, kColH2 = 272, kColHF = 304;
+
+enum : int {
+  B_FULL = 0,                   // [kNB] stage bytes landed               (producer expect_tx + peer forward)
+  B_EMPTY = B_FULL + kNB,       // [kNB] stage consumed                   (tcgen05.commit, both CTAs)
+  B_DFULL = B_EMPTY + kNB,      // [2] accumulator chunk complete         (tcgen05.commit, both CTAs)
+  B_DEMPTY = B_DFULL + 2,       // [2] accumulator chunk drained          (epilogue warps of both CTAs)
+  B_H1 = B_DEMPTY + 2,          // [7] chunk c of HF written
+  B_H2FULL = B_H1 + 7,          // H2c written
+  B_H2EMPTY = B_H2FULL + 1,     // H2c consumed by the output-layer MMAs  (tcgen05.commit)
+  B_YFULL = B_H2EMPTY + 1,      // Y complete                             (tcgen05.commit)
+  B_XFULL = B_YFULL + 1,        // X written, Y consumed
+  B_COUNT = B_XFULL + 1
+};
+static_assert(B_COUNT <= 32, "phase bits are tracked in one 32-bit mask");
+
+struct Plan {                     // host-side, cached on the model
+  int L = 0;
+  int hpad[2] = {0, 0};
+  int act = 0;
+  bool fp16 = false;
+  int bias_per_net = 0;           // floats: padded hidden biases, then 32 output biases
+  int n_stages = 0;
+  uint32_t st_off[kMaxStages];    // ring offset of the stage (bytes)
+  uint32_t st_bytes[kMaxStages];  // bytes PER CTA
+  uint32_t st_src[kMaxStages];    // tape offset of the stage (leader half first, then the peer half)
+  uint8_t st_keep[kMaxStages];    // earlier stages that may still be in flight when this one is filled
+  size_t tape_bytes = 0;
+  uint8_t* tape_dev = nullptr;
+  float* bias_dev = nullptr;      // [3][bias_per_net]
+};
+
+struct Args {
+  DevParams P;
+  const uint8_t* tape;
+  const float* bias;
+  const float* x0;
+  const float* bc;
+  float* out;
+  int64_t B;
+  int scheme;
+  float dt, t0;
+  int n_steps, save_every, n_save;
+  int L, bias_per_net, n_stages;
+  int hpad[2];
+  int exp;
+  uint32_t st_off[kMaxStages];
+  uint32_t st_bytes[kMaxStages];
+  uint32_t st_src[kMaxStages];
+  uint8_t st_keep[kMaxStages];
+};
+
+struct SmemLayout {
+  static constexpr size_t off_xn = 0;
+  static constexpr size_t off_acc = off_xn + (size_t)kS * kLd * 4;
+  static constexpr size_t off_xs = off_acc + (size_t)kS * kM * 4;
+  static constexpr size_t off_ring = (off_xs + (size_t)kS * kM * 4 + 127) / 128 * 128;
+  static constexpr size_t off_bars = off_ring + (size_t)kRingBytes;
+  static constexpr size_t off_tmem = off_bars + 8 * B_COUNT;
+  static constexpr size_t off_b3 = off_tmem + 16;            // [3][32] output-layer biases
+  static constexpr size_t bytes = off_b3 + sizeof(float) * 96;
+};
+
+__device__ __forceinline__ void bar_wait(uint64_t* bars, int id, uint32_t& mask) {
+  ptx::mbar_wait(bars + id, (mask >> id) & 1u);
+  mask ^= 1u << id;
+}
+
+// wait-time profile (OPZ_TC_PROFILE=1, relu kernels only): [0..7] MMA warp, [8..15] first epilogue warp of CTA 0
+__device__ unsigned long long g_tc2_wait[16];
+enum { W_X = 0, W_DEMPTY = 1, W_H1 = 2, W_FULL = 3, W_H2FULL = 4, W_TOTAL = 5,
+       E_DFULL = 8, E_H2EMPTY = 9, E_YFULL = 10, E_PHYS_A = 11, E_TOTAL = 12, E_PHYS_B = 13, E_LD = 14, E_ST = 15 };
+template <bool PROF>
+__device__ __forceinline__ void bar_wait_t(uint64_t* bars, int id, uint32_t& mask, long long* acc, int slot) {
+  if constexpr (PROF) {
+    const long long t0 = clock64();
+    bar_wait(bars, id, mask);
+    acc[slot] += clock64() - t0;
+  } else {
+    bar_wait(bars, id, mask);
+  }
+}
+
+template <bool FP16, int ACT>
+__device__ __forceinline__ uint32_t pack_act(float a, float b) {
+  if constexpr (ACT == OPZ_ACT_RELU) return FP16 ? ptx::pack_f16x2_relu(a, b) : ptx::pack_bf16x2_relu(a, b);
+  a = act_fast<ACT>(a);
+  b = act_fast<ACT>(b);
+  return FP16 ? ptx::pack_f16x2(a, b) : ptx::pack_bf16x2(a, b);
+}
+
+// ROWS x (16 KIN) weight block against KIN k-steps of the A operand: one straight run of tcgen05.mma whose
+// descriptor / address offsets are immediates (issued by the elected lane)
+template <int ROWS, int KIN>
+__device__ __forceinline__ void issue_static(uint32_t d, uint32_t a0, uint64_t bd0, uint32_t idesc) {
+  const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+#pragma unroll
+  for (int k = 0; k < KIN; ++k) ptx::mma_ts2_lohi(d, a0 + (uint32_t)k * 8u, lo + (uint32_t)(k * ROWS), hi, idesc, k > 0);
+}
+
+// E epilogue warps per CTA: E / 4 threads share one ocean column (TMEM lane); each owns LV = 128 / E cells.
+template <bool FP16, int ACT, int E, bool PROF>
+__global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __grid_constant__ Args a) {
+  constexpr int kThreads = (2 + E) * 32;
+  constexpr int kEpiThreads = E * 32;
+  constexpr int PS = E / 4;            // threads per column
+  constexpr int LV = kNz / PS;         // cells per thread
+  constexpr int CPW = kCW / PS;        // accumulator columns per warp and chunk
+  static_assert(E == 8 || E == 16, "8 or 16 epilogue warps");
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* s_xn = reinterpret_cast<float*>(smem + SmemLayout::off_xn);
+  float* s_acc = reinterpret_cast<float*>(smem + SmemLayout::off_acc);
+  float* s_xs = reinterpret_cast<float*>(smem + SmemLayout::off_xs);
+  uint8_t* s_ring = smem + SmemLayout::off_ring;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::off_bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_tmem);
+  float* s_b3 = reinterpret_cast<float*>(smem + SmemLayout::off_b3);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t n_tiles = (a.B + kM - 1) / kM;
+  const int stages = a.scheme == OPZ_RK4 ? 4 : (a.scheme == OPZ_RK2 ? 2 : 1);
+  const int n_rhs = a.n_steps * stages;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int64_t n_items = (n_tiles + 1) / 2;      // one pair of adjacent tiles per cluster and iteration
+  const int64_t item0 = blockIdx.x / 2, item_stride = gridDim.x / 2;
+  const uint32_t leader_bars = ptx::mapa(ptx::smem_u32(bars), 0u);
+  auto arrive_issuer = [&](int id) {              // barriers the MMA issuer waits on live in the leader CTA
+    if (rank != 0) ptx::mbar_arrive_remote_relaxed(leader_bars + 8u * (uint32_t)id);
+    else ptx::mbar_arrive_relaxed(bars + id);
+  };
+  int boff_out = 0;
+  for (int j = 0; j < a.L - 1; ++j) boff_out += a.hpad[j];
+  for (int i = threadIdx.x; i < 96; i += kThreads) s_b3[i] = a.bias[(i / 32) * a.bias_per_net + boff_out + (i % 32)];
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kNB; ++s) { ptx::mbar_init(bars + B_FULL + s, rank == 0 ? 2 : 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(bars + B_DFULL + b, 1); ptx::mbar_init(bars + B_DEMPTY + b, 2 * E); }
+      for (int c = 0; c < 7; ++c) ptx::mbar_init(bars + B_H1 + c, 2 * E);
+      ptx::mbar_init(bars + B_H2FULL, 2 * E);
+      ptx::mbar_init(bars + B_H2EMPTY, 1);
+      ptx::mbar_init(bars + B_YFULL, 1);
+      ptx::mbar_init(bars + B_XFULL, 2 * E);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc2<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= weight-tape producer (one per CTA: its half of every stage) =================
+    if (lane == 0 && n_rhs > 0) {
+      uint32_t gs = 0, c = 0;   // stages issued / stages known to be consumed
+      for (int64_t item = item0; item < n_items; item += item_stride) {
+        for (int r = 0; r < n_rhs; ++r) {
+          for (int s = 0; s < a.n_stages; ++s, ++gs) {
+            const uint32_t keep = a.st_keep[s];
+            while (c + keep < gs) {  // stage c must have been consumed: its bytes (or its barrier pair) are reused
+              ptx::mbar_wait(bars + B_EMPTY + (c % kNB), (c / kNB) & 1u);
+              ++c;
+            }
+            const uint32_t bytes = a.st_bytes[s];
+            uint64_t* full = bars + B_FULL + (gs % kNB);
+            ptx::mbar_arrive_expect_tx(full, bytes);
+            ptx::bulk_g2s(s_ring + a.st_off[s], a.tape + a.st_src[s] + rank * bytes, bytes, full);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && rank != 0) {
+    // ================= peer CTA: forward "my half of the stage has landed" to the leader =================
+    if (lane == 0 && n_rhs > 0) {
+      uint32_t gs = 0;
+      for (int64_t item = item0; item < n_items; item += item_stride)
+        for (int r = 0; r < n_rhs; ++r)
+          for (int s = 0; s < a.n_stages; ++s, ++gs) {
+            ptx::mbar_wait(bars + B_FULL + (gs % kNB), (gs / kNB) & 1u);
+            ptx::mbar_arrive_remote_relaxed(leader_bars + 8u * (uint32_t)(B_FULL + (gs % kNB)));
+          }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA) =================
+    // The whole warp walks the schedule (the loops build_plan() used to lay out the tape) with warp-uniform
+    // counters; one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    if (n_rhs > 0) {
+      uint32_t mask = (1u << (B_DEMPTY + 0)) | (1u << (B_DEMPTY + 1));  // "drained" starts released
+      uint32_t gs = 0, g = 0;
+      long long wacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long t_begin = PROF ? clock64() : 0;
+      const uint32_t ring_u32 = ptx::smem_u32(s_ring);
+      const uint32_t idesc0 = ptx::idesc_f16kind(2 * kM, 0, FP16);
+      const int L = a.L;
+      auto wait_full = [&]() {
+        if constexpr (PROF) {
+          const long long t0 = clock64();
+          ptx::mbar_wait(bars + B_FULL + (gs % kNB), (gs / kNB) & 1u);
+          wacc[W_FULL] += clock64() - t0;
+        } else {
+          ptx::mbar_wait(bars + B_FULL + (gs % kNB), (gs / kNB) & 1u);
+        }
+      };
+      for (int64_t item = item0; item < n_items; item += item_stride) {
+#pragma unroll 1
+        for (int r = 0; r < n_rhs; ++r) {
+          bool have_pend = false;
+          uint32_t pend_net = 0, pend_c = 0, pend_ks = 0;
+          int s = 0;
+          // output-layer MMAs of the pending fused chunk: Y_net (+)= H2c * W_out[:, chunk]^T, B block at `boff`
+          auto out_op = [&](uint32_t boff, int commit_a, int commit_b) {
+            bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);
+            ptx::tc_fence_after();
+            const uint64_t bd0 = ptx::smem_desc(ring_u32 + boff, 16u * 16u, 128);  // 16 rows per CTA
+            const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+            const uint32_t idesc = idesc0 | ((32u >> 3) << 17);
+            const uint32_t dy = tmem + kColY + 32u * pend_net;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < (int)pend_ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, hi, idesc, pend_c > 0 || k > 0);
+              ptx::tc_commit2(bars + B_H2EMPTY);
+              ptx::tc_commit2(bars + commit_a);
+              if (commit_b >= 0) ptx::tc_commit2(bars + commit_b);
+            }
+            __syncwarp();
+            have_pend = false;
+          };
+          bar_wait_t<PROF>(bars, B_XFULL, mask, wacc, W_X);
+#pragma unroll 1
+          for (int net = 0; net < 3; ++net) {
+#pragma unroll 1
+            for (int j = 0; j < L - 1; ++j) {
+              const bool fused = (j == L - 2);
+              const int kin = (j == 0) ? kS / 16 : a.hpad[j - 1] / 16;
+              const int hp = a.hpad[j];
+              const uint32_t a_base = (j == 0) ? kColX : kColHF;
+#pragma unroll 1
+              for (int c0 = 0; c0 < hp; c0 += kCW, ++s, ++gs) {
+                const uint32_t rows = (uint32_t)min(kCW, hp - c0);
+                const uint32_t buf = g & 1u;
+                ++g;
+                wait_full();
+                bar_wait_t<PROF>(bars, B_DEMPTY + buf, mask, wacc, W_DEMPTY);
+                const uint32_t sbase = ring_u32 + a.st_off[s];
+                const uint64_t bd0 = ptx::smem_desc(sbase, (rows / 2) * 16u, 128);  // this CTA holds rows / 2 rows: [k/8][rows/2][8]
+                const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
+                const uint32_t d = tmem + kColD0 + buf * kCW;
+                const bool wait_h1 = (j > 0) && (c0 == 0);   // HF chunk h covers k-steps [4h, 4h + 4)
+                const bool more = have_pend;                 // output-layer MMAs follow in this stage
+                if (!wait_h1 && rows == (uint32_t)kCW && (kin == 25 || kin == 6)) {
+                  // hot path: full-width chunk whose A operand is already complete
+                  ptx::tc_fence_after();
+                  if (ptx::elect_one()) {
+                    if (kin == 25) issue_static<kCW, 25>(d, tmem + a_base, bd0, idesc);
+                    else issue_static<kCW, 6>(d, tmem + a_base, bd0, idesc);
+                    ptx::tc_commit2(bars + B_DFULL + buf);
+                    if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                  }
+                  __syncwarp();
+                } else {
+#pragma unroll
+                  for (int h = 0; h < kMaxKs / 4; ++h) {
+                    if (h * 4 < kin) {
+                      if (wait_h1) bar_wait_t<PROF>(bars, B_H1 + h, mask, wacc, W_H1);
+                      ptx::tc_fence_after();  // orders the MMAs after the epilogue's tcgen05.st seen through the barriers above
+                      if (ptx::elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                          const int k = h * 4 + kk;
+                          if (k < kin) ptx::mma_ts2(d, tmem + a_base + (uint32_t)k * 8u, bd0 + (uint64_t)((uint32_t)k * rows), idesc, k > 0);
+                        }
+                      }
+                      __syncwarp();
+                    }
+                  }
+                  if (ptx::elect_one()) {
+                    ptx::tc_commit2(bars + B_DFULL + buf);
+                    if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                  }
+                  __syncwarp();
+                }
+                // the output-layer MMAs of the PREVIOUS fused chunk ride in this stage, after this chunk's MMAs, so
+                // that the tensor pipe has work while the epilogue converts that chunk
+                if (more) out_op(a.st_off[s] + (rows / 2) * (uint32_t)kin * 32u, B_EMPTY + (int)(gs % kNB), -1);
+                if (fused) { have_pend = true; pend_net = (uint32_t)net; pend_c = (uint32_t)(c0 / kCW); pend_ks = rows >> 4; }
+              }
+            }
+          }
+          // the last fused chunk's output-layer MMAs have a (small) stage of their own
+          wait_full();
+          out_op(a.st_off[s], B_EMPTY + (int)(gs % kNB), B_YFULL);
+          ++gs;
+        }
+      }
+      if (PROF && blockIdx.x == 0 && lane == 0) {
+        wacc[W_TOTAL] = clock64() - t_begin;
+        for (int i = 0; i < 8; ++i) g_tc2_wait[i] = (unsigned long long)wacc[i];
+      }
+    }
+  } else {
+    // ================= epilogue + physics =================
+    // warp -> TMEM lane quadrant q (hardware: warp % 4) and sub-index ps; thread (q, lane) = ocean column m;
+    // the PS threads of a column split the accumulator columns of every chunk and the cells of the physics.
+    const int e = warp - 2;
+    const int q = warp % 4;
+    const int ps = e / 4;
+    const int m = q * 32 + lane;
+    const int etid = e * 32 + lane;
+    const int c0 = ps * LV;            // first cell this thread owns
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t mask = 1u << B_H2EMPTY;   // released state
+    uint32_t g = 0;
+    const float h = a.dt;
+    const DevParams& P = a.P;
+    const bool prof_me = PROF && blockIdx.x == 0 && warp == 2;
+    const bool getenv_nobias = a.exp & 1;  // EXPERIMENT
+    long long eacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = PROF ? clock64() : 0;
+    auto epi_bar_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
+
+    for (int64_t item = item0; item < n_items; item += item_stride) {
+      const int64_t tile = item * 2 + rank;   // may be one past the last tile for the peer: a padding tile, never stored
+      const int64_t col0 = tile * kM;
+      const int64_t col = col0 + m;
+      // ---- load the initial profiles (coalesced through the padded state array) ----
+      epi_bar_sync();  // previous tile's snapshot readers are done with s_xn
+      for (int ee = etid; ee < kM * kS; ee += kEpiThreads) {
+        const int mm = ee / kS, i = ee - mm * kS;
+        const int64_t c = col0 + mm;
+        s_xn[i * kLd + mm] = c < a.B ? a.x0[c * kS + i] : 0.0f;
+      }
+      float bc[OPZ_BC_STRIDE];
+#pragma unroll
+      for (int qq = 0; qq < OPZ_BC_STRIDE; ++qq) bc[qq] = col < a.B ? a.bc[col * OPZ_BC_STRIDE + qq] : 0.0f;
+      epi_bar_sync();
+      auto save = [&](int slot_idx) {
+        epi_bar_sync();  // every column's s_xn is final
+        for (int ee = etid; ee < kM * kS; ee += kEpiThreads) {
+          const int mm = ee / kS, i = ee - mm * kS;
+          const int64_t c = col0 + mm;
+          if (c < a.B) a.out[(c * a.n_save + slot_idx) * kS + i] = s_xn[i * kLd + mm];
+        }
+      };
+      if (a.save_every > 0) save(0);
+      // 16-bit image of this thread's cells of the stage state -> tensor memory (A operand of the first layers)
+      auto publish_x = [&](const float (&xv)[3][LV]) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          uint32_t pk[LV / 2];
+#pragma unroll
+          for (int j = 0; j < LV / 2; ++j) pk[j] = pack_act<FP16, OPZ_ACT_IDENTITY>(xv[v][2 * j], xv[v][2 * j + 1]);
+          const uint32_t dst = tmem + lane_addr + kColX + (uint32_t)(v * (kNz / 2) + c0 / 2);
+          if constexpr (LV == 16) ptx::tmem_st8(dst, pk);
+          else ptx::tmem_st4(dst, pk);
+        }
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_issuer(B_XFULL);
+      };
+      {
+        float xv[3][LV];
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+          for (int i = 0; i < LV; ++i) {
+            const int idx = v * kNz + c0 + i;
+            xv[v][i] = s_xn[idx * kLd + m];
+            s_xs[idx * kM + m] = xv[v][i];
+          }
+        if (n_rhs > 0) publish_x(xv);
+      }
+
+      int rhs_idx = 0;
+#pragma unroll 1
+      for (int n = 0; n < a.n_steps; ++n) {
+        const float tn = a.t0 + (float)n * h;
+#pragma unroll 1
+        for (int st = 0; st < stages; ++st, ++rhs_idx) {
+          // ---- drain the accumulator chunks of the hidden layers ----
+#pragma unroll 1
+          for (int net = 0; net < 3; ++net) {
+            const float* bnet = a.bias + net * a.bias_per_net;
+            int boff = 0;
+#pragma unroll 1
+            for (int j = 0; j < a.L - 1; ++j) {
+              const bool fused = (j == a.L - 2);
+              const int hp = a.hpad[j];
+#pragma unroll 1
+              for (int c = 0; c * kCW < hp; ++c) {
+                const uint32_t buf = g & 1u;
+                ++g;
+                const int ncols = min(kCW, hp - c * kCW) - ps * CPW;   // columns of this chunk that belong to this warp (<= 0: none)
+                // biases of this warp's columns: through L1, requested before the barrier wait
+                float4 b4[CPW / 4];
+                {
+                  const float4* bb = reinterpret_cast<const float4*>(bnet + boff + c * kCW + ps * CPW);
+#pragma unroll
+                  for (int i = 0; i < CPW / 4; ++i) b4[i] = (getenv_nobias) ? make_float4(0.f, 0.f, 0.f, 0.f) : ((i * 4 < ncols) ? __ldg(bb + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+                if (prof_me) bar_wait_t<PROF>(bars, B_DFULL + buf, mask, eacc, E_DFULL - 8);
+                else bar_wait(bars, B_DFULL + buf, mask);
+                ptx::tc_fence_after();
+                const long long t_ld = prof_me ? clock64() : 0;
+                const uint32_t src = tmem + lane_addr + kColD0 + buf * kCW + (uint32_t)(ps * CPW);
+                const uint32_t dst = tmem + lane_addr + (fused ? kColH2 : kColHF + (uint32_t)c * (kCW / 2)) + (uint32_t)(ps * CPW / 2);
+                uint32_t rr[CPW / 16][16];
+#pragma unroll
+                for (int grp = 0; grp < CPW / 16; ++grp)
+                  if (grp * 16 < ncols) ptx::tmem_ld16(src + grp * 16, rr[grp]);
+                ptx::tmem_wait_ld();
+                if (prof_me) eacc[E_LD - 8] += clock64() - t_ld;
+                uint32_t pk[CPW / 16][8];
+#pragma unroll
+                for (int grp = 0; grp < CPW / 16; ++grp) {
+                  if (grp * 16 < ncols) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                      const float4 b = b4[grp * 4 + jj];
+                      pk[grp][2 * jj] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][4 * jj]) + b.x, __uint_as_float(rr[grp][4 * jj + 1]) + b.y);
+                      pk[grp][2 * jj + 1] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][4 * jj + 2]) + b.z, __uint_as_float(rr[grp][4 * jj + 3]) + b.w);
+                    }
+                  }
+                }
+                if (fused) {  // the output-layer MMAs of the previous chunk must have consumed H2c
+                  if (prof_me) bar_wait_t<PROF>(bars, B_H2EMPTY, mask, eacc, E_H2EMPTY - 8);
+                  else bar_wait(bars, B_H2EMPTY, mask);
+                  ptx::tc_fence_after();
+                }
+                const long long t_st = prof_me ? clock64() : 0;
+#pragma unroll
+                for (int grp = 0; grp < CPW / 16; ++grp)
+                  if (grp * 16 < ncols) ptx::tmem_st8(dst + grp * 8, pk[grp]);
+                ptx::tmem_wait_st();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  arrive_issuer(B_DEMPTY + buf);
+                  arrive_issuer(fused ? B_H2FULL : B_H1 + c);
+                }
+                if (prof_me) eacc[E_ST - 8] += clock64() - t_st;
+              }
+              boff += hp;
+            }
+          }
+          // ---- physics, part A: everything that does not need the NN outputs (runs while the last output-layer
+          //      MMAs are still in flight).  Index i of the x arrays is cell c0 - 1 + i. ----
+          epi_bar_sync();  // the stage state written by the other warps of this tile (previous right-hand side) is visible
+          const long long t_a = PROF ? clock64() : 0;
+          float Du[LV + 1], Dv[LV + 1], DT[LV + 1];   // diffusive part of the flux on faces c0 .. c0 + LV
+          float cu[LV], cv[LV];                        // Coriolis terms of the owned cells
+          {
+            float xu[LV + 2], xw[LV + 2], xT[LV + 2];
+#pragma unroll
+            for (int i = 0; i < LV + 2; ++i) {
+              const int cell = c0 - 1 + i;
+              const bool ok = cell >= 0 && cell < kNz;
+              xu[i] = ok ? s_xs[cell * kM + m] : 0.0f;
+              xw[i] = ok ? s_xs[(kNz + cell) * kM + m] : 0.0f;
+              xT[i] = ok ? s_xs[(2 * kNz + cell) * kM + m] : 0.0f;
+            }
+            const bool mpp = P.flags & OPZ_FLAG_MPP;
+#pragma unroll
+            for (int i = 0; i <= LV; ++i) {
+              const int f = c0 + i;
+              Du[i] = 0.0f; Dv[i] = 0.0f; DT[i] = 0.0f;
+              if (mpp && f >= 1 && f < kNz) {
+                const float gu = (xu[i + 1] - xu[i]) * P.nzf;
+                const float gv = (xw[i + 1] - xw[i]) * P.nzf;
+                const float gT = (xT[i + 1] - xT[i]) * P.nzf;
+                const float Ri = richardson<true>(P, gu, gv, gT);
+                const float nu = nu_of_ri<true>(P, Ri);
+                const float nuT = nuT_of<true>(P, nu, gu, gT);
+                Du[i] = P.c_u * nu * gu;
+                Dv[i] = P.c_v * nu * gv;
+                DT[i] = P.c_T * nuT * gT;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < LV; ++i) {
+              cu[i] = P.cor_u * (P.s_v * xw[i + 1] + P.mu_v);
+              cv[i] = P.cor_v * (P.s_u * xu[i + 1] + P.mu_u);
+            }
+          }
+          float ts = tn;
+          if (a.scheme == OPZ_RK4) ts = (st == 0) ? tn : (st == 3 ? tn + h : tn + h * 0.5f);
+          else if (a.scheme == OPZ_RK2) ts = (st == 0) ? tn : tn + h;
+          const float Fb[3] = {bc[0] - P.off[0], bc[2] - P.off[1], bc[4] - P.off[2]};
+          const float Ft[3] = {bc[1] - P.off[0], bc[3] - P.off[1], wT_top_value(P, bc, ts)};
+          // ---- NN outputs ----
+          if (prof_me) { eacc[E_PHYS_A - 8] += clock64() - t_a; bar_wait_t<PROF>(bars, B_YFULL, mask, eacc, E_YFULL - 8); }
+          else bar_wait(bars, B_YFULL, mask);
+          ptx::tc_fence_after();
+          const long long t_b = PROF ? clock64() : 0;
+          // Runge-Kutta bookkeeping in the oracle's operation order: acc = k1 (+ 2 k2 + 2 k3);
+          // stage input xs = xn + cs k; last stage xn += cf (acc + k)
+          const bool first = (st == 0), last = (st == stages - 1);
+          const float wk = (a.scheme == OPZ_RK4 && !first && !last) ? 2.0f : 1.0f;
+          const float cs = (a.scheme == OPZ_RK4 && st < 2) ? h * 0.5f : h;
+          const float cf = a.scheme == OPZ_RK4 ? h / 6.0f : (a.scheme == OPZ_RK2 ? h * 0.5f : h);
+          const float cx = last ? cf : cs;
+          float xnew[3][LV];
+          epi_bar_sync();  // every thread has read the old stage state of its neighbours' cells
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            // total flux on faces c0 .. c0 + LV: face f > 0 interior takes NN output j = f - 1 (TMEM column j of Y_v)
+            float F[LV + 1];
+            {
+              const uint32_t ybase = tmem + lane_addr + kColY + (uint32_t)(v * 32);
+              uint32_t ylo[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, yhi[LV];
+              if (c0 > 0) ptx::tmem_ld8(ybase + (uint32_t)(c0 - 8), ylo);   // ylo[7] = output c0 - 1 (face c0)
+              if constexpr (LV == 16) ptx::tmem_ld16(ybase + (uint32_t)c0, yhi);
+              else ptx::tmem_ld8(ybase + (uint32_t)c0, yhi);
+              ptx::tmem_wait_ld();
+              const float* b3 = s_b3 + v * 32;
+              const float* D = v == 0 ? Du : (v == 1 ? Dv : DT);
+#pragma unroll
+              for (int i = 0; i <= LV; ++i) {
+                const int f = c0 + i;
+                if (f == 0) F[i] = Fb[v];
+                else if (f == kNz) F[i] = Ft[v];
+                else {
+                  const float y = (i == 0 ? __uint_as_float(ylo[7]) : __uint_as_float(yhi[i == 0 ? 0 : i - 1])) + b3[f - 1];
+                  F[i] = y - D[i];
+                }
+              }
+            }
+            const float A = v == 0 ? P.A_u : (v == 1 ? P.A_v : P.A_T);
+#pragma unroll
+            for (int i = 0; i < LV; ++i) {
+              float k = A * ((F[i + 1] - F[i]) * P.nzf);
+              if (v == 0) k += cu[i];
+              else if (v == 1) k -= cv[i];
+              const int idx = v * kNz + c0 + i;
+              const int o = idx * kM + m, on = idx * kLd + m;
+              const float xo = s_xn[on];
+              const float acc_in = first ? 0.0f : s_acc[o];
+              const float sum = acc_in + wk * k;       // first stage: 0 + 1*k == k exactly
+              const float xv = xo + cx * (last ? sum : k);
+              s_acc[o] = sum;
+              s_xs[o] = xv;
+              if (last) s_xn[on] = xv;
+              xnew[v][i] = xv;
+            }
+          }
+          if (rhs_idx + 1 < n_rhs) publish_x(xnew);  // also tells the MMA warp that Y has been consumed
+          if (prof_me) eacc[E_PHYS_B - 8] += clock64() - t_b;
+        }
+        if (a.save_every > 0 && (n + 1) % a.save_every == 0) save((n + 1) / a.save_every);
+      }
+      if (a.save_every <= 0) save(0);
+    }
+    if (prof_me && lane == 0) {
+      eacc[E_TOTAL - 8] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) g_tc2_wait[8 + i] = (unsigned long long)eacc[i];
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // the peer's tensor / shared memory stay valid until both CTAs are done
+  if (warp == 1) ptx::tmem_dealloc2<512>(tmem);
+}
+
+// ---- host: weight tape in stage order -----------------------------------------------------------------
+static uint16_t f16_rne(float f) {  // IEEE binary16, round to nearest even, saturating to +-65504
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t absu = u & 0x7FFFFFFFu;
+  if (absu > 0x7F800000u) return (uint16_t)(sign | 0x7E00u);
+  if (absu >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);
+  if (absu < 0x33000001u) return (uint16_t)sign;
+  const int e = (int)(absu >> 23) - 127;
+  uint32_t mant = (absu & 0x7FFFFFu) | 0x800000u;
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);
+  uint32_t half_m = mant >> shift;
+  const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_m & 1u))) ++half_m;
+  uint32_t out;
+  if (e >= -14) out = ((uint32_t)(e + 15) << 10) + (half_m - 0x400u);
+  else out = half_m;
+  return (uint16_t)(sign | out);
+}
+static uint16_t bf16_rne(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// One CTA's half (rows [r0, r0 + hrows)) of the K-major no-swizzle block of W (Flux layout: element (k_in, n_out) at
+// w[k * nout + n]) over inputs [k0, k0 + 16 * ksteps): [k/8][row][k%8] 16-bit, zero padded; appended to `dst`.
+static void append_half(std::vector<uint16_t>& dst, bool fp16, const float* w, int nin, int nout, int r0, int hrows, int k0, int ksteps) {
+  const size_t base = dst.size();
+  dst.resize(base + (size_t)hrows * ksteps * 16, 0);
+  for (int kk = 0; kk < ksteps * 16; ++kk) {
+    const int k = k0 + kk;
+    if (k >= nin) continue;
+    for (int r = 0; r < hrows; ++r) {
+      const int n = r0 + r;
+      if (n >= nout) continue;
+      const float v = w[(size_t)k * nout + n];
+      dst[base + ((size_t)(kk / 8) * hrows + r) * 8 + (kk % 8)] = fp16 ? f16_rne(v) : bf16_rne(v);
+    }
+  }
+}
+
+static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, Plan& pl, std::vector<uint16_t>& tape,
+                      std::vector<float>& bias) {
+  const NetDesc& nd = m->nd;
+  const int L = nd.n_layers;
+  if (m->nz != kNz) { set_error("tensor-core path: nz must be 32"); return OPZ_EUNSUP; }
+  if (L != 2 && L != 3) { set_error("tensor-core path: 2 or 3 Dense layers per net"); return OPZ_EUNSUP; }
+  pl.L = L;
+  pl.act = nd.act;
+  pl.fp16 = fp16;
+  int bias_per_net = 0;
+  for (int j = 0; j < L - 1; ++j) {
+    pl.hpad[j] = (nd.sizes[j + 1] + 15) / 16 * 16;
+    if (pl.hpad[j] > kMaxHidden) { set_error("tensor-core path: hidden width above 400"); return OPZ_EUNSUP; }
+    bias_per_net += pl.hpad[j];
+  }
+  bias_per_net += 32;                     // output biases
+  bias_per_net = (bias_per_net + 3) / 4 * 4;   // nets stay 16-byte aligned: the drain reads float4s
+  pl.bias_per_net = bias_per_net;
+  bias.assign((size_t)3 * bias_per_net, 0.0f);
+  tape.clear();
+  pl.n_stages = 0;
+  std::vector<uint16_t> half[2];
+  struct Pending { bool valid; int net, c, cols; } pend{false, 0, 0, 0};
+  bool overflow = false;
+  auto out_halves = [&](const Pending& p) {   // 16 rows per CTA of W_out over the 64 (or fewer) inputs of chunk p.c
+    const float* wn = w.data() + (size_t)p.net * nd.P;
+    for (int hf = 0; hf < 2; ++hf)
+      append_half(half[hf], fp16, wn + nd.w_off[L - 1], nd.sizes[L - 1], nd.sizes[L], hf * 16, 16, p.c * kCW, p.cols / 16);
+  };
+  auto close_stage = [&]() {
+    if (pl.n_stages >= kMaxStages) { overflow = true; half[0].clear(); half[1].clear(); return; }
+    const int s = pl.n_stages++;
+    pl.st_bytes[s] = (uint32_t)(half[0].size() * 2);
+    pl.st_src[s] = (uint32_t)(tape.size() * 2);
+    tape.insert(tape.end(), half[0].begin(), half[0].end());
+    tape.insert(tape.end(), half[1].begin(), half[1].end());
+    half[0].clear();
+    half[1].clear();
+  };
+  for (int net = 0; net < 3; ++net) {
+    const float* wn = w.data() + (size_t)net * nd.P;
+    int boff = 0;
+    for (int j = 0; j < L - 1; ++j) {
+      for (int i = 0; i < nd.sizes[j + 1]; ++i) bias[(size_t)net * bias_per_net + boff + i] = wn[nd.b_off[j] + i];
+      boff += pl.hpad[j];
+    }
+    for (int i = 0; i < nd.sizes[L]; ++i) bias[(size_t)net * bias_per_net + boff + i] = wn[nd.b_off[L - 1] + i];
+    for (int j = 0; j < L - 1; ++j) {
+      const bool fused = (j == L - 2);
+      const int kin = (j == 0) ? kS : pl.hpad[j - 1];
+      const int hp = pl.hpad[j];
+      for (int c = 0; c * kCW < hp; ++c) {
+        const int rows = std::min(kCW, hp - c * kCW);
+        for (int hf = 0; hf < 2; ++hf)
+          append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kin / 16);
+        if (pend.valid) { out_halves(pend); pend.valid = false; }
+        close_stage();
+        if (fused) pend = Pending{true, net, c, rows};
+      }
+    }
+  }
+  if (pend.valid) { out_halves(pend); close_stage(); }
+  if (overflow) { set_error("tensor-core path: schedule longer than the stage table"); return OPZ_EUNSUP; }
+  pl.tape_bytes = tape.size() * 2;
+  // ---- ring placement (byte FIFO, every right-hand side starts at offset 0) and in-flight allowance ----
+  const int n = pl.n_stages;
+  uint32_t cur = 0;
+  for (int s = 0; s < n; ++s) {
+    const uint32_t sz = (pl.st_bytes[s] + 127u) / 128u * 128u;
+    if (sz > (uint32_t)kRingBytes) { set_error("tensor-core path: weight stage larger than the ring"); return OPZ_EUNSUP; }
+    if (cur + sz > (uint32_t)kRingBytes) cur = 0;
+    pl.st_off[s] = cur;
+    cur += sz;
+  }
+  for (int s = 0; s < n; ++s) {
+    // walk back over the cyclic stage sequence: the stage can be filled while the `keep` previous stages are in flight
+    int keep = 0;
+    const uint32_t lo = pl.st_off[s], hi = lo + pl.st_bytes[s];
+    while (keep < kNB - 1) {
+      const int t = ((s - 1 - keep) % n + n) % n;
+      const uint32_t tlo = pl.st_off[t], thi = tlo + pl.st_bytes[t];
+      if (tlo < hi && lo < thi) break;   // overlaps: stage t must have been consumed
+      if (keep + 1 >= n) break;          // never count the stage itself
+      ++keep;
+    }
+    pl.st_keep[s] = (uint8_t)keep;
+  }
+  return OPZ_OK;
+}
+
+}  // namespace tc2
+
+int tc2_model_prepare(opz_model* m, int precision) {
+  using namespace tc2;
+  const bool fp16 = precision == OPZ_PREC_FP16;
+  OPZ_CUDA(cudaSetDevice(m->ctx->device));
+  std::vector<float> w((size_t)3 * m->nd.P);
+  OPZ_CUDA(cudaMemcpyAsync(w.data(), m->w_dev, sizeof(float) * w.size(), cudaMemcpyDeviceToHost, m->ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  Plan* pl = static_cast<Plan*>(m->tc2_plan);
+  if (!pl) { pl = new Plan(); m->tc2_plan = pl; }
+  std::vector<uint16_t> tape;
+  std::vector<float> bias;
+  int rc = build_plan(m, w, fp16, *pl, tape, bias);
+  if (rc) return rc;
+  const size_t tape_al = (pl->tape_bytes + 255) / 256 * 256;
+  const size_t need = tape_al + bias.size() * 4 + 256;
+  if (m->tc2_pack_bytes < need) {
+    if (m->tc2_pack) { OPZ_CUDA(cudaFree(m->tc2_pack)); m->tc2_pack = nullptr; m->tc2_pack_bytes = 0; }
+    if (cudaMalloc(&m->tc2_pack, need) != cudaSuccess) { (void)cudaGetLastError(); set_error("device allocation failed"); return OPZ_ENOMEM; }
+    m->tc2_pack_bytes = need;
+  }
+  pl->tape_dev = static_cast<uint8_t*>(m->tc2_pack);
+  pl->bias_dev = reinterpret_cast<float*>(pl->tape_dev + tape_al);
+  OPZ_CUDA(cudaMemcpyAsync(pl->tape_dev, tape.data(), pl->tape_bytes, cudaMemcpyHostToDevice, m->ctx->stream));
+  OPZ_CUDA(cudaMemcpyAsync(pl->bias_dev, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, m->ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));  // the host vectors go out of scope
+  return OPZ_OK;
+}
+
+void tc2_model_release(opz_model* m) {
+  if (m->tc2_pack) cudaFree(m->tc2_pack);
+  m->tc2_pack = nullptr;
+  m->tc2_pack_bytes = 0;
+  delete static_cast<tc2::Plan*>(m->tc2_plan);
+  m->tc2_plan = nullptr;
+}
+
+int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision) {
+  using namespace tc2;
+  const bool fp16 = precision == OPZ_PREC_FP16;
+  const Plan* pl = static_cast<const Plan*>(m->tc2_plan);
+  if (!pl || pl->fp16 != fp16) { set_error("tensor-core path: model not prepared for this precision"); return OPZ_EINVAL; }
+  Args a{};
+  a.P = c.P;
+  a.tape = pl->tape_dev;
+  a.bias = pl->bias_dev;
+  a.x0 = c.x0; a.bc = c.bc; a.out = c.out; a.B = c.B; a.scheme = c.scheme; a.dt = c.dt; a.t0 = c.t0;
+  a.n_steps = c.n_steps; a.save_every = c.save_every; a.n_save = c.n_save;
+  a.L = pl->L; a.bias_per_net = pl->bias_per_net; a.n_stages = pl->n_stages;
+  a.hpad[0] = pl->hpad[0]; a.hpad[1] = pl->hpad[1];
+  a.exp = getenv("OPZ_TC_EXP") ? atoi(getenv("OPZ_TC_EXP")) : 0;
+  std::memcpy(a.st_off, pl->st_off, sizeof(a.st_off));
+  std::memcpy(a.st_bytes, pl->st_bytes, sizeof(a.st_bytes));
+  std::memcpy(a.st_src, pl->st_src, sizeof(a.st_src));
+  std::memcpy(a.st_keep, pl->st_keep, sizeof(a.st_keep));
+  const size_t smem = SmemLayout::bytes;
+  if ((int)smem > ctx->smem_optin) { set_error("tensor-core path: shared memory budget exceeded"); return OPZ_EUNSUP; }
+  const bool profile = getenv("OPZ_TC_PROFILE") != nullptr && pl->act == OPZ_ACT_RELU;
+  using KernelT = void (*)(const Args);
+  int E = 8;   // epilogue warps per CTA
+  if (const char* e = getenv("OPZ_TC_EPI_WARPS")) E = atoi(e) == 16 ? 16 : 8;
+#define OPZ_TC2_ROW(F, EW) {rollout_tc2_kernel<F, 0, EW, false>, rollout_tc2_kernel<F, 1, EW, false>, rollout_tc2_kernel<F, 2, EW, false>, \
+                            rollout_tc2_kernel<F, 3, EW, false>, rollout_tc2_kernel<F, 4, EW, false>, rollout_tc2_kernel<F, 5, EW, false>}
+  static const KernelT table[2][2][6] = {{OPZ_TC2_ROW(false, 8), OPZ_TC2_ROW(true, 8)}, {OPZ_TC2_ROW(false, 16), OPZ_TC2_ROW(true, 16)}};
+#undef OPZ_TC2_ROW
+  KernelT kern = table[E == 16 ? 1 : 0][fp16 ? 1 : 0][pl->act];
+  if (profile) {
+    if (E == 16) kern = fp16 ? rollout_tc2_kernel<true, OPZ_ACT_RELU, 16, true> : rollout_tc2_kernel<false, OPZ_ACT_RELU, 16, true>;
+    else kern = fp16 ? rollout_tc2_kernel<true, OPZ_ACT_RELU, 8, true> : rollout_tc2_kernel<false, OPZ_ACT_RELU, 8, true>;
+  }
+  OPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (c.B + kM - 1) / kM;
+  const int64_t n_items = (n_tiles + 1) / 2;
+  int64_t grid = std::min<int64_t>(n_items, ctx->sm_count / 2) * 2;
+  if (grid < 2) grid = 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((2 + E) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OPZ_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  OPZ_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  if (profile) {
+    OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long w[16];
+    OPZ_CUDA(cudaMemcpyFromSymbol(w, g_tc2_wait, sizeof(w)));
+    const int64_t my_items = (n_items + grid / 2 - 1) / (grid / 2);
+    const int stages = c.scheme == OPZ_RK4 ? 4 : (c.scheme == OPZ_RK2 ? 2 : 1);
+    const double per = 1.0 / ((double)my_items * c.n_steps * stages);
+    fprintf(stderr, "opz tc2 profile (CTA 0, cycles per tile right-hand side): MMA warp total %.0f | wait X %.0f, D-empty %.0f, H1 %.0f, "
+            "weights %.0f, H2-full %.0f || epilogue warp total %.0f | wait D-full %.0f, H2-empty %.0f, Y-full %.0f, physics A %.0f, physics B + publish %.0f, drain ld %.0f, drain st+arrive %.0f\n",
+            w[W_TOTAL] * per, w[W_X] * per, w[W_DEMPTY] * per, w[W_H1] * per, w[W_FULL] * per, w[W_H2FULL] * per,
+            w[E_TOTAL] * per, w[E_DFULL] * per, w[E_H2EMPTY] * per, w[E_YFULL] * per, w[E_PHYS_A] * per, w[E_PHYS_B] * per, w[E_LD] * per, w[E_ST] * per);
+  }
+  return OPZ_OK;
+}
+
+}  // namespace opz

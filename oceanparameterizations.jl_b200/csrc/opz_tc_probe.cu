@@ -239,3 +239,162 @@ extern "C" int opz_debug_umma_rate(int N, int per_commit, int reps, int mode, in
   cycles_per_mma[1] = (double)h[grid] / ((double)per_commit * reps);  // issue loop only (CTA 0)
   return OPZ_OK;
 }
+
+// ---- static issue probe: 25 tcgen05.mma (M=128, TS) per batch with immediate operand offsets, as the rollout kernel
+// issues them; reports cycles per MMA for the whole run (issue + drain) and for the issue sequence alone.
+namespace opz {
+__device__ __forceinline__ void probe_mma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+template <int N>
+__global__ void __launch_bounds__(64, 1) umma_static_kernel(int reps, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x / 32;
+  if (warp == 0) {
+    if (threadIdx.x == 0) { ptx::mbar_init(bars, 1); ptx::fence_barrier_init(); }
+    __syncwarp();
+    ptx::tmem_alloc<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = ptx::idesc_f16kind(128, N, true);
+    const uint64_t bd0 = ptx::smem_desc(ptx::smem_u32(smem), (uint32_t)N * 16u, 128);
+    const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+    if (ptx::elect_one()) {
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 25; ++k) probe_mma_ts_lohi(tmem, tmem + 256u + (uint32_t)k * 8u, lo + (uint32_t)(k * N), hi, idesc, k > 0);
+      }
+      const long long t1 = clock64();
+      ptx::tc_commit(bars);
+      ptx::mbar_wait(bars, 0);
+      const long long t2 = clock64();
+      out[0] = t2 - t0;
+      out[1] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem);
+}
+}  // namespace opz
+
+extern "C" int opz_debug_umma_static(int N, int reps, double* cycles_per_mma) {
+  long long* d;
+  OPZ_CUDA(cudaMalloc(&d, sizeof(long long) * 2));
+  const size_t smem = 96 * 1024 + 64;
+  void (*k)(int, long long*) = N == 8 ? opz::umma_static_kernel<8> : N == 16 ? opz::umma_static_kernel<16> : N == 32 ? opz::umma_static_kernel<32>
+                               : N == 64 ? opz::umma_static_kernel<64> : N == 128 ? opz::umma_static_kernel<128> : opz::umma_static_kernel<256>;
+  OPZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<1, 64, smem>>>(reps, d);
+  OPZ_CUDA(cudaGetLastError());
+  OPZ_CUDA(cudaDeviceSynchronize());
+  long long h[2];
+  OPZ_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  cycles_per_mma[0] = (double)h[0] / (25.0 * reps);
+  cycles_per_mma[1] = (double)h[1] / (25.0 * reps);
+  return OPZ_OK;
+}
+
+// ---- tensor-memory read throughput: W warps each read 64 columns x 32 lanes (tcgen05.ld 32x32b.x16 x 4 + wait) `iters` times;
+// with_mma = 1 keeps one thread issuing N = 64 TS MMAs into other columns meanwhile.
+namespace opz {
+__global__ void __launch_bounds__(576, 1) tmem_read_kernel(int n_warps, int iters, int with_mma, int x32, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x / 32;
+  if (warp == 0) {
+    if (threadIdx.x == 0) { ptx::mbar_init(bars, 1); ptx::fence_barrier_init(); tmem_slot[1] = 0u; }
+    __syncwarp();
+    ptx::tmem_alloc<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    volatile uint32_t* stop = reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
+    if (with_mma) {
+      const uint32_t idesc = ptx::idesc_f16kind(128, 64, true);
+      const uint64_t bd0 = ptx::smem_desc(ptx::smem_u32(smem), 64u * 16u, 128);
+      const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+      if (ptx::elect_one()) {
+        long long n = 0;
+        const long long t0 = clock64();
+        while (*stop < (uint32_t)n_warps) {
+#pragma unroll
+          for (int k = 0; k < 25; ++k) probe_mma_ts_lohi(tmem, tmem + 256u + (uint32_t)k * 8u, lo + (uint32_t)(k * 64), hi, idesc, k > 0);
+          n += 25;
+        }
+        const long long t1 = clock64();
+        ptx::tc_commit(bars);
+        ptx::mbar_wait(bars, 0);
+        out[2] = t1 - t0;
+        out[3] = n;
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 2 && warp < 2 + n_warps) {
+    const uint32_t lane_addr = (uint32_t)((warp % 4) * 32) << 16;
+    uint32_t sink = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (x32) {
+        uint32_t r[2][32];
+        ptx::tmem_ld32(tmem + lane_addr + 128, r[0]);
+        ptx::tmem_ld32(tmem + lane_addr + 160, r[1]);
+        ptx::tmem_wait_ld();
+        sink ^= r[0][5] ^ r[1][7];
+      } else {
+        uint32_t r[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(tmem + lane_addr + 128 + g * 16, r[g]);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sink ^= r[g][3];
+      }
+    }
+    const long long t1 = clock64();
+    if (sink == 0x12345u) out[7] = 0;
+    if (threadIdx.x % 32 == 0) {
+      if (warp == 2) { out[0] = t1 - t0; out[1] = iters; }
+      atomicAdd(reinterpret_cast<unsigned int*>(tmem_slot + 1), 1u);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem);
+}
+}  // namespace opz
+
+extern "C" int opz_debug_tmem_read(int n_warps, int iters, int with_mma, int x32, double* res) {
+  long long* d;
+  OPZ_CUDA(cudaMalloc(&d, sizeof(long long) * 8));
+  OPZ_CUDA(cudaMemset(d, 0, sizeof(long long) * 8));
+  const size_t smem = 96 * 1024 + 64;
+  OPZ_CUDA(cudaFuncSetAttribute(opz::tmem_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  opz::tmem_read_kernel<<<1, 576, smem>>>(n_warps, iters, with_mma, x32, d);
+  OPZ_CUDA(cudaGetLastError());
+  OPZ_CUDA(cudaDeviceSynchronize());
+  long long h[8];
+  OPZ_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  res[0] = (double)h[0] / (double)h[1];                 // cycles per 64-column read of one warp
+  res[1] = h[3] ? (double)h[2] / (double)h[3] : 0.0;    // cycles per MMA meanwhile
+  return OPZ_OK;
+}
