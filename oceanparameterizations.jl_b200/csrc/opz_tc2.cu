@@ -36,15 +36,15 @@ namespace tc2 {
 constexpr int kNz = 32;
 constexpr int kS = 3 * kNz;          // 96 state entries per column
 constexpr int kM = 128;              // columns per tile (one tile per CTA, two per pair)
-constexpr int kLd = kM + 1;          // padded leading dimension of s_xn (conflict-free transposing copies)
 constexpr int kCW = 64;              // accumulator chunk width (TMEM columns)
 constexpr int kMaxHidden = 400;      // HF region: 200 TMEM columns
 constexpr int kNB = 8;               // stage barrier pairs (stages in flight <= kNB - 1)
 constexpr int kMaxStages = 48;       // stages per right-hand side
-constexpr int kRingBytes = 82944;    // 3 x (32 rows x 400 k + 16 rows x 64 k) x 2 B
+constexpr int kRingBytes = 84480;    // 3 x (32 rows x (400 + 8) k + 16 rows x 64 k) x 2 B
 constexpr int kMaxKs = 28;           // 7 HF chunks x 4 k-steps
 
-constexpr uint32_t kColD0 = 0, kColY = 128, kColX = 224, kColH2 = 272, kColHF = 304;
+constexpr uint32_t kColD0 = 0, kColY = 128, kColX = 224, kColH2 = 272, kColHF = 304, kColOne = 504;
+// kColOne: one k-step (8 columns) holding [1, 0, ..., 0] per lane: the A operand of the bias MMAs
 
 enum : int {
   B_FULL = 0,                   // [kNB] stage bytes landed               (producer expect_tx + peer forward)
@@ -65,7 +65,6 @@ struct Plan {                     // host-side, cached on the model
   int hpad[2] = {0, 0};
   int act = 0;
   bool fp16 = false;
-  int bias_per_net = 0;           // floats: padded hidden biases, then 32 output biases
   int n_stages = 0;
   uint32_t st_off[kMaxStages];    // ring offset of the stage (bytes)
   uint32_t st_bytes[kMaxStages];  // bytes PER CTA
@@ -73,13 +72,12 @@ struct Plan {                     // host-side, cached on the model
   uint8_t st_keep[kMaxStages];    // earlier stages that may still be in flight when this one is filled
   size_t tape_bytes = 0;
   uint8_t* tape_dev = nullptr;
-  float* bias_dev = nullptr;      // [3][bias_per_net]
+  float b3[96];                   // output-layer biases [net][32]
 };
 
 struct Args {
   DevParams P;
   const uint8_t* tape;
-  const float* bias;
   const float* x0;
   const float* bc;
   float* out;
@@ -87,9 +85,9 @@ struct Args {
   int scheme;
   float dt, t0;
   int n_steps, save_every, n_save;
-  int L, bias_per_net, n_stages;
+  int L, n_stages;
   int hpad[2];
-  int exp;
+  float b3[96];   // output-layer biases [net][32] (the hidden-layer biases ride in the weight tape)
   uint32_t st_off[kMaxStages];
   uint32_t st_bytes[kMaxStages];
   uint32_t st_src[kMaxStages];
@@ -98,14 +96,17 @@ struct Args {
 
 struct SmemLayout {
   static constexpr size_t off_xn = 0;
-  static constexpr size_t off_acc = off_xn + (size_t)kS * kLd * 4;
+  static constexpr size_t off_acc = off_xn + (size_t)kS * kM * 4;
   static constexpr size_t off_xs = off_acc + (size_t)kS * kM * 4;
   static constexpr size_t off_ring = (off_xs + (size_t)kS * kM * 4 + 127) / 128 * 128;
   static constexpr size_t off_bars = off_ring + (size_t)kRingBytes;
   static constexpr size_t off_tmem = off_bars + 8 * B_COUNT;
-  static constexpr size_t off_b3 = off_tmem + 16;            // [3][32] output-layer biases
-  static constexpr size_t bytes = off_b3 + sizeof(float) * 96;
+  static constexpr size_t bytes = off_tmem + 16;
 };
+
+// s_xn is stored with a rotation so that both the per-column accesses (threads = consecutive columns) and the
+// transposing snapshot copies (threads = consecutive state entries) are bank-conflict free without padding
+__device__ __forceinline__ int xn_idx(int i, int m) { return i * kM + ((m + i) & (kM - 1)); }
 
 __device__ __forceinline__ void bar_wait(uint64_t* bars, int id, uint32_t& mask) {
   ptx::mbar_wait(bars + id, (mask >> id) & 1u);
@@ -135,13 +136,19 @@ __device__ __forceinline__ uint32_t pack_act(float a, float b) {
   return FP16 ? ptx::pack_f16x2(a, b) : ptx::pack_bf16x2(a, b);
 }
 
-// ROWS x (16 KIN) weight block against KIN k-steps of the A operand: one straight run of tcgen05.mma whose
-// descriptor / address offsets are immediates (issued by the elected lane)
-template <int ROWS, int KIN>
-__device__ __forceinline__ void issue_static(uint32_t d, uint32_t a0, uint64_t bd0, uint32_t idesc) {
-  const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+// k-steps [K0, K1) of a ROWS-row weight block against the A operand: one straight run of tcgen05.mma whose
+// descriptor / address offsets are immediates (issued by the elected lane); the first k-step of a chunk overwrites D
+template <int ROWS, int K0, int K1>
+__device__ __forceinline__ void issue_range(uint32_t d, uint32_t a0, uint32_t lo, uint32_t hi, uint32_t idesc) {
 #pragma unroll
-  for (int k = 0; k < KIN; ++k) ptx::mma_ts2_lohi(d, a0 + (uint32_t)k * 8u, lo + (uint32_t)(k * ROWS), hi, idesc, k > 0);
+  for (int k = K0; k < K1; ++k) ptx::mma_ts2_lohi(d, a0 + (uint32_t)k * 8u, lo + (uint32_t)(k * ROWS), hi, idesc, k > 0);
+}
+// HF chunks [3g', ...) of a 25-k-step layer in three groups: k-steps [0,12), [12,20), [20,25)
+template <int ROWS>
+__device__ __forceinline__ void issue_hf_group(int grp, uint32_t d, uint32_t a0, uint32_t lo, uint32_t hi, uint32_t idesc) {
+  if (grp == 0) issue_range<ROWS, 0, 12>(d, a0, lo, hi, idesc);
+  else if (grp == 1) issue_range<ROWS, 12, 20>(d, a0, lo, hi, idesc);
+  else issue_range<ROWS, 20, 25>(d, a0, lo, hi, idesc);
 }
 
 // E epilogue warps per CTA: E / 4 threads share one ocean column (TMEM lane); each owns LV = 128 / E cells.
@@ -160,7 +167,6 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
   uint8_t* s_ring = smem + SmemLayout::off_ring;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::off_bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_tmem);
-  float* s_b3 = reinterpret_cast<float*>(smem + SmemLayout::off_b3);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t n_tiles = (a.B + kM - 1) / kM;
@@ -174,9 +180,6 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
     if (rank != 0) ptx::mbar_arrive_remote_relaxed(leader_bars + 8u * (uint32_t)id);
     else ptx::mbar_arrive_relaxed(bars + id);
   };
-  int boff_out = 0;
-  for (int j = 0; j < a.L - 1; ++j) boff_out += a.hpad[j];
-  for (int i = threadIdx.x; i < 96; i += kThreads) s_b3[i] = a.bias[(i / 32) * a.bias_per_net + boff_out + (i % 32)];
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kNB; ++s) { ptx::mbar_init(bars + B_FULL + s, rank == 0 ? 2 : 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
@@ -297,16 +300,48 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 const uint32_t d = tmem + kColD0 + buf * kCW;
                 const bool wait_h1 = (j > 0) && (c0 == 0);   // HF chunk h covers k-steps [4h, 4h + 4)
                 const bool more = have_pend;                 // output-layer MMAs follow in this stage
-                if (!wait_h1 && rows == (uint32_t)kCW && (kin == 25 || kin == 6)) {
-                  // hot path: full-width chunk whose A operand is already complete
+                const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
+                const uint32_t a0 = tmem + a_base;
+                const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25 || kin == 6);
+                // bias MMA: D += [1, 0, ..] x [b; don't care]: the block of rows / 2 x 8 halves right behind the weights; its
+                // second k-group reads whatever follows in the ring (finite 16-bit weights), multiplied by the zeros of A
+                const uint32_t bias_lo = blo + (rows / 2) * (uint32_t)kin * 2u;   // descriptor address units of 16 B
+                const uint32_t a_one = tmem + kColOne;
+                if (static_shape && !wait_h1) {
+                  // hot path: the A operand is already complete; one straight immediate-offset run
                   ptx::tc_fence_after();
                   if (ptx::elect_one()) {
-                    if (kin == 25) issue_static<kCW, 25>(d, tmem + a_base, bd0, idesc);
-                    else issue_static<kCW, 6>(d, tmem + a_base, bd0, idesc);
+                    if (rows == (uint32_t)kCW) {
+                      if (kin == 25) issue_range<kCW, 0, 25>(d, a0, blo, bhi, idesc);
+                      else issue_range<kCW, 0, 6>(d, a0, blo, bhi, idesc);
+                    } else {
+                      if (kin == 25) issue_range<16, 0, 25>(d, a0, blo, bhi, idesc);
+                      else issue_range<16, 0, 6>(d, a0, blo, bhi, idesc);
+                    }
+                    ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
                     ptx::tc_commit2(bars + B_DFULL + buf);
                     if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
                   }
                   __syncwarp();
+                } else if (static_shape && kin == 25) {
+                  // first chunk of a 400-wide layer fed by HF: follow the epilogue in three groups of HF chunks
+                  // (k-steps [0,12) need HF chunks 0..2, [12,20) chunks 3..4, [20,25) chunks 5..6)
+#pragma unroll 1
+                  for (int grp = 0; grp < 3; ++grp) {
+                    const int h0 = grp == 0 ? 0 : (grp == 1 ? 3 : 5), h1 = grp == 0 ? 3 : (grp == 1 ? 5 : 7);
+                    for (int h = h0; h < h1; ++h) bar_wait_t<PROF>(bars, B_H1 + h, mask, wacc, W_H1);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                      if (rows == (uint32_t)kCW) issue_hf_group<kCW>(grp, d, a0, blo, bhi, idesc);
+                      else issue_hf_group<16>(grp, d, a0, blo, bhi, idesc);
+                      if (grp == 2) {
+                        ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
+                        ptx::tc_commit2(bars + B_DFULL + buf);
+                        if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                      }
+                    }
+                    __syncwarp();
+                  }
                 } else {
 #pragma unroll
                   for (int h = 0; h < kMaxKs / 4; ++h) {
@@ -324,6 +359,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                     }
                   }
                   if (ptx::elect_one()) {
+                    ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
                     ptx::tc_commit2(bars + B_DFULL + buf);
                     if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
                   }
@@ -331,7 +367,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 }
                 // the output-layer MMAs of the PREVIOUS fused chunk ride in this stage, after this chunk's MMAs, so
                 // that the tensor pipe has work while the epilogue converts that chunk
-                if (more) out_op(a.st_off[s] + (rows / 2) * (uint32_t)kin * 32u, B_EMPTY + (int)(gs % kNB), -1);
+                if (more) out_op(a.st_off[s] + (rows / 2) * ((uint32_t)kin * 32u + 16u), B_EMPTY + (int)(gs % kNB), -1);
                 if (fused) { have_pend = true; pend_net = (uint32_t)net; pend_c = (uint32_t)(c0 / kCW); pend_ks = rows >> 4; }
               }
             }
@@ -363,11 +399,15 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
     const float h = a.dt;
     const DevParams& P = a.P;
     const bool prof_me = PROF && blockIdx.x == 0 && warp == 2;
-    const bool getenv_nobias = a.exp & 1;  // EXPERIMENT
     long long eacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = PROF ? clock64() : 0;
     auto epi_bar_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
+    if (ps == 0) {  // the "ones" k-step of this thread's TMEM lane: [1, 0, ..., 0] as 16-bit pairs (ordered before the MMAs by X-full)
+      const uint32_t one[8] = {FP16 ? 0x00003C00u : 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      ptx::tmem_st8(tmem + lane_addr + kColOne, one);
+      ptx::tmem_wait_st();
+    }
     for (int64_t item = item0; item < n_items; item += item_stride) {
       const int64_t tile = item * 2 + rank;   // may be one past the last tile for the peer: a padding tile, never stored
       const int64_t col0 = tile * kM;
@@ -377,7 +417,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
       for (int ee = etid; ee < kM * kS; ee += kEpiThreads) {
         const int mm = ee / kS, i = ee - mm * kS;
         const int64_t c = col0 + mm;
-        s_xn[i * kLd + mm] = c < a.B ? a.x0[c * kS + i] : 0.0f;
+        s_xn[xn_idx(i, mm)] = c < a.B ? a.x0[c * kS + i] : 0.0f;
       }
       float bc[OPZ_BC_STRIDE];
 #pragma unroll
@@ -388,7 +428,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
         for (int ee = etid; ee < kM * kS; ee += kEpiThreads) {
           const int mm = ee / kS, i = ee - mm * kS;
           const int64_t c = col0 + mm;
-          if (c < a.B) a.out[(c * a.n_save + slot_idx) * kS + i] = s_xn[i * kLd + mm];
+          if (c < a.B) a.out[(c * a.n_save + slot_idx) * kS + i] = s_xn[xn_idx(i, mm)];
         }
       };
       if (a.save_every > 0) save(0);
@@ -415,7 +455,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll
           for (int i = 0; i < LV; ++i) {
             const int idx = v * kNz + c0 + i;
-            xv[v][i] = s_xn[idx * kLd + m];
+            xv[v][i] = s_xn[xn_idx(idx, m)];
             s_xs[idx * kM + m] = xv[v][i];
           }
         if (n_rhs > 0) publish_x(xv);
@@ -430,8 +470,6 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
           // ---- drain the accumulator chunks of the hidden layers ----
 #pragma unroll 1
           for (int net = 0; net < 3; ++net) {
-            const float* bnet = a.bias + net * a.bias_per_net;
-            int boff = 0;
 #pragma unroll 1
             for (int j = 0; j < a.L - 1; ++j) {
               const bool fused = (j == a.L - 2);
@@ -441,13 +479,6 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 const uint32_t buf = g & 1u;
                 ++g;
                 const int ncols = min(kCW, hp - c * kCW) - ps * CPW;   // columns of this chunk that belong to this warp (<= 0: none)
-                // biases of this warp's columns: through L1, requested before the barrier wait
-                float4 b4[CPW / 4];
-                {
-                  const float4* bb = reinterpret_cast<const float4*>(bnet + boff + c * kCW + ps * CPW);
-#pragma unroll
-                  for (int i = 0; i < CPW / 4; ++i) b4[i] = (getenv_nobias) ? make_float4(0.f, 0.f, 0.f, 0.f) : ((i * 4 < ncols) ? __ldg(bb + i) : make_float4(0.f, 0.f, 0.f, 0.f));
-                }
                 if (prof_me) bar_wait_t<PROF>(bars, B_DFULL + buf, mask, eacc, E_DFULL - 8);
                 else bar_wait(bars, B_DFULL + buf, mask);
                 ptx::tc_fence_after();
@@ -465,11 +496,8 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 for (int grp = 0; grp < CPW / 16; ++grp) {
                   if (grp * 16 < ncols) {
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                      const float4 b = b4[grp * 4 + jj];
-                      pk[grp][2 * jj] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][4 * jj]) + b.x, __uint_as_float(rr[grp][4 * jj + 1]) + b.y);
-                      pk[grp][2 * jj + 1] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][4 * jj + 2]) + b.z, __uint_as_float(rr[grp][4 * jj + 3]) + b.w);
-                    }
+                    for (int jj = 0; jj < 8; ++jj)   // the bias is already in the accumulator (bias MMA)
+                      pk[grp][jj] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][2 * jj]), __uint_as_float(rr[grp][2 * jj + 1]));
                   }
                 }
                 if (fused) {  // the output-layer MMAs of the previous chunk must have consumed H2c
@@ -490,7 +518,6 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 }
                 if (prof_me) eacc[E_ST - 8] += clock64() - t_st;
               }
-              boff += hp;
             }
           }
           // ---- physics, part A: everything that does not need the NN outputs (runs while the last output-layer
@@ -562,7 +589,6 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
               if constexpr (LV == 16) ptx::tmem_ld16(ybase + (uint32_t)c0, yhi);
               else ptx::tmem_ld8(ybase + (uint32_t)c0, yhi);
               ptx::tmem_wait_ld();
-              const float* b3 = s_b3 + v * 32;
               const float* D = v == 0 ? Du : (v == 1 ? Dv : DT);
 #pragma unroll
               for (int i = 0; i <= LV; ++i) {
@@ -570,7 +596,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 if (f == 0) F[i] = Fb[v];
                 else if (f == kNz) F[i] = Ft[v];
                 else {
-                  const float y = (i == 0 ? __uint_as_float(ylo[7]) : __uint_as_float(yhi[i == 0 ? 0 : i - 1])) + b3[f - 1];
+                  const float y = (i == 0 ? __uint_as_float(ylo[7]) : __uint_as_float(yhi[i == 0 ? 0 : i - 1])) + a.b3[v * 32 + f - 1];
                   F[i] = y - D[i];
                 }
               }
@@ -582,7 +608,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
               if (v == 0) k += cu[i];
               else if (v == 1) k -= cv[i];
               const int idx = v * kNz + c0 + i;
-              const int o = idx * kM + m, on = idx * kLd + m;
+              const int o = idx * kM + m, on = xn_idx(idx, m);
               const float xo = s_xn[on];
               const float acc_in = first ? 0.0f : s_acc[o];
               const float sum = acc_in + wk * k;       // first stage: 0 + 1*k == k exactly
@@ -655,8 +681,7 @@ static void append_half(std::vector<uint16_t>& dst, bool fp16, const float* w, i
   }
 }
 
-static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, Plan& pl, std::vector<uint16_t>& tape,
-                      std::vector<float>& bias) {
+static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, Plan& pl, std::vector<uint16_t>& tape) {
   const NetDesc& nd = m->nd;
   const int L = nd.n_layers;
   if (m->nz != kNz) { set_error("tensor-core path: nz must be 32"); return OPZ_EUNSUP; }
@@ -664,16 +689,11 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   pl.L = L;
   pl.act = nd.act;
   pl.fp16 = fp16;
-  int bias_per_net = 0;
   for (int j = 0; j < L - 1; ++j) {
     pl.hpad[j] = (nd.sizes[j + 1] + 15) / 16 * 16;
     if (pl.hpad[j] > kMaxHidden) { set_error("tensor-core path: hidden width above 400"); return OPZ_EUNSUP; }
-    bias_per_net += pl.hpad[j];
   }
-  bias_per_net += 32;                     // output biases
-  bias_per_net = (bias_per_net + 3) / 4 * 4;   // nets stay 16-byte aligned: the drain reads float4s
-  pl.bias_per_net = bias_per_net;
-  bias.assign((size_t)3 * bias_per_net, 0.0f);
+  for (int i = 0; i < 96; ++i) pl.b3[i] = 0.0f;
   tape.clear();
   pl.n_stages = 0;
   std::vector<uint16_t> half[2];
@@ -696,12 +716,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   };
   for (int net = 0; net < 3; ++net) {
     const float* wn = w.data() + (size_t)net * nd.P;
-    int boff = 0;
-    for (int j = 0; j < L - 1; ++j) {
-      for (int i = 0; i < nd.sizes[j + 1]; ++i) bias[(size_t)net * bias_per_net + boff + i] = wn[nd.b_off[j] + i];
-      boff += pl.hpad[j];
-    }
-    for (int i = 0; i < nd.sizes[L]; ++i) bias[(size_t)net * bias_per_net + boff + i] = wn[nd.b_off[L - 1] + i];
+    for (int i = 0; i < nd.sizes[L]; ++i) pl.b3[net * 32 + i] = wn[nd.b_off[L - 1] + i];
     for (int j = 0; j < L - 1; ++j) {
       const bool fused = (j == L - 2);
       const int kin = (j == 0) ? kS : pl.hpad[j - 1];
@@ -710,7 +725,15 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
         const int rows = std::min(kCW, hp - c * kCW);
         for (int hf = 0; hf < 2; ++hf)
           append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kin / 16);
+        for (int hf = 0; hf < 2; ++hf)   // bias block: one k-group, row r = [b_r, 0, 0, 0, 0, 0, 0, 0]
+          for (int r = 0; r < rows / 2; ++r) {
+            const int n = c * kCW + hf * (rows / 2) + r;
+            const float bv = n < nd.sizes[j + 1] ? wn[nd.b_off[j] + n] : 0.0f;
+            half[hf].push_back(fp16 ? f16_rne(bv) : bf16_rne(bv));
+            for (int z = 0; z < 7; ++z) half[hf].push_back(0);
+          }
         if (pend.valid) { out_halves(pend); pend.valid = false; }
+        else for (int hf = 0; hf < 2; ++hf) half[hf].resize(half[hf].size() + (size_t)(rows / 2) * 8, 0);  // the bias MMA's second k-group stays inside the stage
         close_stage();
         if (fused) pend = Pending{true, net, c, rows};
       }
@@ -757,20 +780,17 @@ int tc2_model_prepare(opz_model* m, int precision) {
   Plan* pl = static_cast<Plan*>(m->tc2_plan);
   if (!pl) { pl = new Plan(); m->tc2_plan = pl; }
   std::vector<uint16_t> tape;
-  std::vector<float> bias;
-  int rc = build_plan(m, w, fp16, *pl, tape, bias);
+  int rc = build_plan(m, w, fp16, *pl, tape);
   if (rc) return rc;
   const size_t tape_al = (pl->tape_bytes + 255) / 256 * 256;
-  const size_t need = tape_al + bias.size() * 4 + 256;
+  const size_t need = tape_al + 256;
   if (m->tc2_pack_bytes < need) {
     if (m->tc2_pack) { OPZ_CUDA(cudaFree(m->tc2_pack)); m->tc2_pack = nullptr; m->tc2_pack_bytes = 0; }
     if (cudaMalloc(&m->tc2_pack, need) != cudaSuccess) { (void)cudaGetLastError(); set_error("device allocation failed"); return OPZ_ENOMEM; }
     m->tc2_pack_bytes = need;
   }
   pl->tape_dev = static_cast<uint8_t*>(m->tc2_pack);
-  pl->bias_dev = reinterpret_cast<float*>(pl->tape_dev + tape_al);
   OPZ_CUDA(cudaMemcpyAsync(pl->tape_dev, tape.data(), pl->tape_bytes, cudaMemcpyHostToDevice, m->ctx->stream));
-  OPZ_CUDA(cudaMemcpyAsync(pl->bias_dev, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, m->ctx->stream));
   OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));  // the host vectors go out of scope
   return OPZ_OK;
 }
@@ -791,12 +811,11 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   Args a{};
   a.P = c.P;
   a.tape = pl->tape_dev;
-  a.bias = pl->bias_dev;
   a.x0 = c.x0; a.bc = c.bc; a.out = c.out; a.B = c.B; a.scheme = c.scheme; a.dt = c.dt; a.t0 = c.t0;
   a.n_steps = c.n_steps; a.save_every = c.save_every; a.n_save = c.n_save;
-  a.L = pl->L; a.bias_per_net = pl->bias_per_net; a.n_stages = pl->n_stages;
+  a.L = pl->L; a.n_stages = pl->n_stages;
   a.hpad[0] = pl->hpad[0]; a.hpad[1] = pl->hpad[1];
-  a.exp = getenv("OPZ_TC_EXP") ? atoi(getenv("OPZ_TC_EXP")) : 0;
+  std::memcpy(a.b3, pl->b3, sizeof(a.b3));
   std::memcpy(a.st_off, pl->st_off, sizeof(a.st_off));
   std::memcpy(a.st_bytes, pl->st_bytes, sizeof(a.st_bytes));
   std::memcpy(a.st_src, pl->st_src, sizeof(a.st_src));

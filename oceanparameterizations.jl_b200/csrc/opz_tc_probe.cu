@@ -398,3 +398,75 @@ extern "C" int opz_debug_tmem_read(int n_warps, int iters, int with_mma, int x32
   res[1] = h[3] ? (double)h[2] / (double)h[3] : 0.0;    // cycles per MMA meanwhile
   return OPZ_OK;
 }
+
+// ---- the same for a CTA pair: cta_group::2, M = 256, each CTA holds N / 2 rows of B ----
+namespace opz {
+template <int N>
+__global__ void __launch_bounds__(64, 1) umma_static2_kernel(int reps, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x / 32;
+  const uint32_t rank = ptx::cluster_ctarank();
+  if (warp == 0) {
+    if (threadIdx.x == 0) { ptx::mbar_init(bars, 1); ptx::fence_barrier_init(); }
+    __syncwarp();
+    ptx::tmem_alloc2<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = ptx::idesc_f16kind(256, N, true);
+    const uint64_t bd0 = ptx::smem_desc(ptx::smem_u32(smem), (uint32_t)(N / 2) * 16u, 128);
+    const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
+    if (ptx::elect_one()) {
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 25; ++k) ptx::mma_ts2_lohi(tmem, tmem + 256u + (uint32_t)k * 8u, lo + (uint32_t)(k * N), hi, idesc, k > 0);
+      }
+      const long long t1 = clock64();
+      ptx::tc_commit2(bars);
+      ptx::mbar_wait(bars, 0);
+      const long long t2 = clock64();
+      out[0] = t2 - t0;
+      out[1] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 0) ptx::tmem_dealloc2<512>(tmem);
+}
+}  // namespace opz
+
+extern "C" int opz_debug_umma_static2(int N, int reps, double* cycles_per_mma) {
+  long long* d;
+  OPZ_CUDA(cudaMalloc(&d, sizeof(long long) * 2));
+  const size_t smem = 96 * 1024 + 64;
+  void (*k)(int, long long*) = N == 16 ? opz::umma_static2_kernel<16> : N == 32 ? opz::umma_static2_kernel<32>
+                               : N == 64 ? opz::umma_static2_kernel<64> : N == 128 ? opz::umma_static2_kernel<128> : opz::umma_static2_kernel<256>;
+  OPZ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(64);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OPZ_CUDA(cudaLaunchKernelEx(&cfg, k, reps, d));
+  OPZ_CUDA(cudaGetLastError());
+  OPZ_CUDA(cudaDeviceSynchronize());
+  long long h[2];
+  OPZ_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  cycles_per_mma[0] = (double)h[0] / (25.0 * reps);
+  cycles_per_mma[1] = (double)h[1] / (25.0 * reps);
+  return OPZ_OK;
+}

@@ -261,9 +261,12 @@ class Model:
         return cls(sizes, act, flat[:P].copy(), flat[P:2 * P].copy(), flat[2 * P:3 * P].copy())
 
 
-def make_model(sizes, act, seed=0, out_scale=1.0, dtype=np.float32) -> Model:
+def make_model(sizes, act, seed=0, out_scale=1.0, dtype=np.float32, bias_scale=0.0) -> Model:
     """Seeded Glorot-uniform nets; `out_scale` multiplies the LAST layer's W (b=0), the knob
-    used to keep the synthetic random-weight NDE well conditioned."""
+    used to keep the synthetic random-weight NDE well conditioned.  `bias_scale` > 0
+    replaces Flux's zero biases by U(+-bias_scale) (hidden layers) and U(+-bias_scale*out_scale) (output
+    layer), as a trained model would have them; drawn AFTER the weights so that bias_scale=0 models
+    are unchanged."""
     rng = np.random.Generator(np.random.PCG64(seed))
     nets = []
     for _ in range(3):
@@ -273,6 +276,16 @@ def make_model(sizes, act, seed=0, out_scale=1.0, dtype=np.float32) -> Model:
             off = n_params(sizes) - nout - nin * nout
             flat[off:off + nin * nout] *= dtype(out_scale)
         nets.append(flat)
+    if bias_scale > 0.0:
+        brng = np.random.Generator(np.random.PCG64(seed + 7919))
+        for flat in nets:
+            off = 0
+            for i in range(len(sizes) - 1):
+                nin, nout = sizes[i], sizes[i + 1]
+                off += nin * nout
+                sc = bias_scale * (out_scale if i == len(sizes) - 2 else 1.0)
+                flat[off:off + nout] = brng.uniform(-sc, sc, size=nout).astype(dtype)
+                off += nout
     return Model(tuple(sizes), act, *nets)
 
 

@@ -118,6 +118,36 @@ def test_tc_ensemble_shard_invariance_and_multi_tile(opz, oracle, ctx):
     model.close()
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("sizes,act,B", [((96, 400, 400, 31), 1, 300), ((96, 50, 20, 31), 3, 77), ((96, 400, 31), 4, 130)])
+def test_tc_nonzero_biases(opz, oracle, ctx, sizes, act, B, prec):
+    """Flux initialises biases to zero, trained models do not keep them there: every Dense bias non-zero (the tensor-core
+    path folds the hidden biases into the weight tape as an extra k-step against a constant-one operand)."""
+    PREC = opz.PREC_FP16 if prec == "fp16" else opz.PREC_BF16
+    quant = oracle.quant_fp16 if prec == "fp16" else oracle.quant_bf16
+    p = oracle.Params()
+    x0, bc = oracle.synthetic_columns(B, p)
+    m = oracle.make_model(sizes, act, seed=11, out_scale=0.1, bias_scale=0.3)
+    assert all(np.abs(w).max() > 0 for w in (m.w_uw, m.w_vw, m.w_wT))
+    m0 = oracle.make_model(sizes, act, seed=11, out_scale=0.1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 24, 8, precision=PREC)
+    ref = oracle.rollout(x0, bc, m, p, oracle.SCHEME_RK4, dt, 24, 8)
+    ref0 = oracle.rollout(x0, bc, m0, p, oracle.SCHEME_RK4, dt, 24, 8)
+    refq = oracle.rollout(x0, bc, m, p, oracle.SCHEME_RK4, dt, 24, 8, quant=quant)
+    err = oracle.profile_error(out, ref, 32)
+    errq = oracle.profile_error(out, refq, 32)
+    bias_effect = oracle.profile_error(ref0, ref, 32)
+    print(f"{sizes} act {act} biased: {prec} vs fp32 oracle {err:.2e}; vs {prec}-emulating oracle {errq:.2e}; bias effect {bias_effect:.2e}")
+    assert bias_effect > 20 * max(err, 1e-4)   # the biases matter at the size of this test
+    assert np.isfinite(out).all()
+    assert err < (TOL_BF16 if prec == "bf16" else 2e-3)
+    assert errq < (5e-3 if prec == "bf16" else 5e-4)   # biases are rounded to the operand format on the tensor path (bf16: 2^-9 relative)
+    model.close()
+
+
 def test_tc_rejects_unsupported(opz, oracle, ctx):
     p = oracle.Params(flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS | oracle.FLAG_SMOOTH_NN)
     x0, bc = oracle.synthetic_columns(3, p)
