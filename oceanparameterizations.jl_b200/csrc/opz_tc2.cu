@@ -256,27 +256,22 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
       for (int64_t item = item0; item < n_items; item += item_stride) {
 #pragma unroll 1
         for (int r = 0; r < n_rhs; ++r) {
-          bool have_pend = false;
-          uint32_t pend_net = 0, pend_c = 0, pend_ks = 0;
+          // Output-layer MMAs of a fused chunk g (Y_net (+)= H2c * W_out[:, chunk]^T) are issued TWO stages later, at the
+          // head of the stage of chunk g + 2: that stage waits for "accumulator buffer of chunk g drained" anyway, which is
+          // the moment H2c(g) has been written, so they cost no extra blocking wait and no extra issue region.
+          // q1: issued in the coming stage; q0: in the one after.
+          uint32_t q1_net = 0, q1_c = 0, q1_ks = 0, q0_net = 0, q0_c = 0, q0_ks = 0;   // ks == 0: nothing pending
           int s = 0;
-          // output-layer MMAs of the pending fused chunk: Y_net (+)= H2c * W_out[:, chunk]^T, B block at `boff`
-          auto out_op = [&](uint32_t boff, int commit_a, int commit_b) {
-            bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);
-            ptx::tc_fence_after();
-            const uint64_t bd0 = ptx::smem_desc(ring_u32 + boff, 16u * 16u, 128);  // 16 rows per CTA
-            const uint32_t lo = (uint32_t)bd0, hi = (uint32_t)(bd0 >> 32);
-            const uint32_t idesc = idesc0 | ((32u >> 3) << 17);
-            const uint32_t dy = tmem + kColY + 32u * pend_net;
-            if (ptx::elect_one()) {
+          const uint32_t idesc_out = idesc0 | ((32u >> 3) << 17);
+          // issue (elected lane): ks MMAs A = H2c, B block of 16 rows per CTA at ring offset boff
+          auto out_mmas = [&](uint32_t boff, uint32_t net, uint32_t c, uint32_t ks) {
+            const uint64_t bd = ptx::smem_desc(ring_u32 + boff, 16u * 16u, 128);
+            const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
+            const uint32_t dy = tmem + kColY + 32u * net;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < (int)pend_ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, hi, idesc, pend_c > 0 || k > 0);
-              ptx::tc_commit2(bars + B_H2EMPTY);
-              ptx::tc_commit2(bars + commit_a);
-              if (commit_b >= 0) ptx::tc_commit2(bars + commit_b);
-            }
-            __syncwarp();
-            have_pend = false;
+            for (int k = 0; k < 4; ++k)
+              if (k < (int)ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, hi, idesc_out, c > 0 || k > 0);
+            ptx::tc_commit2(bars + B_H2EMPTY);
           };
           bar_wait_t<PROF>(bars, B_XFULL, mask, wacc, W_X);
 #pragma unroll 1
@@ -294,23 +289,27 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 ++g;
                 wait_full();
                 bar_wait_t<PROF>(bars, B_DEMPTY + buf, mask, wacc, W_DEMPTY);
+                const bool more = q1_ks > 0;                 // output-layer MMAs of chunk g - 2 lead this stage
+                if (more) bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);   // arrives right behind "drained"
                 const uint32_t sbase = ring_u32 + a.st_off[s];
                 const uint64_t bd0 = ptx::smem_desc(sbase, (rows / 2) * 16u, 128);  // this CTA holds rows / 2 rows: [k/8][rows/2][8]
                 const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
                 const uint32_t d = tmem + kColD0 + buf * kCW;
-                const bool wait_h1 = (j > 0) && (c0 == 0);   // HF chunk h covers k-steps [4h, 4h + 4)
-                const bool more = have_pend;                 // output-layer MMAs follow in this stage
+                const bool wait_h1 = (j > 0) && (c0 == 0);
                 const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
                 const uint32_t a0 = tmem + a_base;
                 const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25 || kin == 6);
                 // bias MMA: D += [1, 0, ..] x [b; don't care]: the block of rows / 2 x 8 halves right behind the weights; its
-                // second k-group reads whatever follows in the ring (finite 16-bit weights), multiplied by the zeros of A
+                // second k-group reads what follows inside the stage (zeros or finite weights), multiplied by the zeros of A
                 const uint32_t bias_lo = blo + (rows / 2) * (uint32_t)kin * 2u;   // descriptor address units of 16 B
                 const uint32_t a_one = tmem + kColOne;
+                const uint32_t out_off = a.st_off[s] + (rows / 2) * ((uint32_t)kin * 32u + 16u);
+                const int ebar = B_EMPTY + (int)(gs % kNB);
                 if (static_shape && !wait_h1) {
                   // hot path: the A operand is already complete; one straight immediate-offset run
                   ptx::tc_fence_after();
                   if (ptx::elect_one()) {
+                    if (more) out_mmas(out_off, q1_net, q1_c, q1_ks);
                     if (rows == (uint32_t)kCW) {
                       if (kin == 25) issue_range<kCW, 0, 25>(d, a0, blo, bhi, idesc);
                       else issue_range<kCW, 0, 6>(d, a0, blo, bhi, idesc);
@@ -320,7 +319,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                     }
                     ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
                     ptx::tc_commit2(bars + B_DFULL + buf);
-                    if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                    ptx::tc_commit2(bars + ebar);
                   }
                   __syncwarp();
                 } else if (static_shape && kin == 25) {
@@ -332,17 +331,23 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                     for (int h = h0; h < h1; ++h) bar_wait_t<PROF>(bars, B_H1 + h, mask, wacc, W_H1);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
+                      if (grp == 0 && more) out_mmas(out_off, q1_net, q1_c, q1_ks);
                       if (rows == (uint32_t)kCW) issue_hf_group<kCW>(grp, d, a0, blo, bhi, idesc);
                       else issue_hf_group<16>(grp, d, a0, blo, bhi, idesc);
                       if (grp == 2) {
                         ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
                         ptx::tc_commit2(bars + B_DFULL + buf);
-                        if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                        ptx::tc_commit2(bars + ebar);
                       }
                     }
                     __syncwarp();
                   }
                 } else {
+                  if (more) {
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) out_mmas(out_off, q1_net, q1_c, q1_ks);
+                    __syncwarp();
+                  }
 #pragma unroll
                   for (int h = 0; h < kMaxKs / 4; ++h) {
                     if (h * 4 < kin) {
@@ -361,20 +366,35 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                   if (ptx::elect_one()) {
                     ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
                     ptx::tc_commit2(bars + B_DFULL + buf);
-                    if (!more) ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                    ptx::tc_commit2(bars + ebar);
                   }
                   __syncwarp();
                 }
-                // the output-layer MMAs of the PREVIOUS fused chunk ride in this stage, after this chunk's MMAs, so
-                // that the tensor pipe has work while the epilogue converts that chunk
-                if (more) out_op(a.st_off[s] + (rows / 2) * ((uint32_t)kin * 32u + 16u), B_EMPTY + (int)(gs % kNB), -1);
-                if (fused) { have_pend = true; pend_net = (uint32_t)net; pend_c = (uint32_t)(c0 / kCW); pend_ks = rows >> 4; }
+                q1_net = q0_net; q1_c = q0_c; q1_ks = q0_ks;
+                q0_net = (uint32_t)net; q0_c = (uint32_t)(c0 / kCW); q0_ks = fused ? (rows >> 4) : 0u;
               }
             }
           }
-          // the last fused chunk's output-layer MMAs have a (small) stage of their own
+          // tail stage: the output-layer MMAs of the last two chunks (here their H2-full waits are real waits)
           wait_full();
-          out_op(a.st_off[s], B_EMPTY + (int)(gs % kNB), B_YFULL);
+          {
+            uint32_t off = a.st_off[s];
+            if (q1_ks > 0) {
+              bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) out_mmas(off, q1_net, q1_c, q1_ks);
+              __syncwarp();
+              off += q1_ks * 512u;
+            }
+            bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              out_mmas(off, q0_net, q0_c, q0_ks);
+              ptx::tc_commit2(bars + B_YFULL);
+              ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+            }
+            __syncwarp();
+          }
           ++gs;
         }
       }
@@ -527,31 +547,37 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
           float Du[LV + 1], Dv[LV + 1], DT[LV + 1];   // diffusive part of the flux on faces c0 .. c0 + LV
           float cu[LV], cv[LV];                        // Coriolis terms of the owned cells
           {
+            // branch-free on purpose (clamped loads, selects): the LV + 1 faces are independent dependency chains that the
+            // scheduler can only interleave inside one basic block; values computed for a boundary face are discarded
             float xu[LV + 2], xw[LV + 2], xT[LV + 2];
 #pragma unroll
             for (int i = 0; i < LV + 2; ++i) {
-              const int cell = c0 - 1 + i;
-              const bool ok = cell >= 0 && cell < kNz;
-              xu[i] = ok ? s_xs[cell * kM + m] : 0.0f;
-              xw[i] = ok ? s_xs[(kNz + cell) * kM + m] : 0.0f;
-              xT[i] = ok ? s_xs[(2 * kNz + cell) * kM + m] : 0.0f;
+              const int cell = min(max(c0 - 1 + i, 0), kNz - 1);
+              xu[i] = s_xs[cell * kM + m];
+              xw[i] = s_xs[(kNz + cell) * kM + m];
+              xT[i] = s_xs[(2 * kNz + cell) * kM + m];
             }
             const bool mpp = P.flags & OPZ_FLAG_MPP;
+            const bool ca = P.flags & OPZ_FLAG_CA;
+            const bool ca_du = P.flags & OPZ_FLAG_CA_SELECT_DUDZ;
 #pragma unroll
             for (int i = 0; i <= LV; ++i) {
               const int f = c0 + i;
-              Du[i] = 0.0f; Dv[i] = 0.0f; DT[i] = 0.0f;
-              if (mpp && f >= 1 && f < kNz) {
-                const float gu = (xu[i + 1] - xu[i]) * P.nzf;
-                const float gv = (xw[i + 1] - xw[i]) * P.nzf;
-                const float gT = (xT[i + 1] - xT[i]) * P.nzf;
-                const float Ri = richardson<true>(P, gu, gv, gT);
-                const float nu = nu_of_ri<true>(P, Ri);
-                const float nuT = nuT_of<true>(P, nu, gu, gT);
-                Du[i] = P.c_u * nu * gu;
-                Dv[i] = P.c_v * nu * gv;
-                DT[i] = P.c_T * nuT * gT;
-              }
+              const bool interior = mpp && f >= 1 && f < kNz;
+              const float gu = (xu[i + 1] - xu[i]) * P.nzf;
+              const float gv = (xw[i + 1] - xw[i]) * P.nzf;
+              const float gT = (xT[i + 1] - xT[i]) * P.nzf;
+              // = richardson<true>, nu_of_ri<true>, nuT_of<true> of opz_device.cuh with the flag tests hoisted
+              const float Bz = P.cBz * (gT + P.eps);
+              const float sa = P.s_u * (gu + P.eps);
+              const float sb = P.s_v * (gv + P.eps);
+              const float Ri = __fdividef(Bz, sa * sa + sb * sb);
+              const float nu = P.nu0 + __fdividef(P.nu_m, 1.0f + __expf((Ri - P.Ric) * P.two_inv_dRi));
+              const float sel = ca_du ? gu : gT;
+              const float nuT = (ca && !(sel > 0.0f)) ? P.kappa : nu * P.inv_Pr;
+              Du[i] = interior ? P.c_u * nu * gu : 0.0f;
+              Dv[i] = interior ? P.c_v * nu * gv : 0.0f;
+              DT[i] = interior ? P.c_T * nuT * gT : 0.0f;
             }
 #pragma unroll
             for (int i = 0; i < LV; ++i) {
@@ -593,12 +619,8 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll
               for (int i = 0; i <= LV; ++i) {
                 const int f = c0 + i;
-                if (f == 0) F[i] = Fb[v];
-                else if (f == kNz) F[i] = Ft[v];
-                else {
-                  const float y = (i == 0 ? __uint_as_float(ylo[7]) : __uint_as_float(yhi[i == 0 ? 0 : i - 1])) + a.b3[v * 32 + f - 1];
-                  F[i] = y - D[i];
-                }
+                const float y = (i == 0 ? __uint_as_float(ylo[7]) : __uint_as_float(yhi[i == 0 ? 0 : i - 1])) + a.b3[v * 32 + max(f - 1, 0)];
+                F[i] = f == 0 ? Fb[v] : (f == kNz ? Ft[v] : y - D[i]);
               }
             }
             const float A = v == 0 ? P.A_u : (v == 1 ? P.A_v : P.A_T);
@@ -697,7 +719,8 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   tape.clear();
   pl.n_stages = 0;
   std::vector<uint16_t> half[2];
-  struct Pending { bool valid; int net, c, cols; } pend{false, 0, 0, 0};
+  // output-layer blocks ride two stages behind their fused chunk (see the MMA issuer): q1 goes into the coming stage
+  struct Pending { bool valid; int net, c, cols; } q1{false, 0, 0, 0}, q0{false, 0, 0, 0};
   bool overflow = false;
   auto out_halves = [&](const Pending& p) {   // 16 rows per CTA of W_out over the 64 (or fewer) inputs of chunk p.c
     const float* wn = w.data() + (size_t)p.net * nd.P;
@@ -732,14 +755,17 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
             half[hf].push_back(fp16 ? f16_rne(bv) : bf16_rne(bv));
             for (int z = 0; z < 7; ++z) half[hf].push_back(0);
           }
-        if (pend.valid) { out_halves(pend); pend.valid = false; }
+        if (q1.valid) out_halves(q1);
         else for (int hf = 0; hf < 2; ++hf) half[hf].resize(half[hf].size() + (size_t)(rows / 2) * 8, 0);  // the bias MMA's second k-group stays inside the stage
         close_stage();
-        if (fused) pend = Pending{true, net, c, rows};
+        q1 = q0;
+        q0 = Pending{fused, net, c, rows};
       }
     }
   }
-  if (pend.valid) { out_halves(pend); close_stage(); }
+  if (q1.valid) out_halves(q1);
+  out_halves(q0);   // the last chunk of a net is always a fused one
+  close_stage();
   if (overflow) { set_error("tensor-core path: schedule longer than the stage table"); return OPZ_EUNSUP; }
   pl.tape_bytes = tape.size() * 2;
   // ---- ring placement (byte FIFO, every right-hand side starts at offset 0) and in-flight allowance ----
