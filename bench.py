@@ -372,7 +372,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches), "finite": finite,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "kernel": ("rollout_fp32_kernel" if prec_name == "fp32" else "rollout_tc_kernel (tcgen05, " + prec_name + " operands, fp32 accumulate)"),
+                     "kernel": ("rollout_fp32_kernel" if prec_name == "fp32" else "rollout_tc2_kernel (tcgen05 cta_group::2, " + prec_name + " operands, fp32 accumulate)"),
                      "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_kernel_ms,
                      "fp32_fma_peak_tflops_at_max_clock": 74.4},
     }
