@@ -52,7 +52,7 @@ enum : int {
   B_DFULL = B_EMPTY + kNB,      // [2] accumulator chunk complete         (tcgen05.commit, both CTAs)
   B_DEMPTY = B_DFULL + 2,       // [2] accumulator chunk drained          (epilogue warps of both CTAs)
   B_H1 = B_DEMPTY + 2,          // [7] chunk c of HF written
-  B_H2FULL = B_H1 + 7,          // H2c written
+  B_H2FULL = B_H1 + 7,          // (unused: "H2c written" is signalled by the chunk's D-empty arrival)
   B_H2EMPTY = B_H2FULL + 1,     // H2c consumed by the output-layer MMAs  (tcgen05.commit)
   B_YFULL = B_H2EMPTY + 1,      // Y complete                             (tcgen05.commit)
   B_XFULL = B_YFULL + 1,        // X written, Y consumed
@@ -239,6 +239,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
     if (n_rhs > 0) {
       uint32_t mask = (1u << (B_DEMPTY + 0)) | (1u << (B_DEMPTY + 1));  // "drained" starts released
       uint32_t gs = 0, g = 0;
+      bool first_rhs = true;
       long long wacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const long long t_begin = PROF ? clock64() : 0;
       const uint32_t ring_u32 = ptx::smem_u32(s_ring);
@@ -288,9 +289,10 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 const uint32_t buf = g & 1u;
                 ++g;
                 wait_full();
-                bar_wait_t<PROF>(bars, B_DEMPTY + buf, mask, wacc, W_DEMPTY);
+                // "buffer drained" of chunk g - 2 (for a fused chunk also: its H2c is written).  The first two chunks of a
+                // right-hand side find their buffers' phases already consumed by the previous tail (see below).
+                if (s >= 2 || first_rhs) bar_wait_t<PROF>(bars, B_DEMPTY + buf, mask, wacc, W_DEMPTY);
                 const bool more = q1_ks > 0;                 // output-layer MMAs of chunk g - 2 lead this stage
-                if (more) bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);   // arrives right behind "drained"
                 const uint32_t sbase = ring_u32 + a.st_off[s];
                 const uint64_t bd0 = ptx::smem_desc(sbase, (rows / 2) * 16u, 128);  // this CTA holds rows / 2 rows: [k/8][rows/2][8]
                 const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
@@ -375,18 +377,19 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
               }
             }
           }
-          // tail stage: the output-layer MMAs of the last two chunks (here their H2-full waits are real waits)
+          // tail stage: the output-layer MMAs of the last two chunks, each behind the "drained" arrival of its buffer
+          // (these two phases are therefore not waited for again by the first two chunks of the next right-hand side)
           wait_full();
           {
             uint32_t off = a.st_off[s];
+            bar_wait_t<PROF>(bars, B_DEMPTY + (g & 1u), mask, wacc, W_H2FULL);          // chunk g - 2
             if (q1_ks > 0) {
-              bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);
               ptx::tc_fence_after();
               if (ptx::elect_one()) out_mmas(off, q1_net, q1_c, q1_ks);
               __syncwarp();
               off += q1_ks * 512u;
             }
-            bar_wait_t<PROF>(bars, B_H2FULL, mask, wacc, W_H2FULL);
+            bar_wait_t<PROF>(bars, B_DEMPTY + ((g + 1u) & 1u), mask, wacc, W_H2FULL);   // chunk g - 1
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               out_mmas(off, q0_net, q0_c, q0_ks);
@@ -395,6 +398,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
             }
             __syncwarp();
           }
+          first_rhs = false;
           ++gs;
         }
       }
@@ -533,8 +537,8 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                  arrive_issuer(B_DEMPTY + buf);
-                  arrive_issuer(fused ? B_H2FULL : B_H1 + c);
+                  arrive_issuer(B_DEMPTY + buf);          // accumulator drained AND (fused chunk) H2c written
+                  if (!fused) arrive_issuer(B_H1 + c);
                 }
                 if (prof_me) eacc[E_ST - 8] += clock64() - t_st;
               }
