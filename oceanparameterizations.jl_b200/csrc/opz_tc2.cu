@@ -86,6 +86,7 @@ struct Args {
   float dt, t0;
   int n_steps, save_every, n_save;
   int L, n_stages;
+  int n_mma_warps;   // 1 or 2 issuing warps in the leader CTA
   int hpad[2];
   float b3[96];   // output-layer biases [net][32] (the hidden-layer biases ride in the weight tape)
   uint32_t st_off[kMaxStages];
@@ -128,6 +129,18 @@ __device__ __forceinline__ void bar_wait_t(uint64_t* bars, int id, uint32_t& mas
   }
 }
 
+// wait for completion number `phase` (0-based) of a barrier; callers never ask for anything older than the last completion
+template <bool PROF>
+__device__ __forceinline__ void wait_phase(uint64_t* bars, int id, uint32_t phase, long long* acc, int slot) {
+  if constexpr (PROF) {
+    const long long t0 = clock64();
+    ptx::mbar_wait(bars + id, phase & 1u);
+    acc[slot] += clock64() - t0;
+  } else {
+    ptx::mbar_wait(bars + id, phase & 1u);
+  }
+}
+
 template <bool FP16, int ACT>
 __device__ __forceinline__ uint32_t pack_act(float a, float b) {
   if constexpr (ACT == OPZ_ACT_RELU) return FP16 ? ptx::pack_f16x2_relu(a, b) : ptx::pack_bf16x2_relu(a, b);
@@ -153,8 +166,9 @@ __device__ __forceinline__ void issue_hf_group(int grp, uint32_t d, uint32_t a0,
 
 // E epilogue warps per CTA: E / 4 threads share one ocean column (TMEM lane); each owns LV = 128 / E cells.
 template <bool FP16, int ACT, int E, bool PROF>
-__global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __grid_constant__ Args a) {
-  constexpr int kThreads = (2 + E) * 32;
+__global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __grid_constant__ Args a) {
+  constexpr int kThreads = (3 + E) * 32;
+  constexpr int kMma2Warp = 2 + E;     // second MMA-issuing warp (the epilogue warps keep indices 2 .. 1 + E: warp % 4 = TMEM quadrant)
   constexpr int kEpiThreads = E * 32;
   constexpr int PS = E / 4;            // threads per column
   constexpr int LV = kNz / PS;         // cells per thread
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
       }
     }
     __syncwarp();
-  } else if (warp == 1 && rank != 0) {
+  } else if (warp == 1 && rank != 0) {  // (warp 2 + E of the peer CTA idles)
     // ================= peer CTA: forward "my half of the stage has landed" to the leader =================
     if (lane == 0 && n_rhs > 0) {
       uint32_t gs = 0;
@@ -232,14 +246,18 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
           }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA) =================
+  } else if (warp == 1 || warp == kMma2Warp) {
+    // ================= MMA issuer(s) (leader CTA) =================
+    // With two issuing warps, warp 1 owns the even stages and warp 2 + E the odd ones: both walk the same schedule with the
+    // same counters, every barrier phase is computed from those counters (no per-warp toggling), and a warp simply skips
+    // the stages of the other.  What orders the two warps' MMAs where it matters: accumulator buffers and H2c go through the
+    // epilogue's barriers; the output-layer MMAs all ACCUMULATE into a Y the epilogue zeroed, so their order is free.
     // The whole warp walks the schedule (the loops build_plan() used to lay out the tape) with warp-uniform
     // counters; one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
-    if (n_rhs > 0) {
-      uint32_t mask = (1u << (B_DEMPTY + 0)) | (1u << (B_DEMPTY + 1));  // "drained" starts released
-      uint32_t gs = 0, g = 0;
-      bool first_rhs = true;
+    const uint32_t me = warp == 1 ? 0u : 1u;
+    const uint32_t nw = (uint32_t)a.n_mma_warps;
+    if (n_rhs > 0 && me < nw && rank == 0) {
+      uint32_t gs = 0, g = 0, rhs_ctr = 0;   // global stage / accumulator-chunk / right-hand-side counters
       long long wacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const long long t_begin = PROF ? clock64() : 0;
       const uint32_t ring_u32 = ptx::smem_u32(s_ring);
@@ -271,12 +289,13 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const uint32_t dy = tmem + kColY + 32u * net;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < (int)ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, hi, idesc_out, c > 0 || k > 0);
+              if (k < (int)ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, hi, idesc_out, true);   // Y was zeroed by the epilogue
             ptx::tc_commit2(bars + B_H2EMPTY);
           };
-          bar_wait_t<PROF>(bars, B_XFULL, mask, wacc, W_X);
+          wait_phase<PROF>(bars, B_XFULL, rhs_ctr, wacc, W_X);
 #pragma unroll 1
           for (int net = 0; net < 3; ++net) {
+            const uint32_t h1_phase = 3u * rhs_ctr + (uint32_t)net;   // H1[h] completes once per net and right-hand side
 #pragma unroll 1
             for (int j = 0; j < L - 1; ++j) {
               const bool fused = (j == L - 2);
@@ -287,11 +306,18 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
               for (int c0 = 0; c0 < hp; c0 += kCW, ++s, ++gs) {
                 const uint32_t rows = (uint32_t)min(kCW, hp - c0);
                 const uint32_t buf = g & 1u;
+                const uint32_t gi = g;                       // global index of this accumulator chunk
                 ++g;
+                const bool mine = (nw == 1u) || ((gs & 1u) == me);
+                if (!mine) {   // the other issuing warp's stage: only the bookkeeping
+                  q1_net = q0_net; q1_c = q0_c; q1_ks = q0_ks;
+                  q0_net = (uint32_t)net; q0_c = (uint32_t)(c0 / kCW); q0_ks = fused ? (rows >> 4) : 0u;
+                  continue;
+                }
                 wait_full();
-                // "buffer drained" of chunk g - 2 (for a fused chunk also: its H2c is written).  The first two chunks of a
-                // right-hand side find their buffers' phases already consumed by the previous tail (see below).
-                if (s >= 2 || first_rhs) bar_wait_t<PROF>(bars, B_DEMPTY + buf, mask, wacc, W_DEMPTY);
+                // "buffer drained" of chunk g - 2 = completion (g >> 1) - 1 of this buffer's barrier (for a fused chunk also:
+                // its H2c is written)
+                if (gi >= 2u) wait_phase<PROF>(bars, B_DEMPTY + (int)buf, (gi >> 1) - 1u, wacc, W_DEMPTY);
                 const bool more = q1_ks > 0;                 // output-layer MMAs of chunk g - 2 lead this stage
                 const uint32_t sbase = ring_u32 + a.st_off[s];
                 const uint64_t bd0 = ptx::smem_desc(sbase, (rows / 2) * 16u, 128);  // this CTA holds rows / 2 rows: [k/8][rows/2][8]
@@ -330,7 +356,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll 1
                   for (int grp = 0; grp < 3; ++grp) {
                     const int h0 = grp == 0 ? 0 : (grp == 1 ? 3 : 5), h1 = grp == 0 ? 3 : (grp == 1 ? 5 : 7);
-                    for (int h = h0; h < h1; ++h) bar_wait_t<PROF>(bars, B_H1 + h, mask, wacc, W_H1);
+                    for (int h = h0; h < h1; ++h) wait_phase<PROF>(bars, B_H1 + h, h1_phase, wacc, W_H1);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
                       if (grp == 0 && more) out_mmas(out_off, q1_net, q1_c, q1_ks);
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll
                   for (int h = 0; h < kMaxKs / 4; ++h) {
                     if (h * 4 < kin) {
-                      if (wait_h1) bar_wait_t<PROF>(bars, B_H1 + h, mask, wacc, W_H1);
+                      if (wait_h1) wait_phase<PROF>(bars, B_H1 + h, h1_phase, wacc, W_H1);
                       ptx::tc_fence_after();  // orders the MMAs after the epilogue's tcgen05.st seen through the barriers above
                       if (ptx::elect_one()) {
 #pragma unroll
@@ -378,18 +404,17 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
             }
           }
           // tail stage: the output-layer MMAs of the last two chunks, each behind the "drained" arrival of its buffer
-          // (these two phases are therefore not waited for again by the first two chunks of the next right-hand side)
-          wait_full();
-          {
+          if (nw == 1u || (gs & 1u) == me) {
+            wait_full();
             uint32_t off = a.st_off[s];
-            bar_wait_t<PROF>(bars, B_DEMPTY + (g & 1u), mask, wacc, W_H2FULL);          // chunk g - 2
+            wait_phase<PROF>(bars, B_DEMPTY + (int)((g - 2u) & 1u), (g - 2u) >> 1, wacc, W_H2FULL);   // chunk g - 2
             if (q1_ks > 0) {
               ptx::tc_fence_after();
               if (ptx::elect_one()) out_mmas(off, q1_net, q1_c, q1_ks);
               __syncwarp();
               off += q1_ks * 512u;
             }
-            bar_wait_t<PROF>(bars, B_DEMPTY + ((g + 1u) & 1u), mask, wacc, W_H2FULL);   // chunk g - 1
+            wait_phase<PROF>(bars, B_DEMPTY + (int)((g - 1u) & 1u), (g - 1u) >> 1, wacc, W_H2FULL);   // chunk g - 1
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               out_mmas(off, q0_net, q0_c, q0_ks);
@@ -398,11 +423,11 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
             }
             __syncwarp();
           }
-          first_rhs = false;
+          ++rhs_ctr;
           ++gs;
         }
       }
-      if (PROF && blockIdx.x == 0 && lane == 0) {
+      if (PROF && blockIdx.x == 0 && lane == 0 && me == 0u) {
         wacc[W_TOTAL] = clock64() - t_begin;
         for (int i = 0; i < 8; ++i) g_tc2_wait[i] = (unsigned long long)wacc[i];
       }
@@ -533,6 +558,14 @@ __global__ void __launch_bounds__((2 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll
                 for (int grp = 0; grp < CPW / 16; ++grp)
                   if (grp * 16 < ncols) ptx::tmem_st8(dst + grp * 8, pk[grp]);
+                if (net == 0 && j == 0 && c == 0) {
+                  // first chunk of a right-hand side: zero this thread's share of Y (every output-layer MMA accumulates).  All
+                  // threads have read the previous Y (this chunk's MMAs were issued behind the X-full barrier), and the first
+                  // output-layer MMA waits for a LATER chunk's drained arrival of these same warps.
+                  const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+                  for (int z = 0; z < 96 / PS; z += 8) ptx::tmem_st8(tmem + lane_addr + kColY + (uint32_t)(ps * (96 / PS) + z), zero);
+                }
                 ptx::tmem_wait_st();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -846,6 +879,8 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   a.L = pl->L; a.n_stages = pl->n_stages;
   a.hpad[0] = pl->hpad[0]; a.hpad[1] = pl->hpad[1];
   std::memcpy(a.b3, pl->b3, sizeof(a.b3));
+  a.n_mma_warps = 2;
+  if (const char* e = getenv("OPZ_TC_MMA_WARPS")) a.n_mma_warps = atoi(e) == 1 ? 1 : 2;
   std::memcpy(a.st_off, pl->st_off, sizeof(a.st_off));
   std::memcpy(a.st_bytes, pl->st_bytes, sizeof(a.st_bytes));
   std::memcpy(a.st_src, pl->st_src, sizeof(a.st_src));
@@ -875,7 +910,7 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   if (grid < 2) grid = 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((2 + E) * 32);
+  cfg.blockDim = dim3((3 + E) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
