@@ -1,6 +1,7 @@
 // opz_capi.cu — the extern "C" surface declared in include/opz.h.
 // Host-pointer entry points stage through grow-only device scratch owned by the context and
 // are blocking; `_dev` entry points enqueue on the context stream and return.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -102,6 +103,10 @@ int opz_ctx_destroy(opz_ctx* ctx) {
   bptt_release(ctx);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  for (cudaEvent_t e : ctx->slab_ev)
+    if (e) cudaEventDestroy(e);
   if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OPZ_OK;
@@ -280,12 +285,53 @@ int opz_rollout_forward(opz_ctx* ctx, const opz_model* m, const opz_params* p, c
   if ((rc = ensure_scratch(ctx, 0, sizeof(float) * B * S, (void**)&dx))) return rc;
   if ((rc = ensure_scratch(ctx, 1, sizeof(float) * B * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
   if ((rc = ensure_scratch(ctx, 2, sizeof(float) * B * n_save * S, (void**)&dout))) return rc;
-  OPZ_CUDA(cudaMemcpyAsync(dx, x0, sizeof(float) * B * S, cudaMemcpyHostToDevice, ctx->stream));
-  OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = opz_rollout_forward_dev(ctx, m, p, dx, dbc, B, scheme, dt_nd, t0, n_steps, save_every, precision, dout)))
-    return rc;
-  OPZ_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * B * n_save * S, cudaMemcpyDeviceToHost, ctx->stream));
-  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  // Large ensembles are pipelined in slabs of whole waves of column tiles: slab i + 1 is copied in and slab i - 1 copied out
+  // while slab i is stepped (columns are independent, so the slab boundaries do not change a single bit of the result).
+  // With pageable host memory the copies degrade to staged synchronous ones; the result is the same.
+  const int64_t wave = (int64_t)ctx->sm_count * 128;          // one 128-column tile per SM
+  int64_t slab = wave * 8;
+  int n_slabs = (int)((B + slab - 1) / slab);
+  if (n_slabs > 16) { n_slabs = 16; slab = ((B + n_slabs - 1) / n_slabs + wave - 1) / wave * wave; n_slabs = (int)((B + slab - 1) / slab); }
+  if (n_slabs < 3) {
+    OPZ_CUDA(cudaMemcpyAsync(dx, x0, sizeof(float) * B * S, cudaMemcpyHostToDevice, ctx->stream));
+    OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = opz_rollout_forward_dev(ctx, m, p, dx, dbc, B, scheme, dt_nd, t0, n_steps, save_every, precision, dout)))
+      return rc;
+    OPZ_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * B * n_save * S, cudaMemcpyDeviceToHost, ctx->stream));
+    OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OPZ_OK;
+  }
+  if (!ctx->h2d_stream) OPZ_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) OPZ_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 1 + 2 * n_slabs; ++i)
+    if (!ctx->slab_ev[i]) OPZ_CUDA(cudaEventCreateWithFlags(&ctx->slab_ev[i], cudaEventDisableTiming));
+  // work queued on the context's stream before this call comes first
+  OPZ_CUDA(cudaEventRecord(ctx->slab_ev[0], ctx->stream));
+  OPZ_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->slab_ev[0], 0));
+  OPZ_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->slab_ev[0], 0));
+  int rc_slab = OPZ_OK;
+  for (int i = 0; i < n_slabs; ++i) {
+    const int64_t c0 = (int64_t)i * slab, nb = std::min<int64_t>(slab, B - c0);
+    cudaEvent_t ev_in = ctx->slab_ev[1 + 2 * i], ev_done = ctx->slab_ev[2 + 2 * i];
+    OPZ_CUDA(cudaMemcpyAsync(dx + c0 * S, x0 + c0 * S, sizeof(float) * nb * S, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    OPZ_CUDA(cudaMemcpyAsync(dbc + c0 * OPZ_BC_STRIDE, bc + c0 * OPZ_BC_STRIDE, sizeof(float) * nb * OPZ_BC_STRIDE,
+                             cudaMemcpyHostToDevice, ctx->h2d_stream));
+    OPZ_CUDA(cudaEventRecord(ev_in, ctx->h2d_stream));
+    OPZ_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+    rc_slab = opz_rollout_forward_dev(ctx, m, p, dx + c0 * S, dbc + c0 * OPZ_BC_STRIDE, nb, scheme, dt_nd, t0, n_steps, save_every,
+                                      precision, dout + c0 * n_save * S);
+    if (rc_slab) break;
+    OPZ_CUDA(cudaEventRecord(ev_done, ctx->stream));
+    OPZ_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev_done, 0));
+    OPZ_CUDA(cudaMemcpyAsync(out + c0 * n_save * S, dout + c0 * n_save * S, sizeof(float) * nb * n_save * S, cudaMemcpyDeviceToHost,
+                             ctx->d2h_stream));
+  }
+  // blocking call: nothing of it is in flight when it returns (also after an error in the middle)
+  cudaError_t e1 = cudaStreamSynchronize(ctx->h2d_stream), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->d2h_stream);
+  if (rc_slab) return rc_slab;
+  OPZ_CUDA(e1);
+  OPZ_CUDA(e2);
+  OPZ_CUDA(e3);
   return OPZ_OK;
 }
 

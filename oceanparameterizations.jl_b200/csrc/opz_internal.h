@@ -15,6 +15,9 @@ struct opz_ctx {
   // grow-only device scratch (staging of host buffers; BPTT checkpoints)
   void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // host-buffer rollouts: copy-in / copy-out streams and events for the slab pipeline (created on first use)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t slab_ev[34] = {};   // [0] entry fence, [1 + 2i] slab i copied in, [2 + 2i] slab i computed
   // BPTT path (opz_bptt.cu): private stream for graph capture (the adopted stream may be the legacy
   // default stream, which cannot be captured) and the cached graph executables
   cudaStream_t capture_stream = nullptr;

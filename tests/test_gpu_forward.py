@@ -204,3 +204,38 @@ def test_reference_shaped_api(opz, oracle, ctx):
     assert rel_err(k, kr) < 5e-5
     uw, vw, wT = opz.predict_flux(uw_NN, vw_NN, wT_NN, x0[3], BCs, cond_t, scalings, constants, derivatives, None)
     assert uw.shape == (33,)
+
+
+def test_host_buffer_rollout_slab_pipeline_is_bit_exact(opz, oracle):
+    """opz_rollout_forward pipelines large ensembles in slabs (copy-in / step / copy-out on three streams).  Columns are
+    independent, so the result must equal the one-launch device-resident call bit for bit, and a sample of columns
+    must sit on the oracle."""
+    import torch
+    p = oracle.Params()
+    ctx = opz.default_context()
+    B = 3 * 8 * 148 * 128 + 4321            # four slabs, the last one ragged
+    x0s, bcs = oracle.synthetic_columns(4096, p)
+    reps = (B + 4095) // 4096
+    x0 = np.ascontiguousarray(np.tile(x0s, (reps, 1))[:B])
+    bc = np.ascontiguousarray(np.tile(bcs, (reps, 1))[:B])
+    x0[:, :32] += np.linspace(0.0, 1e-3, B, dtype=np.float32)[:, None]   # no two columns alike
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1, bias_scale=0.2)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    for prec in (opz.PREC_FP16, opz.PREC_FP32):
+        n_steps, save_every = (2, 1) if prec == opz.PREC_FP16 else (1, 0)
+        host = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, n_steps, save_every, precision=prec)
+        xd, bd = torch.from_numpy(x0).cuda(), torch.from_numpy(bc).cuda()
+        od = torch.empty(host.shape, dtype=torch.float32, device="cuda")
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        opz.rollout_forward_dev(model, pp, xd.data_ptr(), bd.data_ptr(), B, opz.SCHEME_RK4, dt, n_steps, save_every, od.data_ptr(),
+                                precision=prec)
+        torch.cuda.synchronize()
+        assert np.array_equal(host, od.cpu().numpy())
+        pick = np.array([0, 1, 148 * 128 * 8 - 1, 148 * 128 * 8, 2 * 148 * 128 * 8 + 5, B - 1])
+        ref = oracle.rollout(x0[pick], bc[pick], m, p, oracle.SCHEME_RK4, dt, n_steps, save_every if save_every else n_steps)
+        if not save_every:
+            ref = ref[:, -1:]   # final state only
+        assert oracle.profile_error(host[pick], ref, 32) < (1e-3 if prec == opz.PREC_FP16 else 1e-4)
+    model.close()
