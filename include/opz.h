@@ -159,6 +159,26 @@ int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, con
                       const float* loss_w_host, int precision, float* loss_out_dev,
                       float* grad_out_dev);
 
+/* ---- the same, plus the gradient w.r.t. the five modified Pacanowski-Philander parameters -------
+ * Replaces the Zygote gradient inside optimise_modified_pacanowski_philander / DE
+ * (wind_mixing/src/diffusivity_parameter_optimisation.jl:1-33 the right-hand side, :112-200 the
+ * loss and its optimisation): grad_mpp_out[5] = d loss / d (nu0, nu_m, dRi, Ric, Pr), the
+ * reference's parameter order (:2), UNSCALED (the reference optimises p / p_initial, :44-48,70;
+ * that factor stays on the host).  The reference's DE is this library's right-hand side with a
+ * zero-weight model and flags OPZ_FLAG_MPP | OPZ_FLAG_RI_EPS | OPZ_FLAG_BC_MINUS_SCALE0; with a
+ * non-zero model the NN fluxes are simply part of the differentiated solve.  Needs OPZ_FLAG_MPP.
+ * Obtained in the same backward sweep as grad_out; multi-GPU callers all-reduce it with grad_out. */
+int opz_loss_grad_mpp(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
+                      const float* bc, int64_t B, int64_t B_total, int scheme, float dt_nd,
+                      float t0, int n_steps, int save_every, const float* target,
+                      const float* loss_w, int precision, float* loss_out, float* grad_out,
+                      float* grad_mpp_out);
+int opz_loss_grad_mpp_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p,
+                          const float* x0_dev, const float* bc_dev, int64_t B, int64_t B_total,
+                          int scheme, float dt_nd, float t0, int n_steps, int save_every,
+                          const float* target_dev, const float* loss_w_host, int precision,
+                          float* loss_out_dev, float* grad_out_dev, float* grad_mpp_out_dev);
+
 /* ---- batched MLP forward ------------------------------------------------------------------------
  * Replaces predict(V, model; scaled=true) (src/predict.jl:12-34): one launch over Nt input
  * columns.  which_net: 0 uw, 1 vw, 2 wT.  x[Nt][3nz] -> y[Nt][nz-1]. */

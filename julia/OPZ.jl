@@ -142,6 +142,20 @@ function loss_and_gradient(model::Model, params::OpzParams, weights::Vector{Floa
     return loss[1], loss[2:7], grad
 end
 
+# ---- the same plus d loss / d (ν₀, ν₋, ΔRi, Riᶜ, Pr): the gradient optimise_modified_pacanowski_philander takes with Zygote
+#      (diffusivity_parameter_optimisation.jl:1-33, 112-200); unscaled, the caller multiplies by its scalings.parameters ------
+function loss_and_gradient_mpp(model::Model, params::OpzParams, x0::Matrix{Float32}, bc::Matrix{Float32},
+                               target::Array{Float32,3}, loss_w::Vector{Float32}, timestepper::Stepper, n_steps, save_every; t0=0f0)
+    B = size(x0, 2)
+    loss = zeros(Float32, 7); grad = zeros(Float32, 3model.P); gmpp = zeros(Float32, 5)
+    GC.@preserve x0 bc target loss_w loss grad gmpp check(ccall((:opz_loss_grad_mpp, libopz), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{OpzParams}, Ptr{Float32}, Ptr{Float32}, Int64, Int64, Cint, Cfloat, Cfloat, Cint, Cint,
+         Ptr{Float32}, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+        ctx().h, model.h, Ref(params), x0, bc, B, B, timestepper.scheme, timestepper.dt, t0, n_steps, save_every,
+        target, loss_w, timestepper.precision, loss, grad, gmpp))
+    return loss[1], loss[2:7], grad, gmpp
+end
+
 # ---- predict(𝒱, model) (src/predict.jl:12-34): one batched launch --------------------------------------
 function predict(𝒱, model::Model, which_net::Integer; scaled=false)
     x = Float32.(𝒱.uvT_scaled)                      # 3Nz × Nt  == C [Nt][3Nz]

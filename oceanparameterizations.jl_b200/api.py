@@ -436,6 +436,26 @@ def loss_grad(model: NDEModel, params: L.OpzParams, x0, bc, target, loss_w, sche
     return float(loss_out[0]), loss_out[1:].copy(), grad
 
 
+def loss_grad_mpp(model: NDEModel, params: L.OpzParams, x0, bc, target, loss_w, scheme: int, dt_nd: float, n_steps: int,
+                  save_every: int, *, t0: float = 0.0, B_total: Optional[int] = None, precision: int = L.PREC_FP32):
+    """loss_grad plus d loss / d (nu0, nu_m, dRi, Ric, Pr) (diffusivity_parameter_optimisation.jl:2, unscaled):
+    returns (total, components[6], grad[3P], grad_mpp[5])."""
+    x0 = _f32(x0)
+    B = x0.shape[0]
+    bc = _f32(bc, (B, L.BC_STRIDE))
+    n_save = n_steps // save_every + 1
+    target = _f32(target, (B, n_save, x0.shape[1]))
+    lw = _f32(loss_w, (6,))
+    loss_out = np.zeros(7, dtype=np.float32)
+    grad = np.zeros(3 * model.P, dtype=np.float32)
+    gmpp = np.zeros(5, dtype=np.float32)
+    L.check(L.lib.opz_loss_grad_mpp(model.ctx._h, model._h, C.byref(params), _fptr(x0), _fptr(bc), B,
+                                    B if B_total is None else int(B_total), scheme, float(dt_nd), float(t0), int(n_steps),
+                                    int(save_every), _fptr(target), _fptr(lw), precision, _fptr(loss_out), _fptr(grad),
+                                    _fptr(gmpp)))
+    return float(loss_out[0]), loss_out[1:].copy(), grad, gmpp
+
+
 def loss_grad_dev(model: NDEModel, params: L.OpzParams, x0_ptr: int, bc_ptr: int, B: int, B_total: int, target_ptr: int,
                   loss_w, scheme: int, dt_nd: float, n_steps: int, save_every: int, loss_out_ptr: int, grad_out_ptr: int, *,
                   t0: float = 0.0, precision: int = L.PREC_FP32) -> None:
@@ -625,6 +645,40 @@ def train_NDE(uw_NN, vw_NN, wT_NN, 𝒟train, tsteps, timestepper, optimizers, e
     model.close()
     out = tuple(NN_constructions.__dict__[k](weights[NN_ranges.__dict__[k]]) for k in ("uw", "vw", "wT"))
     return out + (history,)
+
+
+def optimise_modified_pacanowski_philander(model: NDEModel, params: L.OpzParams, x0, bc, target, loss_w, timestepper,
+                                           n_steps: int, save_every: int, optimizers, maxiters: int = 100, *,
+                                           callback=None, comm=None, B_total: Optional[int] = None):
+    """Host loop of optimise_modified_pacanowski_philander (diffusivity_parameter_optimisation.jl:36-231): the five
+    parameters p = (nu0, nu_m, dRi, Ric, Pr) are optimised in the reference's scaled form p / p_initial (:44-48), clipped to
+    its box [0, 10] (:197), with the gradient of the profile loss taken by libopz (opz_loss_grad_mpp) instead of Zygote.
+    `model` carries the NN weights that stay fixed (an all-zero model reproduces the reference's NN-free DE, :1-33);
+    `params` supplies everything else and is updated in place.  `comm(buf)` sums a float32 buffer over ranks (multi-GPU).
+    Returns (p[5], history of total losses)."""
+    p0 = np.array([params.nu0, params.nu_m, params.dRi, params.Ric, params.Pr], dtype=np.float64)
+    if np.any(p0 <= 0):
+        raise ValueError("the initial parameters must be positive (they are the scalings)")
+    scaled = np.ones(5, dtype=np.float64)
+    history = []
+    for opt in optimizers:
+        for it in range(maxiters):
+            p = scaled * p0
+            params.nu0, params.nu_m, params.dRi, params.Ric, params.Pr = (float(v) for v in p)
+            total, comps, _, gm = loss_grad_mpp(model, params, x0, bc, target, loss_w, timestepper.scheme, timestepper.dt,
+                                                n_steps, save_every, B_total=B_total, precision=timestepper.precision)
+            buf = np.concatenate([[total], comps, gm]).astype(np.float32)
+            if comm is not None:
+                comm(buf)
+            total, comps, gm = float(buf[0]), buf[1:7], buf[7:].astype(np.float64)
+            history.append(total)
+            if callback is not None:
+                callback(p.copy(), total, comps, it)
+            g_scaled = gm * p0                      # d loss / d (p / p0)
+            scaled = np.clip(np.asarray(opt.apply(scaled, g_scaled), dtype=np.float64), 0.0, 10.0)
+    p = scaled * p0
+    params.nu0, params.nu_m, params.dRi, params.Ric, params.Pr = (float(v) for v in p)
+    return p, history
 
 
 def predict(𝒱, model: NDEModel, which_net: int, *, scaled: bool = False):

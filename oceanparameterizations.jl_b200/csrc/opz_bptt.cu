@@ -70,6 +70,7 @@ struct Args {
   double* loss_part;     // [B][6]
   float* loss_out;       // [7]
   float* grad;           // [3P]
+  float* gphys;          // [5] or null: gradient w.r.t. the modified Pacanowski-Philander parameters (nu0, nu_m, dRi, Ric, Pr)
   const Cursor* cur;
   int64_t B, B_total;
   int64_t rows_cap;      // Rcap * B
@@ -352,6 +353,31 @@ __global__ void __launch_bounds__(1024) final_fwd_kernel(const __grid_constant__
 }
 
 // ---- physics VJP + transpose of the last Dense layer: one CTA per column --------------------------------
+// ---- cotangents of the five modified Pacanowski-Philander parameters from one interior face ----------------------
+// (diffusivity_parameter_optimisation.jl:1-33: p = (nu0, nu_m, dRi, Ric, Pr) of nu = nu0 + nu_m (1 - tanh((Ri - Ric)/dRi))/2,
+//  nu_T = nu / Pr).  nubar = cotangent of nu from all three fluxes, FbT = cotangent of the total T flux, th = tanh(...).
+__device__ __forceinline__ void mpp_param_cotangents(const DevParams& P, float nubar, float FbT, float th, float Ri, float nu,
+                                                     float gT, bool keep, bool ok, float (&gp)[5]) {
+  const float sech2 = 1.0f - th * th;
+  gp[0] += nubar;
+  gp[1] += nubar * ((1.0f - th) / 2.0f);
+  if (ok) {
+    gp[2] += nubar * (P.nu_m / 2.0f * sech2 * (Ri - P.Ric) / (P.dRi * P.dRi));
+    gp[3] += nubar * (P.nu_m / (2.0f * P.dRi) * sech2);
+  }
+  if (keep) gp[4] += FbT * (P.c_T * nu * gT / (P.Pr * P.Pr));
+}
+// sum gp over the warp; lane 0 adds the result to out[5]
+__device__ __forceinline__ void mpp_param_flush(float (&gp)[5], float* out) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    float v = gp[i];
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+    if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(out + i, v);
+  }
+}
+
 __global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__ Args a, int stage, int dn) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -371,6 +397,7 @@ __global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__
     kb[i] = a.KBAR[col * S3 + i];
   }
   __syncthreads();
+  float gp[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   if (tid <= nz) {
     const int f = tid;
     float gbu = 0.0f, gbv = 0.0f, gbT = 0.0f;
@@ -405,10 +432,12 @@ __global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__
         gbu = -P.c_u * nu * Fbu + (ok ? Ribar * (-Ri * 2.0f * P.s_u * ea / S2) : 0.0f);
         gbv = -P.c_v * nu * Fbv + (ok ? Ribar * (-Ri * 2.0f * P.s_v * eb / S2) : 0.0f);
         gbT = -P.c_T * nuT * FbT + (ok ? Ribar * dRi_dgT : 0.0f);
+        if (a.gphys) mpp_param_cotangents(P, nubar, FbT, th, Ri, nu, gT, keep, ok, gp);
       }
     }
     gb[f] = gbu; gb[(nz + 1) + f] = gbv; gb[2 * (nz + 1) + f] = gbT;
   }
+  if (a.gphys && tid < ((nz + 1 + 31) / 32) * 32) mpp_param_flush(gp, a.gphys);   // whole warps that hold faces
   __syncthreads();
   if (tid < S3) {
     const int v = tid / nz, c = tid - v * nz;
@@ -744,6 +773,7 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   }
   OPZ_CUDA(cudaMemsetAsync(c.grad_out, 0, sizeof(float) * P3, st));
   OPZ_CUDA(cudaMemsetAsync(c.loss_out, 0, sizeof(float) * 7, st));
+  if (c.gphys_out) OPZ_CUDA(cudaMemsetAsync(c.gphys_out, 0, sizeof(float) * 5, st));
   if (B == 0) return OPZ_OK;
 
   const int stages = c.r.scheme == OPZ_RK4 ? 4 : (c.r.scheme == OPZ_RK2 ? 2 : 1);
@@ -816,6 +846,7 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   a.wT_net = (int64_t)wT_net;
   a.loss_out = c.loss_out;
   a.grad = c.grad_out;
+  a.gphys = c.gphys_out;
   a.B = B; a.B_total = c.B_total; a.rows_cap = rows_cap;
   a.S3 = S3; a.nout = nout; a.L = L;
   a.scheme = c.r.scheme; a.stages = stages;

@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
   prefetch(a.n_steps * stages - 1);
   __syncthreads();
 
+  float gp[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // this thread's share of d loss / d (nu0, nu_m, dRi, Ric, Pr) (rank 0 only: the physics is replicated)
   int rs_parity = 0;
   for (int n = a.n_steps - 1; n >= 0; --n) {
     for (int s = stages - 1; s >= 0; --s) {
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
             gbu = -P.c_u * nu * Fbu + (ok ? Ribar * (-Ri * 2.0f * P.s_u * ea / S2) : 0.0f);
             gbv = -P.c_v * nu * Fbv + (ok ? Ribar * (-Ri * 2.0f * P.s_v * eb / S2) : 0.0f);
             gbT = -P.c_T * nuT * FbT + (ok ? Ribar * dRi_dgT : 0.0f);
+            if (a.gphys && rank == 0 && col_ok) mpp_param_cotangents(P, nubar, FbT, th, Ri, nu, gT, keep, ok, gp);   // not the padding slots
           }
         }
         Fs[f * CP + c] = gbu; Fs[((nz + 1) + f) * CP + c] = gbv; Fs[(2 * (nz + 1) + f) * CP + c] = gbT;
@@ -534,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
       OPZ_PH(16);
     }
   }
+  if (a.gphys && rank == 0) mpp_param_flush(gp, a.gphys);   // every thread of the CTA takes part (zeros outside the face threads)
   if (timing)
     for (int i = 0; i < 24; ++i) g_phase_cycles[i] = (unsigned long long)ph[i];
   cluster_sync_all();  // no CTA exits while a peer may still address its shared memory

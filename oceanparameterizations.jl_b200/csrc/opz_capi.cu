@@ -336,10 +336,10 @@ int opz_rollout_forward(opz_ctx* ctx, const opz_model* m, const opz_params* p, c
 }
 
 // ---- loss + gradient ----------------------------------------------------------------------------
-int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
-                      int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps,
-                      int save_every, const float* target, const float* loss_w, int precision,
-                      float* loss_out, float* grad_out) {
+static int loss_grad_dev_impl(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                              int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps,
+                              int save_every, const float* target, const float* loss_w, int precision,
+                              float* loss_out, float* grad_out, float* gphys_out) {
   int rc = check_common(ctx, m, p);
   if (rc) return rc;
   if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
@@ -358,12 +358,32 @@ int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, con
   c.B_total = B_total;
   c.loss_out = loss_out;
   c.grad_out = grad_out;
+  c.gphys_out = gphys_out;
   return fp32_loss_grad(ctx, m, c);
 }
 
-int opz_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
-                  int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps, int save_every,
-                  const float* target, const float* loss_w, int precision, float* loss_out, float* grad_out) {
+int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                      int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps,
+                      int save_every, const float* target, const float* loss_w, int precision,
+                      float* loss_out, float* grad_out) {
+  return loss_grad_dev_impl(ctx, m, p, x0, bc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, target, loss_w, precision,
+                            loss_out, grad_out, nullptr);
+}
+
+int opz_loss_grad_mpp_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                          int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps,
+                          int save_every, const float* target, const float* loss_w, int precision,
+                          float* loss_out, float* grad_out, float* grad_mpp_out) {
+  if (!grad_mpp_out) { set_error("null buffer"); return OPZ_EINVAL; }
+  if (p && !(p->flags & OPZ_FLAG_MPP)) { set_error("opz_loss_grad_mpp: OPZ_FLAG_MPP is off, the parameters have no effect"); return OPZ_EINVAL; }
+  return loss_grad_dev_impl(ctx, m, p, x0, bc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, target, loss_w, precision,
+                            loss_out, grad_out, grad_mpp_out);
+}
+
+static int loss_grad_host_impl(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                               int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps, int save_every,
+                               const float* target, const float* loss_w, int precision, float* loss_out, float* grad_out,
+                               float* grad_mpp_out) {
   int rc = check_common(ctx, m, p);
   if (rc) return rc;
   if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
@@ -377,20 +397,39 @@ int opz_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, const f
   if ((rc = ensure_scratch(ctx, 0, sizeof(float) * (B ? B : 1) * S, (void**)&dx))) return rc;
   if ((rc = ensure_scratch(ctx, 1, sizeof(float) * (B ? B : 1) * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
   if ((rc = ensure_scratch(ctx, 2, sizeof(float) * (B ? B : 1) * n_save * S, (void**)&dtgt))) return rc;
-  if ((rc = ensure_scratch(ctx, 3, sizeof(float) * (P3 + 8), (void**)&dgrad))) return rc;
+  if ((rc = ensure_scratch(ctx, 3, sizeof(float) * (P3 + 16), (void**)&dgrad))) return rc;
   dloss = dgrad + P3;
+  float* dmpp = grad_mpp_out ? dgrad + P3 + 8 : nullptr;
   if (B > 0) {
     OPZ_CUDA(cudaMemcpyAsync(dx, x0, sizeof(float) * B * S, cudaMemcpyHostToDevice, ctx->stream));
     OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
     OPZ_CUDA(cudaMemcpyAsync(dtgt, target, sizeof(float) * B * n_save * S, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if ((rc = opz_loss_grad_dev(ctx, m, p, dx, dbc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, dtgt, loss_w,
-                              precision, dloss, dgrad)))
+  if (grad_mpp_out && !(p->flags & OPZ_FLAG_MPP)) { set_error("opz_loss_grad_mpp: OPZ_FLAG_MPP is off, the parameters have no effect"); return OPZ_EINVAL; }
+  if ((rc = loss_grad_dev_impl(ctx, m, p, dx, dbc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, dtgt, loss_w,
+                               precision, dloss, dgrad, dmpp)))
     return rc;
   OPZ_CUDA(cudaMemcpyAsync(grad_out, dgrad, sizeof(float) * P3, cudaMemcpyDeviceToHost, ctx->stream));
   OPZ_CUDA(cudaMemcpyAsync(loss_out, dloss, sizeof(float) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+  if (grad_mpp_out) OPZ_CUDA(cudaMemcpyAsync(grad_mpp_out, dmpp, sizeof(float) * 5, cudaMemcpyDeviceToHost, ctx->stream));
   OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return OPZ_OK;
+}
+
+int opz_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                  int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps, int save_every,
+                  const float* target, const float* loss_w, int precision, float* loss_out, float* grad_out) {
+  return loss_grad_host_impl(ctx, m, p, x0, bc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, target, loss_w, precision,
+                             loss_out, grad_out, nullptr);
+}
+
+int opz_loss_grad_mpp(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
+                      int64_t B, int64_t B_total, int scheme, float dt_nd, float t0, int n_steps, int save_every,
+                      const float* target, const float* loss_w, int precision, float* loss_out, float* grad_out,
+                      float* grad_mpp_out) {
+  if (!grad_mpp_out) { set_error("null buffer"); return OPZ_EINVAL; }
+  return loss_grad_host_impl(ctx, m, p, x0, bc, B, B_total, scheme, dt_nd, t0, n_steps, save_every, target, loss_w, precision,
+                             loss_out, grad_out, grad_mpp_out);
 }
 
 // ---- batched MLP --------------------------------------------------------------------------------

@@ -78,6 +78,7 @@ struct LossGradCall {
   int64_t B_total;
   float* loss_out;        // device [7]
   float* grad_out;        // device [3P]
+  float* gphys_out;       // device [5] or null: d loss / d (nu0, nu_m, dRi, Ric, Pr)
 };
 int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c);
 void bptt_release(opz_ctx* ctx);

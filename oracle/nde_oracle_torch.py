@@ -60,8 +60,10 @@ def _box3(a):
     return torch.cat([lo, mid, hi], dim=-1)
 
 
-def rhs(x, bc, t, w, sizes, act, p: O.Params):
-    """d x / d(t/tau); x[B,3Nz], bc[B,8], w flat [3P] (torch tensors of one dtype)."""
+def rhs(x, bc, t, w, sizes, act, p: O.Params, phys=None):
+    """d x / d(t/tau); x[B,3Nz], bc[B,8], w flat [3P] (torch tensors of one dtype).  `phys` (optional tensor [5]) overrides
+    (nu0, nu_m, dRi, Ric, Pr) of `p` so that autograd can differentiate with respect to them
+    (diffusivity_parameter_optimisation.jl:2)."""
     Nz = p.Nz
     P = O.n_params(sizes)
     dt = x.dtype
@@ -76,8 +78,8 @@ def rhs(x, bc, t, w, sizes, act, p: O.Params):
     bot = [bc[:, 2 * i] - sub * off[i] for i in range(3)]
     top = [bc[:, 2 * i + 1] - sub * off[i] for i in range(3)]
     if p.flags & O.FLAG_DIURNAL:
-        phys = bc[:, 6] * math.sin(2.0 * math.pi / p.diurnal_period * (float(t) * p.tau)) / (p.alpha * p.g)
-        tp = (phys - p.mu[5]) / p.sigma[5]
+        wT_phys = bc[:, 6] * math.sin(2.0 * math.pi / p.diurnal_period * (float(t) * p.tau)) / (p.alpha * p.g)
+        tp = (wT_phys - p.mu[5]) / p.sigma[5]
         if p.flags & O.FLAG_DIURNAL_MINUS_SCALE0:
             tp = tp - off[2]
         top[2] = tp
@@ -92,12 +94,13 @@ def rhs(x, bc, t, w, sizes, act, p: O.Params):
             Ri = _box3(Ri)[:, 1:-1]
         else:
             Ri = (p.H * p.g * p.alpha * s_T * (g[2] + e)) / ((s_u * (g[0] + e)) ** 2 + (s_v * (g[1] + e)) ** 2)
-        nu = p.nu0 + p.nu_m * ((1.0 - torch.tanh((Ri - p.Ric) / p.dRi)) / 2.0)
+        nu0, nu_m, dRi, Ric, Pr = (p.nu0, p.nu_m, p.dRi, p.Ric, p.Pr) if phys is None else (phys[0], phys[1], phys[2], phys[3], phys[4])
+        nu = nu0 + nu_m * ((1.0 - torch.tanh((Ri - Ric) / dRi)) / 2.0)
         if p.flags & O.FLAG_CA:
             sel = g[0] if (p.flags & O.FLAG_CA_SELECT_DUDZ) else g[2]
-            nuT = torch.where(sel > 0, nu / p.Pr, torch.full_like(nu, p.kappa))
+            nuT = torch.where(sel > 0, nu / Pr, torch.full_like(nu, p.kappa))
         else:
-            nuT = nu / p.Pr
+            nuT = nu / Pr
         F[0] = F[0] - s_u / s_uw / p.H * nu * g[0]
         F[1] = F[1] - s_v / s_vw / p.H * nu * g[1]
         F[2] = F[2] - s_T / s_wT / p.H * nuT * g[2]
@@ -111,25 +114,25 @@ def rhs(x, bc, t, w, sizes, act, p: O.Params):
     return torch.cat([du, dv, dT], dim=1).to(dt)
 
 
-def step(x, bc, t, h, w, sizes, act, p, scheme):
+def step(x, bc, t, h, w, sizes, act, p, scheme, phys=None):
     if scheme == O.SCHEME_EULER:
-        return x + h * rhs(x, bc, t, w, sizes, act, p)
+        return x + h * rhs(x, bc, t, w, sizes, act, p, phys)
     if scheme == O.SCHEME_RK2:
-        k1 = rhs(x, bc, t, w, sizes, act, p)
-        k2 = rhs(x + h * k1, bc, t + h, w, sizes, act, p)
+        k1 = rhs(x, bc, t, w, sizes, act, p, phys)
+        k2 = rhs(x + h * k1, bc, t + h, w, sizes, act, p, phys)
         return x + (h * 0.5) * (k1 + k2)
-    k1 = rhs(x, bc, t, w, sizes, act, p)
-    k2 = rhs(x + (h * 0.5) * k1, bc, t + h * 0.5, w, sizes, act, p)
-    k3 = rhs(x + (h * 0.5) * k2, bc, t + h * 0.5, w, sizes, act, p)
-    k4 = rhs(x + h * k3, bc, t + h, w, sizes, act, p)
+    k1 = rhs(x, bc, t, w, sizes, act, p, phys)
+    k2 = rhs(x + (h * 0.5) * k1, bc, t + h * 0.5, w, sizes, act, p, phys)
+    k3 = rhs(x + (h * 0.5) * k2, bc, t + h * 0.5, w, sizes, act, p, phys)
+    k4 = rhs(x + h * k3, bc, t + h, w, sizes, act, p, phys)
     return x + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
 
 
-def rollout(x0, bc, w, sizes, act, p, scheme, dt_nd, n_steps, save_every, t0=0.0):
+def rollout(x0, bc, w, sizes, act, p, scheme, dt_nd, n_steps, save_every, t0=0.0, phys=None):
     x = x0
     out = [x]
     for n in range(n_steps):
-        x = step(x, bc, t0 + n * dt_nd, dt_nd, w, sizes, act, p, scheme)
+        x = step(x, bc, t0 + n * dt_nd, dt_nd, w, sizes, act, p, scheme, phys)
         if (n + 1) % save_every == 0:
             out.append(x)
     return torch.stack(out, dim=1)  # [B, n_save, 3Nz]
@@ -153,15 +156,20 @@ def loss_components(sol, target, Nz, B_total=None):
 
 
 def loss_and_grad(x0, bc, model: O.Model, p: O.Params, scheme, dt_nd, n_steps, save_every, target, loss_w, t0=0.0,
-                  dtype=torch.float64, B_total=None):
-    """Returns (total, components[6] (weighted), grad[3P]) as numpy float64."""
+                  dtype=torch.float64, B_total=None, with_mpp=False):
+    """Returns (total, components[6] (weighted), grad[3P]) as numpy float64; with_mpp=True appends
+    d total / d (nu0, nu_m, dRi, Ric, Pr) [5]."""
     w = torch.tensor(np.asarray(model.flat(), dtype=np.float64), dtype=dtype, requires_grad=True)
     x0t = torch.tensor(np.asarray(x0, dtype=np.float64), dtype=dtype)
     bct = torch.tensor(np.asarray(bc, dtype=np.float64), dtype=dtype)
     tg = torch.tensor(np.asarray(target, dtype=np.float64), dtype=dtype)
-    sol = rollout(x0t, bct, w, tuple(model.sizes), model.act, p, scheme, dt_nd, n_steps, save_every, t0)
+    phys = torch.tensor([p.nu0, p.nu_m, p.dRi, p.Ric, p.Pr], dtype=dtype, requires_grad=True) if with_mpp else None
+    sol = rollout(x0t, bct, w, tuple(model.sizes), model.act, p, scheme, dt_nd, n_steps, save_every, t0, phys)
     comps = loss_components(sol, tg, p.Nz, B_total)
     weighted = [float(loss_w[i]) * comps[i] for i in range(6)]
     total = sum(weighted)
     total.backward()
-    return float(total.detach()), np.array([float(c.detach()) for c in weighted]), w.grad.detach().numpy().astype(np.float64)
+    out = (float(total.detach()), np.array([float(c.detach()) for c in weighted]), w.grad.detach().numpy().astype(np.float64))
+    if with_mpp:
+        out = out + (phys.grad.detach().numpy().astype(np.float64),)
+    return out

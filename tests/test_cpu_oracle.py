@@ -237,3 +237,29 @@ def test_bptt_fixture_pins_the_adjoint(golden_dir):
     t32, _, g32 = A.loss_and_grad(*args, dtype=np.float32)
     assert t32 == pytest.approx(float(g["total"]), rel=1e-4)
     assert np.linalg.norm(g32 - g["grad"]) <= 1e-3 * np.linalg.norm(g["grad"])
+
+
+def test_twin_mpp_parameter_gradient_matches_finite_differences():
+    """The autograd twin's d loss / d (nu0, nu_m, dRi, Ric, Pr) (ground truth of opz_loss_grad_mpp; the reference's DE of
+    diffusivity_parameter_optimisation.jl:1-33 is the NN-free special case) against central differences in float64."""
+    from oracle import nde_oracle_torch as OT
+    import dataclasses
+    flags = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    p = O.Params(flags=flags)
+    B = 4
+    x0, bc = O.synthetic_columns(B, p, dtype=np.float64)
+    x0 = x0 + 0.05 * np.random.default_rng(3).normal(size=x0.shape)
+    sizes = (96, 20, 31)
+    m = O.make_model(sizes, O.ACT_TANH, seed=1, out_scale=0.1, dtype=np.float64)
+    dt, n_steps, se = 30.0 / p.tau, 8, 4
+    p_true = dataclasses.replace(p, nu_m=0.07, Pr=1.4)
+    tgt = O.rollout(x0, bc, m, p_true, O.SCHEME_RK4, dt, n_steps, se)
+    lw = [1, 1, 1, 1e-3, 1e-3, 1e-3]
+    L0, _, _, gm = OT.loss_and_grad(x0, bc, m, p, O.SCHEME_RK4, dt, n_steps, se, tgt, lw, with_mpp=True)
+    names = ("nu0", "nu_m", "dRi", "Ric", "Pr")
+    for i, nme in enumerate(names):
+        v = getattr(p, nme)
+        h = 1e-5 * v
+        Lp = OT.loss_and_grad(x0, bc, m, dataclasses.replace(p, **{nme: v + h}), O.SCHEME_RK4, dt, n_steps, se, tgt, lw)[0]
+        Lm = OT.loss_and_grad(x0, bc, m, dataclasses.replace(p, **{nme: v - h}), O.SCHEME_RK4, dt, n_steps, se, tgt, lw)[0]
+        assert (Lp - Lm) / (2 * h) == pytest.approx(gm[i], rel=2e-5), nme

@@ -200,3 +200,79 @@ def test_loss_grad_rejects_unsupported(opz, oracle, ctx):
     with pytest.raises(opz.OpzError):  # n_steps not a multiple of save_every
         opz.loss_grad(model2, product_params(opz, p), x0, bc, np.zeros((2, 2, 96), np.float32), lw, 2, 1e-4, 3, 2)
     model2.close()
+
+
+def _rel_each(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("name,flags,sizes,act,zero_nn,B", [
+    ("reference_DE_nn_free", "train", (96, 50, 20, 31), 3, True, 18),     # diffusivity_parameter_optimisation.jl:1-33
+    ("construct_nn_with_ca", "infer", (96, 400, 400, 31), 1, False, 18),
+    ("small_mish_training_flags", "train", (96, 50, 20, 31), 3, False, 7),
+])
+def test_loss_grad_mpp_matches_autograd_twin(opz, oracle, ctx, monkeypatch, name, flags, sizes, act, zero_nn, B):
+    """d loss / d (nu0, nu_m, dRi, Ric, Pr) from the same backward sweep, against float64 autograd through
+    the twin; on the cluster path and on the layer-parallel graph path."""
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    fl = {"train": O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0, "infer": O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0}[flags]
+    n_steps, save_every, scheme = 12, 4, 2
+    p, x0, bc, m, m_true, dt = _case(O, fl, sizes, act, B, n_steps, save_every, seed=5)
+    if zero_nn:
+        m = O.Model(m.sizes, m.act, np.zeros_like(m.w_uw), np.zeros_like(m.w_vw), np.zeros_like(m.w_wT))
+    # targets from a solve with DIFFERENT diffusivity parameters (what the reference's optimisation descends towards)
+    p_true = O.Params(flags=fl, tau=p.tau, nu0=2e-4, nu_m=0.06, dRi=0.15, Ric=0.3, Pr=1.3)
+    target = O.rollout(x0, bc, m if zero_nn else m_true, p_true, scheme, dt, n_steps, save_every)
+    lw = np.array([1.0, 0.7, 1.3, 5e-3, 4e-3, 6e-3], dtype=np.float32)
+    t_ref, c_ref, g_ref, gm_ref = OT.loss_and_grad(x0, bc, m, p, scheme, dt, n_steps, save_every, target, lw, B_total=B + 1,
+                                                   with_mpp=True)
+    assert np.all(np.abs(gm_ref) > 0)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    for path, env in (("cluster", {}), ("graph", {"OPZ_BPTT_NO_CLUSTER": "1"})):
+        monkeypatch.delenv("OPZ_BPTT_NO_CLUSTER", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        total, comps, grad, gm = opz.loss_grad_mpp(model, pp, x0, bc, target, lw, scheme, dt, n_steps, save_every, B_total=B + 1)
+        rel = _rel_each(gm, gm_ref)
+        print(f"{name} [{path}]: d loss/d(nu0, nu_m, dRi, Ric, Pr) = {gm}, rel err {rel}")
+        assert total == pytest.approx(t_ref, rel=TOL_LOSS)
+        if not zero_nn:
+            assert _rel_l2(grad, g_ref) < TOL_GRAD
+        # the tolerance of the north star (1e-3 relative, L2) on the gradient in the reference's scaled form p / p_initial
+        # (diffusivity_parameter_optimisation.jl:44-48), plus a per-component bound (FP32 cancellation in the smallest one)
+        pv = np.array([p.nu0, p.nu_m, p.dRi, p.Ric, p.Pr])
+        assert _rel_l2(gm * pv, gm_ref * pv) < TOL_GRAD, (path, rel)
+        assert np.all(rel < 3e-3), (path, rel)
+        # the plain entry point returns the same loss and NN gradient
+        t2, c2, g2 = opz.loss_grad(model, pp, x0, bc, target, lw, scheme, dt, n_steps, save_every, B_total=B + 1)
+        assert t2 == pytest.approx(total, rel=1e-6) and _rel_l2(g2, grad) < 1e-5 or zero_nn
+    # needs the mPP flag
+    p_off = O.Params(flags=O.FLAG_BC_MINUS_SCALE0, tau=p.tau)
+    with pytest.raises(opz.OpzError) as e:
+        opz.loss_grad_mpp(model, product_params(opz, p_off), x0, bc, target, lw, scheme, dt, n_steps, save_every)
+    assert e.value.code == opz.OPZ_EINVAL
+    model.close()
+
+
+def test_optimise_modified_pacanowski_philander_descends(opz, oracle, ctx):
+    """Host loop of optimise_modified_pacanowski_philander (diffusivity_parameter_optimisation.jl:36-231) on the NN-free
+    model: ADAM on the scaled parameters with libopz gradients lowers the loss towards the generating parameters."""
+    O = oracle
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    n_steps, save_every = 24, 6
+    p, x0, bc, m, _, dt = _case(O, fl, (96, 50, 20, 31), 3, 18, n_steps, save_every, seed=3)
+    m = O.Model(m.sizes, m.act, np.zeros_like(m.w_uw), np.zeros_like(m.w_vw), np.zeros_like(m.w_wT))
+    p_true = O.Params(flags=fl, tau=p.tau, nu0=p.nu0, nu_m=p.nu_m * 1.5, dRi=p.dRi, Ric=p.Ric, Pr=p.Pr * 1.2)
+    target = O.rollout(x0, bc, m, p_true, 2, dt, n_steps, save_every)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    lw = np.array([1, 1, 1, 0, 0, 0], dtype=np.float32)
+    pfin, hist = opz.optimise_modified_pacanowski_philander(model, pp, x0, bc, target, lw, opz.RK4(dt), n_steps, save_every,
+                                                            [opz.ADAM(2e-2)], maxiters=40)
+    print("mPP optimisation: loss", hist[0], "->", hist[-1], "parameters", pfin)
+    assert hist[-1] < 0.5 * hist[0]
+    assert np.all(pfin >= 0) and pp.nu_m == pytest.approx(float(pfin[1]), rel=1e-6)
+    model.close()
