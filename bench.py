@@ -157,6 +157,7 @@ BPTT_CASES = 18
 BPTT_DT_SECONDS = 60.0
 BPTT_SAVE_EVERY = 90   # 5400 s between training snapshots = `1:9:1153` of the 600 s data (train_NDE_args.jl:195)
 BPTT_STEPS = 11520     # 8 days
+BPTT_CPU_STEPS = 540   # sample of the CPU baseline of the gradient step
 
 
 def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
@@ -214,6 +215,22 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
     loss = float(buf[P3].item())
     gnorm = float(buf[:P3].norm().item())
     model.close()
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # CPU baseline of the gradient step (Julia is absent; the reference differentiates with Zygote through an adjoint ODE
+        # solve): the float32 PyTorch-autograd twin of the same discrete adjoint on the host cores, on a bounded sample
+        # (all 18 cases, the first BPTT_CPU_STEPS time steps), scaled to the full rollout
+        import time as _time
+        import torch as _torch
+        from oracle import nde_oracle_torch as OT
+        ns = BPTT_CPU_STEPS
+        tg = target[:, :ns // BPTT_SAVE_EVERY + 1]
+        t0 = _time.perf_counter()
+        OT.loss_and_grad(x0, bc, m, p, O.SCHEME_RK4, dt, ns, BPTT_SAVE_EVERY, tg, lw, dtype=_torch.float32)
+        el = _time.perf_counter() - t0
+        cpu = {"value": 1.0 / (el * BPTT_STEPS / ns), "unit": "grad-steps/s", "cores": int(_torch.get_num_threads()), "kind": "port",
+               "sample": f"PyTorch-autograd twin (oracle/nde_oracle_torch.py, float32), 18 cases x first {ns} of {BPTT_STEPS} RK4 steps, "
+                         f"{el:.1f} s, scaled linearly"}
     # algorithmic FLOPs: forward sweep + backward (dX and dW) = 3 x stages x F_rhs per column-step
     flops = 3.0 * STAGES * FLOP_PER_RHS * BPTT_CASES * BPTT_STEPS
     return {"metric": "BPTT grad-steps/sec", "value": 1e3 / ms, "unit": "grad-steps/s", "ms_per_grad_step": ms,
@@ -223,6 +240,7 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
             "finite": bool(np.isfinite(loss) and np.isfinite(gnorm)),
             "achieved_tflops": flops / (ms * 1e-3) / 1e12,
             "collective": "none (1 GPU)" if dist is None else f"NCCL all-reduce(sum) of {P3 + 8} fp32 per step",
+            "cpu_baseline": cpu,
             "note": "latency-bound: 18 columns x 46080 sequential right-hand sides; see DESIGN.md section 6"}
 
 

@@ -701,7 +701,8 @@ bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, bptt::c
   lay.xn = take(S3 * CP); lay.xs = take(S3 * CP); lay.kacc = take(S3 * CP); lay.lam = take(S3 * CP);
   lay.kbar = take(S3 * CP); lay.xsum = take(S3 * CP); lay.xphys = take(S3 * CP);
   lay.Fs = take(3 * (nz + 1) * CP);
-  lay.recv_big_size = cl::kCS * 3 * ulmax * CP;
+  lay.recv_big_size = (cl::kCS * 3 * ulmax * CP + 3) / 4 * 4;
+  off = (off + 3) / 4 * 4;   // 16-byte aligned: the reduce-scatter stores CP columns per transaction
   lay.recv_big = take(lay.recv_big_size * (L >= 4 ? 2 : 1));
   lay.SL = (std::max(NO3, S3) * CP + cl::kCS - 1) / cl::kCS;
   lay.recv_small = take(cl::kCS * lay.SL);

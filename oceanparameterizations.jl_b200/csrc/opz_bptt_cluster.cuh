@@ -61,6 +61,17 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void st_remote(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// CP consecutive floats in one transaction (the address is CP * 4 bytes aligned: every slot index is a multiple of CP)
+template <int CP>
+__device__ __forceinline__ void st_remote_cols(uint32_t addr, const float (&v)[CP]) {
+  if constexpr (CP == 2) asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v[0]), "f"(v[1]) : "memory");
+  else if constexpr (CP == 4)
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+  else {
+#pragma unroll
+    for (int c = 0; c < CP; ++c) st_remote(addr + 4u * c, v[c]);
+  }
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
@@ -471,8 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           for (int u = 0; u < UL; ++u) fma_cols<CP>(acc, Wp[u], dp + u * CP);
           const int owner = k / ULp, kl = k - owner * ULp;
           const uint32_t off = rbase[owner] + 4u * (uint32_t)((int)(rb - sm) + ((rank * 3 + net) * ULp + kl) * CP);
-#pragma unroll
-          for (int c = 0; c < CP; ++c) st_remote(off + 4u * c, acc[c]);
+          st_remote_cols<CP>(off, acc);
         }
         OPZ_PH(11);
         cluster_arrive();
