@@ -179,6 +179,21 @@ int opz_loss_grad_mpp_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p,
                           const float* target_dev, const float* loss_w_host, int precision,
                           float* loss_out_dev, float* grad_out_dev, float* grad_mpp_out_dev);
 
+/* ---- diagnostics of a finished rollout --------------------------------------------
+ * Replaces the per-snapshot loops of NDE_profile (wind_mixing/src/training_postprocessing.jl:250-632):
+ *   fluxes     [B][n_save][3][nz+1]  total scaled fluxes uw, vw, wT = predict_flux at every saved state (:408-419), the
+ *                                    diurnal top flux re-evaluated at each snapshot's time t0 + k*dt_save;
+ *   fluxes_mpp [B][n_save][3][nz+1]  the same with the NN outputs taken as zero: boundary + diffusive part (:432-450);
+ *                                    fluxes - fluxes_mpp on the interior faces is the NN contribution;
+ *   ri         [B][n_save][nz+1]     local_richardson of D^f applied to the state (:428-431): no epsilon, so the two
+ *                                    boundary faces (zero gradients) are NaN, as in the reference;
+ *   loss_t     [B][n_save][3]        loss_per_tstep (loss.jl:44-46): mean squared error of u, v, T against `target`.
+ * sol / target: [B][n_save][3nz] scaled states (the output of opz_rollout_forward); every output pointer may be NULL. */
+int opz_profile_diagnostics(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* sol,
+                            const float* bc, int64_t B, int n_save, float t0, float dt_save,
+                            const float* target, float* fluxes, float* fluxes_mpp, float* ri,
+                            float* loss_t);
+
 /* ---- batched MLP forward ------------------------------------------------------------------------
  * Replaces predict(V, model; scaled=true) (src/predict.jl:12-34): one launch over Nt input
  * columns.  which_net: 0 uw, 1 vw, 2 wT.  x[Nt][3nz] -> y[Nt][nz-1]. */

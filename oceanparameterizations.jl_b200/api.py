@@ -468,6 +468,32 @@ def loss_grad_dev(model: NDEModel, params: L.OpzParams, x0_ptr: int, bc_ptr: int
                                     C.c_void_p(grad_out_ptr)))
 
 
+def profile_diagnostics(model: NDEModel, params: L.OpzParams, sol, bc, *, t0: float = 0.0, dt_save: float = 0.0, target=None,
+                        with_mpp_part: bool = True):
+    """Diagnostics of a finished rollout (NDE_profile, training_postprocessing.jl:396-450): returns a dict with
+    `fluxes` [B, n_save, 3, Nz+1] (predict_flux at every snapshot), `fluxes_mpp` (NN outputs zeroed), `Ri`
+    [B, n_save, Nz+1] and, with a target, `loss_per_tstep` [B, n_save, 3] (loss.jl:44-46)."""
+    sol = _f32(sol)
+    B, n_save, S = sol.shape
+    nz = S // 3
+    bc = _f32(bc, (B, L.BC_STRIDE))
+    fl = np.empty((B, n_save, 3, nz + 1), dtype=np.float32)
+    fm = np.empty_like(fl) if with_mpp_part else None
+    ri = np.empty((B, n_save, nz + 1), dtype=np.float32)
+    tg = _f32(target, sol.shape) if target is not None else None
+    lt = np.empty((B, n_save, 3), dtype=np.float32) if tg is not None else None
+    null = C.POINTER(C.c_float)()
+    L.check(L.lib.opz_profile_diagnostics(model.ctx._h, model._h, C.byref(params), _fptr(sol), _fptr(bc), B, n_save, float(t0),
+                                          float(dt_save), _fptr(tg) if tg is not None else null, _fptr(fl),
+                                          _fptr(fm) if fm is not None else null, _fptr(ri), _fptr(lt) if lt is not None else null))
+    out = {"fluxes": fl, "Ri": ri}
+    if fm is not None:
+        out["fluxes_mpp"] = fm
+    if lt is not None:
+        out["loss_per_tstep"] = lt
+    return out
+
+
 def mlp_forward(model: NDEModel, which_net: int, x, precision: int = L.PREC_FP32) -> np.ndarray:
     x = _f32(x)
     y = np.empty((x.shape[0], model.Nz - 1), dtype=np.float32)

@@ -432,6 +432,40 @@ int opz_loss_grad_mpp(opz_ctx* ctx, const opz_model* m, const opz_params* p, con
                              loss_out, grad_out, grad_mpp_out);
 }
 
+// ---- post-rollout diagnostics -------------------------------------------------------------------
+int opz_profile_diagnostics(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* sol, const float* bc,
+                            int64_t B, int n_save, float t0, float dt_save, const float* target, float* fluxes,
+                            float* fluxes_mpp, float* ri, float* loss_t) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if (!sol || !bc || B < 0 || n_save < 1) { set_error("null buffer, negative B or n_save < 1"); return OPZ_EINVAL; }
+  if (loss_t && !target) { set_error("loss_t needs a target"); return OPZ_EINVAL; }
+  if (B == 0) return OPZ_OK;
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t nz = (size_t)m->nz, S = 3 * nz, nf = 3 * (nz + 1), rows = (size_t)B * n_save;
+  float *dsol, *dbc, *dtgt = nullptr, *dout;
+  if ((rc = ensure_scratch(ctx, 0, sizeof(float) * rows * S, (void**)&dsol))) return rc;
+  if ((rc = ensure_scratch(ctx, 1, sizeof(float) * B * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
+  if (target && (rc = ensure_scratch(ctx, 2, sizeof(float) * rows * S, (void**)&dtgt))) return rc;
+  if ((rc = ensure_scratch(ctx, 3, sizeof(float) * rows * (2 * nf + (nz + 1) + 3), (void**)&dout))) return rc;
+  float* dfl = dout;
+  float* dfm = dfl + rows * nf;
+  float* dri = dfm + rows * nf;
+  float* dlt = dri + rows * (nz + 1);
+  OPZ_CUDA(cudaMemcpyAsync(dsol, sol, sizeof(float) * rows * S, cudaMemcpyHostToDevice, ctx->stream));
+  OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * B * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+  if (target) OPZ_CUDA(cudaMemcpyAsync(dtgt, target, sizeof(float) * rows * S, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fp32_diagnostics(ctx, m, make_dev_params(*p), dsol, dbc, B, n_save, t0, dt_save, dtgt, fluxes ? dfl : nullptr,
+                             fluxes_mpp ? dfm : nullptr, ri ? dri : nullptr, loss_t ? dlt : nullptr)))
+    return rc;
+  if (fluxes) OPZ_CUDA(cudaMemcpyAsync(fluxes, dfl, sizeof(float) * rows * nf, cudaMemcpyDeviceToHost, ctx->stream));
+  if (fluxes_mpp) OPZ_CUDA(cudaMemcpyAsync(fluxes_mpp, dfm, sizeof(float) * rows * nf, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ri) OPZ_CUDA(cudaMemcpyAsync(ri, dri, sizeof(float) * rows * (nz + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (loss_t) OPZ_CUDA(cudaMemcpyAsync(loss_t, dlt, sizeof(float) * rows * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
 // ---- batched MLP --------------------------------------------------------------------------------
 int opz_mlp_forward(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt, int precision,
                     float* y) {

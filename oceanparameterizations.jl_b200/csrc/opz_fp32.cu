@@ -9,6 +9,7 @@
 //
 // Replaces solve_NDE_mutating (wind_mixing/src/training_postprocessing.jl:55-159) with a
 // fixed-step Euler / Heun / RK4 scheme (north_star replaces OrdinaryDiffEq's ROCK4).
+#include <algorithm>
 #include "opz_internal.h"
 #include "opz_simt.cuh"
 
@@ -28,6 +29,9 @@ struct Fp32Args {
   int n_steps, save_every, n_save;
   int max_hidden;
   int which_net;
+  // profile diagnostics (opz_profile_diagnostics): rows are [column][snapshot]
+  int rows_per_bc;   // > 1: forcing row = row / rows_per_bc, time = t0 + (row % rows_per_bc) * dt
+  int skip_nn;       // 1: the NN outputs are taken as zero (the boundary + diffusive part of the fluxes)
 };
 
 template <int M>
@@ -147,23 +151,58 @@ __global__ void __launch_bounds__(kThreads, 1) rhs_fp32_kernel(const __grid_cons
       s.xs[0][i * M + m] = col < a.B ? a.x0[col * S + i] : 0.0f;
     }
     __syncthreads();
-    run_three_nets<M>(a, s, s.xs[0]);
+    if (!a.skip_nn) run_three_nets<M>(a, s, s.xs[0]);
     const int64_t col = col0 + tid;
     if (tid < M && col < a.B) {
+      const int rpb = a.rows_per_bc > 1 ? a.rows_per_bc : 1;
+      const int64_t brow = col / rpb;
+      const float t = a.t0 + (float)(col - brow * rpb) * a.dt;
+      const bool skip = a.skip_nn;
       float bc[OPZ_BC_STRIDE];
 #pragma unroll
-      for (int q = 0; q < OPZ_BC_STRIDE; ++q) bc[q] = a.bc[col * OPZ_BC_STRIDE + q];
+      for (int q = 0; q < OPZ_BC_STRIDE; ++q) bc[q] = a.bc[brow * OPZ_BC_STRIDE + q];
       auto X = [&](int i) { return s.xs[0][i * M + tid]; };
-      auto Y = [&](int net, int j) { return s.Y[(net * nz + j) * M + tid]; };
-      auto K = [&](int i, float k) { a.out[col * S + i] = k; };
+      auto Y = [&](int net, int j) { return skip ? 0.0f : s.Y[(net * nz + j) * M + tid]; };
+      auto K = [&](int i, float k) { if (a.out) a.out[col * S + i] = k; };
       if (a.aux) {
         auto FL = [&](int v, int f, float val) { a.aux[(col * 3 + v) * (nz + 1) + f] = val; };
-        column_rhs(a.P, bc, a.t0, X, Y, K, FL);
+        column_rhs(a.P, bc, t, X, Y, K, FL);
       } else {
-        column_rhs(a.P, bc, a.t0, X, Y, K, NoFlux());
+        column_rhs(a.P, bc, t, X, Y, K, NoFlux());
       }
     }
     __syncthreads();
+  }
+}
+
+// Ri on the Nz + 1 faces of every row (local_richardson of D^f x: zero gradients on the two boundary faces, no epsilon;
+// training_postprocessing.jl:428-431) and the per-snapshot mean squared error of u, v, T against a target (loss_per_tstep,
+// loss.jl:44-46): one thread per (row, face) / (row, variable).
+__global__ void diag_kernel(DevParams P, const float* __restrict__ x, const float* __restrict__ target, int64_t rows,
+                            float* __restrict__ ri, float* __restrict__ loss_t) {
+  const int nz = P.nz, S = 3 * nz;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ri && i < rows * (nz + 1)) {
+    const int64_t r = i / (nz + 1);
+    const int f = (int)(i - r * (nz + 1));
+    const float* xr = x + r * S;
+    float gu = 0.0f, gv = 0.0f, gT = 0.0f;
+    if (f > 0 && f < nz) {
+      gu = (xr[f] - xr[f - 1]) * P.nzf;
+      gv = (xr[nz + f] - xr[nz + f - 1]) * P.nzf;
+      gT = (xr[2 * nz + f] - xr[2 * nz + f - 1]) * P.nzf;
+    }
+    const float sa = P.s_u * gu, sb = P.s_v * gv;
+    ri[i] = (P.cBz * gT) / (sa * sa + sb * sb);   // IEEE: 0/0 on the boundary faces is NaN, exactly like the reference
+  }
+  if (loss_t && target && i < rows * 3) {
+    const int64_t r = i / 3;
+    const int v = (int)(i - r * 3);
+    const float* a = x + r * S + v * nz;
+    const float* b = target + r * S + v * nz;
+    float acc = 0.0f;
+    for (int k = 0; k < nz; ++k) { const float d = a[k] - b[k]; acc = fmaf(d, d, acc); }
+    loss_t[i] = acc / (float)nz;
   }
 }
 
@@ -238,6 +277,31 @@ int fp32_rhs(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* 
   a.x0 = x; a.bc = bc; a.out = dxdt; a.aux = fluxes; a.B = B; a.t0 = t;
   if (M == 64) return launch(ctx, rhs_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (B + 63) / 64, a);
   return launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (B + 31) / 32, a);
+}
+
+int fp32_diagnostics(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* sol, const float* bc, int64_t B, int n_save,
+                     float t0, float dt_save, const float* target, float* fluxes, float* fluxes_mpp, float* ri, float* loss_t) {
+  const int M = pick_tile(ctx, m);
+  if (!M) { set_error("fp32 path: hidden width / nz too large for shared memory"); return OPZ_EUNSUP; }
+  const int64_t rows = B * n_save;
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? fluxes : fluxes_mpp;
+    if (!dst) continue;
+    Fp32Args a = base_args(m, P);
+    a.x0 = sol; a.bc = bc; a.out = nullptr; a.aux = dst; a.B = rows; a.t0 = t0; a.dt = dt_save;
+    a.rows_per_bc = n_save; a.skip_nn = pass;
+    int rc;
+    if (M == 64) rc = launch(ctx, rhs_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (rows + 63) / 64, a);
+    else rc = launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (rows + 31) / 32, a);
+    if (rc) return rc;
+  }
+  if (ri || (loss_t && target)) {
+    const int64_t n = std::max<int64_t>(rows * (m->nz + 1), rows * 3);
+    diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(P, sol, target, rows, ri, loss_t);
+    OPZ_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  return OPZ_OK;
 }
 
 int fp32_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt, float* y) {

@@ -69,6 +69,8 @@ struct RolloutCall {
 int fp32_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c);
 int fp32_rhs(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* x, const float* bc, float t,
              int64_t B, float* dxdt, float* fluxes);
+int fp32_diagnostics(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* sol, const float* bc, int64_t B, int n_save,
+                     float t0, float dt_save, const float* target, float* fluxes, float* fluxes_mpp, float* ri, float* loss_t);
 int fp32_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, int64_t Nt, float* y);
 
 struct LossGradCall {

@@ -239,3 +239,43 @@ def test_host_buffer_rollout_slab_pipeline_is_bit_exact(opz, oracle):
             ref = ref[:, -1:]   # final state only
         assert oracle.profile_error(host[pick], ref, 32) < (1e-3 if prec == opz.PREC_FP16 else 1e-4)
     model.close()
+
+
+@pytest.mark.parametrize("diurnal", [False, True])
+def test_profile_diagnostics_match_oracle(opz, oracle, diurnal):
+    """SURVEY §8 f-2 (NDE_profile, training_postprocessing.jl:396-450): fluxes at every saved snapshot, their NN-free part,
+    Ri profiles and loss_per_tstep, computed on the device from a finished rollout, against the oracle's predict_flux."""
+    O = oracle
+    flags = O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0 | ((O.FLAG_DIURNAL | O.FLAG_DIURNAL_MINUS_SCALE0) if diurnal else 0)
+    p = O.Params(flags=flags)
+    B, n_steps, save_every = 37, 40, 8
+    x0, bc = O.synthetic_columns(B, p, diurnal=diurnal)
+    x0 = (x0 + 0.02 * np.random.default_rng(2).normal(size=x0.shape)).astype(np.float32)
+    m = O.make_model((96, 50, 20, 31), O.ACT_MISH, seed=3, out_scale=0.1, bias_scale=0.1)
+    mz = O.Model(m.sizes, m.act, np.zeros_like(m.w_uw), np.zeros_like(m.w_vw), np.zeros_like(m.w_wT))
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    sol = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, n_steps, save_every)
+    n_save = sol.shape[1]
+    target = O.rollout(x0, bc, O.make_model((96, 50, 20, 31), O.ACT_MISH, seed=9, out_scale=0.1), p, O.SCHEME_RK4, dt, n_steps, save_every)
+    d = opz.profile_diagnostics(model, pp, sol, bc, t0=0.0, dt_save=save_every * dt, target=target)
+    assert d["fluxes"].shape == (B, n_save, 3, 33) and d["Ri"].shape == (B, n_save, 33)
+    for k in range(n_save):
+        t = k * save_every * dt
+        uw, vw, wT, diag = O.predict_flux(sol[:, k], bc, t, m, p, return_diag=True)
+        ref = np.stack([uw, vw, wT], axis=1)
+        assert rel_err(d["fluxes"][:, k], ref) < 2e-5, k
+        uz, vz, wz = O.predict_flux(sol[:, k], bc, t, mz, p)
+        assert rel_err(d["fluxes_mpp"][:, k], np.stack([uz, vz, wz], axis=1)) < 2e-5, k
+        ri_ref = diag["Ri"]
+        assert np.isnan(d["Ri"][:, k, 0]).all() and np.isnan(d["Ri"][:, k, 32]).all()          # boundary faces: 0/0
+        fin = np.isfinite(ri_ref[:, 1:32])
+        assert np.allclose(d["Ri"][:, k, 1:32][fin], ri_ref[:, 1:32][fin], rtol=2e-4, atol=1e-6)
+        lt = np.stack([((sol[:, k, v * 32:(v + 1) * 32] - target[:, k, v * 32:(v + 1) * 32]) ** 2).mean(axis=1) for v in range(3)], axis=1)
+        assert np.allclose(d["loss_per_tstep"][:, k], lt, rtol=1e-5, atol=1e-12)
+    # the NN contribution is what the nets put out on the interior faces
+    nn = d["fluxes"][:, :, :, 1:32] - d["fluxes_mpp"][:, :, :, 1:32]
+    y = np.stack([O.mlp_forward(sol[:, 0], w, m.sizes, m.act) for w in (m.w_uw, m.w_vw, m.w_wT)], axis=1)
+    assert rel_err(nn[:, 0], y) < 1e-4
+    model.close()
