@@ -179,6 +179,18 @@ int opz_loss_grad_mpp_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p,
                           const float* target_dev, const float* loss_w_host, int precision,
                           float* loss_out_dev, float* grad_out_dev, float* grad_mpp_out_dev);
 
+/* ---- supervised flux pre-training of one net ---------------------------------------
+ * Replaces NN_loss / total_loss + Zygote inside train_NN (wind_mixing/src/NN_training.jl:207-249) with predict_uw /
+ * predict_vw / predict_wT (:25-169) as the model: for sample i (one snapshot: profile x[i][3nz], boundary fluxes bc[i][8])
+ *     loss_i = mse(F_pred, F_data) + gradient_scaling * mse(D^c F_data, D^c F_pred)          (:224-228)
+ * where F_pred is the total flux of net `which_net` (0 uw, 1 vw, 2 wT) on the nz+1 faces — the fluxes output of opz_rhs —
+ * and flux_target[N][nz+1] the scaled data.  loss_out[3] = mean over the N samples of (total, first term, second term);
+ * grad_out[P] = gradient of the total w.r.t. that net's weights (Flux.destructure order).  The reference takes one
+ * optimiser step per sample (Flux.train!); pass N = 1 for that, or a batch for the mean gradient. */
+int opz_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, int which_net,
+                       const float* x, const float* bc, const float* flux_target, int64_t N,
+                       float gradient_scaling, float* loss_out, float* grad_out);
+
 /* ---- diagnostics of a finished rollout --------------------------------------------
  * Replaces the per-snapshot loops of NDE_profile (wind_mixing/src/training_postprocessing.jl:250-632):
  *   fluxes     [B][n_save][3][nz+1]  total scaled fluxes uw, vw, wT = predict_flux at every saved state (:408-419), the

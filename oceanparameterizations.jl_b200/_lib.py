@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "opz_version", "opz_last_error", "opz_ctx_create", "opz_ctx_destroy", "opz_ctx_set_stream",
     "opz_ctx_synchronize", "opz_ctx_launch_count", "opz_model_create", "opz_model_set_weights",
     "opz_model_get_weights", "opz_model_set_weights_dev", "opz_model_n_params", "opz_model_destroy",
-    "opz_rhs", "opz_rollout_forward", "opz_rollout_forward_dev", "opz_loss_grad", "opz_loss_grad_dev", "opz_loss_grad_mpp", "opz_loss_grad_mpp_dev", "opz_profile_diagnostics",
+    "opz_rhs", "opz_rollout_forward", "opz_rollout_forward_dev", "opz_loss_grad", "opz_loss_grad_dev", "opz_loss_grad_mpp", "opz_loss_grad_mpp_dev", "opz_profile_diagnostics", "opz_flux_loss_grad",
     "opz_mlp_forward",
 )
 
@@ -90,6 +90,7 @@ def _load() -> C.CDLL:
     lib.opz_loss_grad_mpp.argtypes = lg + [fp]
     lib.opz_loss_grad_mpp_dev.argtypes = lg + [fp]
     lib.opz_profile_diagnostics.argtypes = [vp, vp, P, fp, fp, i64, i32, f32, f32, fp, fp, fp, fp, fp]
+    lib.opz_flux_loss_grad.argtypes = [vp, vp, P, i32, fp, fp, fp, i64, f32, fp, fp]
     lib.opz_mlp_forward.argtypes = [vp, vp, i32, fp, i64, i32, fp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # raises AttributeError if the symbol is not exported

@@ -468,6 +468,20 @@ def loss_grad_dev(model: NDEModel, params: L.OpzParams, x0_ptr: int, bc_ptr: int
                                     C.c_void_p(grad_out_ptr)))
 
 
+def flux_loss_grad(model: NDEModel, params: L.OpzParams, which_net: int, x, bc, flux_target, gradient_scaling: float = 1e-4):
+    """Supervised pre-training loss of ONE net and its gradient (train_NN / NN_loss, NN_training.jl:207-249): x [N, 3Nz],
+    bc [N, 8], flux_target [N, Nz+1] (scaled) -> (total, flux mse, flux-gradient mse, grad[P]); means over the N samples."""
+    x = _f32(x)
+    N = x.shape[0]
+    bc = _f32(bc, (N, L.BC_STRIDE))
+    ft = _f32(flux_target, (N, x.shape[1] // 3 + 1))
+    loss_out = np.zeros(3, dtype=np.float32)
+    grad = np.zeros(model.P, dtype=np.float32)
+    L.check(L.lib.opz_flux_loss_grad(model.ctx._h, model._h, C.byref(params), int(which_net), _fptr(x), _fptr(bc), _fptr(ft), N,
+                                     float(gradient_scaling), _fptr(loss_out), _fptr(grad)))
+    return float(loss_out[0]), float(loss_out[1]), float(loss_out[2]), grad
+
+
 def profile_diagnostics(model: NDEModel, params: L.OpzParams, sol, bc, *, t0: float = 0.0, dt_save: float = 0.0, target=None,
                         with_mpp_part: bool = True):
     """Diagnostics of a finished rollout (NDE_profile, training_postprocessing.jl:396-450): returns a dict with

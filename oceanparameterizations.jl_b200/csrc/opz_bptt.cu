@@ -1096,4 +1096,150 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   return OPZ_OK;
 }
 
+// ================================================================================================================
+// Supervised flux pre-training of ONE net: train_NN / NN_loss (wind_mixing/src/NN_training.jl:207-249),
+// predict_uw / predict_vw / predict_wT (:25-169).  Per sample (one profile snapshot):
+//     loss = mse(F_pred, F_data) + gradient_scaling * mse(D^c F_data, D^c F_pred)
+// with F_pred the total flux of that net on the Nz + 1 faces (what opz_rhs reports) — only its interior entries depend on
+// the weights, through the NN output alone, so the gradient is a plain MLP back-propagation of d loss / d y.
+// The batch value is the mean over the samples (total_loss, :230-232).
+namespace bptt {
+
+// one CTA per sample: forward of the chosen net with records, loss terms, cotangent chain down to dz_0
+__global__ void __launch_bounds__(256) flux_sample_kernel(NetDesc nd, DevParams P, const float* __restrict__ w, int which,
+                                                          const float* __restrict__ x, const float* __restrict__ Fpred,
+                                                          const float* __restrict__ Ftgt, float gscale, int64_t N, int max_w,
+                                                          float* __restrict__ H, float* __restrict__ G, int64_t rec_stride,
+                                                          float* __restrict__ DY, double* __restrict__ loss_part) {
+  extern __shared__ float sm[];
+  const int nz = P.nz, S3 = 3 * nz, nout = nz - 1, L = nd.n_layers;
+  float* hA = sm;               // [max_w]
+  float* hB = hA + max_w;       // [max_w]
+  float* res = hB + max_w;      // [nz + 1]
+  float* dcs = res + nz + 1;    // [nz]
+  const int tid = threadIdx.x;
+  const int64_t r = blockIdx.x;
+  for (int i = tid; i < S3; i += blockDim.x) hA[i] = x[r * S3 + i];
+  __syncthreads();
+  // ---- forward with records: H_l = act(z_l), G_l = act'(z_l) for the hidden layers ----
+  float* in = hA;
+  float* out = hB;
+  int64_t roff = 0;
+  for (int l = 0; l < L - 1; ++l) {
+    const int K = nd.sizes[l], Nl = nd.sizes[l + 1];
+    const float* W = w + nd.w_off[l];
+    const float* b = w + nd.b_off[l];
+    for (int n = tid; n < Nl; n += blockDim.x) {
+      float z = b[n];
+      for (int k = 0; k < K; ++k) z = fmaf(in[k], W[(size_t)k * Nl + n], z);
+      const float hv = act_dyn(z, nd.act);
+      out[n] = hv;
+      H[roff + r * Nl + n] = hv;
+      G[roff + r * Nl + n] = act_grad_dyn(z, nd.act);
+    }
+    __syncthreads();
+    float* t = in; in = out; out = t;
+    roff += rec_stride * Nl;
+  }
+  // ---- loss terms and d loss / d y ----
+  const float* Fp = Fpred + (r * 3 + which) * (nz + 1);
+  const float* Ft = Ftgt + r * (nz + 1);
+  for (int f = tid; f <= nz; f += blockDim.x) res[f] = Fp[f] - Ft[f];
+  __syncthreads();
+  for (int c = tid; c < nz; c += blockDim.x) dcs[c] = (res[c + 1] - res[c]) * P.nzf;   // D^c of the residual
+  __syncthreads();
+  if (tid == 0) {
+    double l1 = 0.0, l2 = 0.0;
+    for (int f = 0; f <= nz; ++f) l1 += (double)res[f] * res[f];
+    for (int c = 0; c < nz; ++c) l2 += (double)dcs[c] * dcs[c];
+    loss_part[2 * r] = l1 / (nz + 1);
+    loss_part[2 * r + 1] = l2 / nz;
+  }
+  float* dz = out;   // free buffer
+  const float invN = 1.0f / (float)N;
+  for (int j = tid; j < nout; j += blockDim.x) {
+    const int f = j + 1;   // interior face
+    const float g = 2.0f * res[f] / (float)(nz + 1) + gscale * (2.0f / (float)nz) * P.nzf * (dcs[f - 1] - dcs[f]);
+    const float v = g * invN;
+    dz[j] = v;
+    DY[r * nout + j] = v;
+  }
+  __syncthreads();
+  // ---- back through the layers: dz_{l-1} = (W_l dz_l) * act'(z_{l-1}), in place over the act' records ----
+  float* cur = dz;
+  float* nxt = in;    // the last hidden activation is already recorded
+  for (int l = L - 1; l >= 1; --l) {
+    const int K = nd.sizes[l], Nl = nd.sizes[l + 1];
+    const float* W = w + nd.w_off[l];
+    roff -= rec_stride * K;
+    for (int k = tid; k < K; k += blockDim.x) {
+      const float* Wk = W + (size_t)k * Nl;
+      float sacc = 0.0f;
+      for (int n = 0; n < Nl; ++n) sacc = fmaf(Wk[n], cur[n], sacc);
+      const int64_t o = roff + r * K + k;
+      const float v = sacc * G[o];
+      G[o] = v;
+      nxt[k] = v;
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+}
+
+}  // namespace bptt
+
+int fp32_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const DevParams& P, int which_net, const float* x, const float* bc,
+                        const float* flux_target, int64_t N, float gradient_scaling, float* loss_out_host, float* grad_out) {
+  using namespace bptt;
+  const NetDesc& nd = m->nd;
+  const int L = nd.n_layers, nz = m->nz, S3 = 3 * nz, nout = nz - 1;
+  cudaStream_t st = ctx->stream;
+  OPZ_CUDA(cudaMemsetAsync(grad_out, 0, sizeof(float) * (size_t)nd.P, st));
+  if (N == 0) { loss_out_host[0] = loss_out_host[1] = loss_out_host[2] = 0.0f; return OPZ_OK; }
+  // records: per hidden layer [N][n_l] of H and G, then DY [N][nout], fluxes [N][3][nz+1], loss partials [N][2] doubles
+  size_t hid = 0;
+  int max_w = std::max(S3, nout);
+  for (int l = 0; l < L - 1; ++l) { hid += (size_t)nd.sizes[l + 1]; max_w = std::max(max_w, nd.sizes[l + 1]); }
+  const size_t floats = (size_t)N * (2 * hid + nout + 3 * (size_t)(nz + 1) + 4) + S3 * (size_t)N + 64;
+  float* base;
+  int rc;
+  if ((rc = ensure_scratch(ctx, 5, sizeof(float) * floats, (void**)&base))) return rc;
+  double* lp = reinterpret_cast<double*>(base);   // [N][2] (the scratch block is 256-byte aligned)
+  float* H = base + 4 * (size_t)N;
+  float* G = H + (size_t)N * hid;
+  float* DY = G + (size_t)N * hid;
+  float* Fp = DY + (size_t)N * nout;
+  float* dk = Fp + (size_t)N * 3 * (nz + 1);       // tendencies of the RHS launch (unused)
+  if ((rc = fp32_rhs(ctx, m, P, x, bc, 0.0f, N, dk, Fp))) return rc;
+  const size_t smem = sizeof(float) * (2 * (size_t)max_w + 2 * (size_t)nz + 1);
+  flux_sample_kernel<<<(unsigned)N, 256, smem, st>>>(nd, P, m->w_dev + (size_t)which_net * nd.P, which_net, x, Fp, flux_target,
+                                                      gradient_scaling, N, max_w, H, G, N, DY, lp);
+  OPZ_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  // dW_l = A_l^T D_l over the N samples: A_0 = x, A_l = H_{l-1}; D_l = dz_l (G records), D_{L-1} = DY
+  size_t aoff = 0, doff = 0;
+  for (int l = 0; l < L; ++l) {
+    const int K = nd.sizes[l], Nl = nd.sizes[l + 1];
+    const float* A = l == 0 ? x : H + aoff;
+    const float* D = l == L - 1 ? DY : G + doff;
+    const int split = (int)std::min<int64_t>(std::max<int64_t>(N / 256, 1), 32);
+    dim3 grid((K + kTK - 1) / kTK, (Nl + kTN - 1) / kTN, split);
+    dw_kernel<<<grid, 256, 0, st>>>(A, 0, K, D, 0, Nl, K, Nl, N, split, grad_out + nd.w_off[l], grad_out + nd.b_off[l], 0);
+    OPZ_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    if (l >= 1) aoff += (size_t)N * K;
+    if (l < L - 1) doff += (size_t)N * Nl;
+  }
+  std::vector<double> hl(2 * (size_t)N);
+  OPZ_CUDA(cudaMemcpyAsync(hl.data(), lp, sizeof(double) * hl.size(), cudaMemcpyDeviceToHost, st));
+  OPZ_CUDA(cudaStreamSynchronize(st));
+  double l1 = 0.0, l2 = 0.0;
+  for (int64_t i = 0; i < N; ++i) { l1 += hl[2 * i]; l2 += hl[2 * i + 1]; }
+  l1 /= (double)N; l2 /= (double)N;
+  loss_out_host[0] = (float)(l1 + (double)gradient_scaling * l2);
+  loss_out_host[1] = (float)l1;
+  loss_out_host[2] = (float)l2;
+  return OPZ_OK;
+}
+
 }  // namespace opz

@@ -432,6 +432,33 @@ int opz_loss_grad_mpp(opz_ctx* ctx, const opz_model* m, const opz_params* p, con
                              loss_out, grad_out, grad_mpp_out);
 }
 
+// ---- supervised flux pre-training of one net --------------------------------------------------------
+int opz_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, int which_net, const float* x, const float* bc,
+                       const float* flux_target, int64_t N, float gradient_scaling, float* loss_out, float* grad_out) {
+  int rc = check_common(ctx, m, p);
+  if (rc) return rc;
+  if (which_net < 0 || which_net > 2) { set_error("which_net must be 0 (uw), 1 (vw) or 2 (wT)"); return OPZ_EINVAL; }
+  if (N < 0 || (N > 0 && (!x || !bc || !flux_target)) || !loss_out || !grad_out) { set_error("null buffer or negative N"); return OPZ_EINVAL; }
+  if (m->nd.n_layers < 2) { set_error("opz_flux_loss_grad: the nets need at least one hidden layer"); return OPZ_EUNSUP; }
+  if (p->flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) { set_error("opz_flux_loss_grad: smooth_NN / smooth_Ri are not differentiated yet"); return OPZ_EUNSUP; }
+  OPZ_CUDA(cudaSetDevice(ctx->device));
+  const size_t S = 3 * (size_t)m->nz, nf = (size_t)m->nz + 1, P1 = (size_t)m->nd.P;
+  float *dx, *dbc, *dt, *dg;
+  if ((rc = ensure_scratch(ctx, 0, sizeof(float) * (N ? N : 1) * S, (void**)&dx))) return rc;
+  if ((rc = ensure_scratch(ctx, 1, sizeof(float) * (N ? N : 1) * OPZ_BC_STRIDE, (void**)&dbc))) return rc;
+  if ((rc = ensure_scratch(ctx, 2, sizeof(float) * (N ? N : 1) * nf, (void**)&dt))) return rc;
+  if ((rc = ensure_scratch(ctx, 3, sizeof(float) * P1, (void**)&dg))) return rc;
+  if (N > 0) {
+    OPZ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * N * S, cudaMemcpyHostToDevice, ctx->stream));
+    OPZ_CUDA(cudaMemcpyAsync(dbc, bc, sizeof(float) * N * OPZ_BC_STRIDE, cudaMemcpyHostToDevice, ctx->stream));
+    OPZ_CUDA(cudaMemcpyAsync(dt, flux_target, sizeof(float) * N * nf, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((rc = fp32_flux_loss_grad(ctx, m, make_dev_params(*p), which_net, dx, dbc, dt, N, gradient_scaling, loss_out, dg))) return rc;
+  OPZ_CUDA(cudaMemcpyAsync(grad_out, dg, sizeof(float) * P1, cudaMemcpyDeviceToHost, ctx->stream));
+  OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPZ_OK;
+}
+
 // ---- post-rollout diagnostics -------------------------------------------------------------------
 int opz_profile_diagnostics(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* sol, const float* bc,
                             int64_t B, int n_save, float t0, float dt_save, const float* target, float* fluxes,

@@ -84,6 +84,9 @@ struct LossGradCall {
 };
 int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c);
 void bptt_release(opz_ctx* ctx);
+// supervised flux pre-training of one net (opz_bptt.cu): device x [N][3nz], bc [N][8], flux_target [N][nz+1]; grad_out device [P]
+int fp32_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const DevParams& P, int which_net, const float* x, const float* bc,
+                        const float* flux_target, int64_t N, float gradient_scaling, float* loss_out_host, float* grad_out);
 
 // tcgen05 tensor-core path (opz_tc.cu)
 int tc_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights

@@ -60,7 +60,7 @@ def _box3(a):
     return torch.cat([lo, mid, hi], dim=-1)
 
 
-def rhs(x, bc, t, w, sizes, act, p: O.Params, phys=None):
+def rhs(x, bc, t, w, sizes, act, p: O.Params, phys=None, return_fluxes=False):
     """d x / d(t/tau); x[B,3Nz], bc[B,8], w flat [3P] (torch tensors of one dtype).  `phys` (optional tensor [5]) overrides
     (nu0, nu_m, dRi, Ric, Pr) of `p` so that autograd can differentiate with respect to them
     (diffusivity_parameter_optimisation.jl:2)."""
@@ -105,6 +105,8 @@ def rhs(x, bc, t, w, sizes, act, p: O.Params, phys=None):
         F[1] = F[1] - s_v / s_vw / p.H * nu * g[1]
         F[2] = F[2] - s_T / s_wT / p.H * nuT * g[2]
     full = [torch.cat([bot[i].unsqueeze(1), F[i], top[i].unsqueeze(1)], dim=1) for i in range(3)]
+    if return_fluxes:
+        return full
     div = [(f[:, 1:] - f[:, :-1]) * float(Nz) for f in full]
     A = -p.tau / p.H
     ft = p.f * p.tau
@@ -173,3 +175,24 @@ def loss_and_grad(x0, bc, model: O.Model, p: O.Params, scheme, dt_nd, n_steps, s
     if with_mpp:
         out = out + (phys.grad.detach().numpy().astype(np.float64),)
     return out
+
+
+def flux_loss_and_grad(x, bc, model: O.Model, p: O.Params, which_net, flux_target, gradient_scaling, dtype=torch.float64):
+    """Supervised pre-training loss of one net (train_NN / NN_loss, NN_training.jl:207-249; predict_uw/vw/wT :25-169 = the
+    total flux of that net) and its gradient w.r.t. that net's weights: returns (total, mse_flux, mse_flux_gradient, grad[P]),
+    means over the samples."""
+    w = torch.tensor(np.asarray(model.flat(), dtype=np.float64), dtype=dtype, requires_grad=True)
+    xt = torch.tensor(np.asarray(x, dtype=np.float64), dtype=dtype)
+    bct = torch.tensor(np.asarray(bc, dtype=np.float64), dtype=dtype)
+    tg = torch.tensor(np.asarray(flux_target, dtype=np.float64), dtype=dtype)
+    F = rhs(xt, bct, 0.0, w, tuple(model.sizes), model.act, p, return_fluxes=True)[which_net]
+    Nz = p.Nz
+    l1 = ((F - tg) ** 2).mean(dim=1)
+    dF = (F[:, 1:] - F[:, :-1]) * float(Nz)
+    dT = (tg[:, 1:] - tg[:, :-1]) * float(Nz)
+    l2 = ((dT - dF) ** 2).mean(dim=1)
+    total = (l1 + gradient_scaling * l2).mean()
+    total.backward()
+    P = model.P
+    g = w.grad.detach().numpy().astype(np.float64)
+    return float(total.detach()), float(l1.mean().detach()), float(l2.mean().detach()), g[which_net * P:(which_net + 1) * P], g

@@ -276,3 +276,49 @@ def test_optimise_modified_pacanowski_philander_descends(opz, oracle, ctx):
     assert hist[-1] < 0.5 * hist[0]
     assert np.all(pfin >= 0) and pp.nu_m == pytest.approx(float(pfin[1]), rel=1e-6)
     model.close()
+
+
+@pytest.mark.parametrize("which,sizes,act,flags,N", [
+    (0, (96, 400, 400, 31), 1, "train", 300),
+    (2, (96, 50, 20, 31), 3, "train_nozw", 1),        # one sample: the reference's Flux.train! step
+    (1, (96, 64, 31), 4, "none", 77),
+])
+def test_flux_loss_grad_matches_autograd_twin(opz, oracle, ctx, which, sizes, act, flags, N):
+    """supervised flux pre-training loss of one net and its gradient (NN_training.jl:207-249) against
+    float64 autograd through the twin's flux."""
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    fl = {"train": O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0, "train_nozw": O.FLAG_MPP | O.FLAG_RI_EPS, "none": 0}[flags]
+    p = O.Params(flags=fl)
+    x0, bc = O.synthetic_columns(N, p)
+    rng = np.random.default_rng(4)
+    x = (x0 + 0.05 * rng.normal(size=x0.shape)).astype(np.float32)
+    m = O.make_model(sizes, act, seed=2, out_scale=0.1, bias_scale=0.1)
+    m_true = O.make_model(sizes, act, seed=12, out_scale=0.1)
+    target = np.ascontiguousarray(O.predict_flux(x, bc, 0.0, m_true, p)[which]).astype(np.float32)   # "data": another model's fluxes
+    gs = 1e-4 * 32.0    # the reference's gradient_scaling (:209) in our nondimensional z (D^c multiplies by Nz)
+    t_ref, l1_ref, l2_ref, g_ref, g_all = OT.flux_loss_and_grad(x, bc, m, p, which, target, gs)
+    others = np.delete(g_all.reshape(3, -1), which, axis=0)
+    assert np.all(others == 0)                         # the other two nets do not enter
+    model = product_model(opz, m)
+    total, l1, l2, grad = opz.flux_loss_grad(model, product_params(opz, p), which, x, bc, target, gs)
+    print(f"flux pre-training net {which} {sizes}: loss {total:.6e} (ref {t_ref:.6e}), grad rel err {_rel_l2(grad, g_ref):.2e}")
+    assert total == pytest.approx(t_ref, rel=TOL_LOSS) and l1 == pytest.approx(l1_ref, rel=TOL_LOSS) and l2 == pytest.approx(l2_ref, rel=TOL_LOSS)
+    assert np.isfinite(grad).all() and np.linalg.norm(g_ref) > 0
+    assert _rel_l2(grad, g_ref) < TOL_GRAD
+    # a descent step along -grad lowers the loss (backtracking on the step length)
+    w0 = model.get_weights()
+    P = model.P
+    lr, t_end = 1.0, np.inf
+    for _ in range(30):
+        w = w0.copy()
+        w[which * P:(which + 1) * P] -= lr * grad
+        model.set_weights(w)
+        t_end = opz.flux_loss_grad(model, product_params(opz, p), which, x, bc, target, gs)[0]
+        if t_end < total:
+            break
+        lr *= 0.5
+    assert t_end < total
+    with pytest.raises(opz.OpzError):
+        opz.flux_loss_grad(model, product_params(opz, p), 3, x, bc, target, gs)
+    model.close()
