@@ -137,7 +137,7 @@ int opz_model_create(opz_ctx* ctx, int nz, int n_sizes, const int* sizes, int ac
   *out = nullptr;
   const int L = n_sizes - 1;
   if (L < 1 || L > kMaxLayers) { set_error("1..6 Dense layers supported"); return OPZ_EINVAL; }
-  if (nz < 2 || nz > kMaxNz) { set_error("nz must be in [2, 64]"); return OPZ_EINVAL; }
+  if (nz < 2 || nz > kMaxNz) { set_error("nz must be in [2, 128]"); return OPZ_EINVAL; }
   if (sizes[0] != 3 * nz || sizes[L] != nz - 1) {
     set_error("the nets must map 3*nz inputs to nz-1 interior-face outputs");
     return OPZ_EINVAL;

@@ -15,7 +15,7 @@
 namespace opz {
 
 constexpr int kMaxLayers = 6;   // Dense layers per net
-constexpr int kMaxNz = 64;      // cells per column supported by the per-thread physics
+constexpr int kMaxNz = 128;     // cells per column supported by the per-thread physics (FP32 path; the tensor path is Nz = 32)
 
 // Host-precomputed FP32 constants.  Every product below is formed in FP32 in the same
 // left-to-right order as the oracle so that the two FP32 paths round alike.

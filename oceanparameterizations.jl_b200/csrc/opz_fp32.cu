@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fp32_kernel(const __grid_cons
 static int pick_tile(const opz_ctx* ctx, const opz_model* m) {
   if ((int)Smem<64>::bytes(m->nz, m->max_hidden) <= ctx->smem_optin) return 64;
   if ((int)Smem<32>::bytes(m->nz, m->max_hidden) <= ctx->smem_optin) return 32;
+  if ((int)Smem<16>::bytes(m->nz, m->max_hidden) <= ctx->smem_optin) return 16;   // Nz = 128 states (BASELINE configs[4]) with nets up to 256 wide
   return 0;
 }
 
@@ -266,7 +267,8 @@ int fp32_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c) {
   a.x0 = c.x0; a.bc = c.bc; a.out = c.out; a.B = c.B; a.scheme = c.scheme; a.dt = c.dt; a.t0 = c.t0;
   a.n_steps = c.n_steps; a.save_every = c.save_every; a.n_save = c.n_save;
   if (M == 64) return launch(ctx, rollout_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (c.B + 63) / 64, a);
-  return launch(ctx, rollout_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (c.B + 31) / 32, a);
+  if (M == 32) return launch(ctx, rollout_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (c.B + 31) / 32, a);
+  return launch(ctx, rollout_fp32_kernel<16>, Smem<16>::bytes(m->nz, m->max_hidden), (c.B + 15) / 16, a);
 }
 
 int fp32_rhs(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* x, const float* bc, float t,
@@ -276,7 +278,8 @@ int fp32_rhs(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* 
   Fp32Args a = base_args(m, P);
   a.x0 = x; a.bc = bc; a.out = dxdt; a.aux = fluxes; a.B = B; a.t0 = t;
   if (M == 64) return launch(ctx, rhs_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (B + 63) / 64, a);
-  return launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (B + 31) / 32, a);
+  if (M == 32) return launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (B + 31) / 32, a);
+  return launch(ctx, rhs_fp32_kernel<16>, Smem<16>::bytes(m->nz, m->max_hidden), (B + 15) / 16, a);
 }
 
 int fp32_diagnostics(opz_ctx* ctx, const opz_model* m, const DevParams& P, const float* sol, const float* bc, int64_t B, int n_save,
@@ -292,7 +295,8 @@ int fp32_diagnostics(opz_ctx* ctx, const opz_model* m, const DevParams& P, const
     a.rows_per_bc = n_save; a.skip_nn = pass;
     int rc;
     if (M == 64) rc = launch(ctx, rhs_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (rows + 63) / 64, a);
-    else rc = launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (rows + 31) / 32, a);
+    else if (M == 32) rc = launch(ctx, rhs_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (rows + 31) / 32, a);
+    else rc = launch(ctx, rhs_fp32_kernel<16>, Smem<16>::bytes(m->nz, m->max_hidden), (rows + 15) / 16, a);
     if (rc) return rc;
   }
   if (ri || (loss_t && target)) {
@@ -312,7 +316,8 @@ int fp32_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, in
   Fp32Args a = base_args(m, P);
   a.x0 = x; a.out = y; a.B = Nt; a.which_net = which_net;
   if (M == 64) return launch(ctx, mlp_fp32_kernel<64>, Smem<64>::bytes(m->nz, m->max_hidden), (Nt + 63) / 64, a);
-  return launch(ctx, mlp_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (Nt + 31) / 32, a);
+  if (M == 32) return launch(ctx, mlp_fp32_kernel<32>, Smem<32>::bytes(m->nz, m->max_hidden), (Nt + 31) / 32, a);
+  return launch(ctx, mlp_fp32_kernel<16>, Smem<16>::bytes(m->nz, m->max_hidden), (Nt + 15) / 16, a);
 }
 
 }  // namespace opz

@@ -279,3 +279,37 @@ def test_profile_diagnostics_match_oracle(opz, oracle, diurnal):
     y = np.stack([O.mlp_forward(sol[:, 0], w, m.sizes, m.act) for w in (m.w_uw, m.w_vw, m.w_wT)], axis=1)
     assert rel_err(nn[:, 0], y) < 1e-4
     model.close()
+
+
+def test_nz128_diurnal_fp32_matches_oracle(opz, oracle):
+    """BASELINE configs[4] on the FP32 path: Nz = 128 columns (state 384, 127 interior faces) with a widened MLP
+    (384-256-256-127 x3) and diurnal surface forcing; parity with the oracle at the FP32 tolerance (1e-4), the single
+    right-hand side, the fluxes and the batched MLP included.  (The tensor-core path is built for Nz = 32 and declines.)"""
+    O = oracle
+    p = O.Params(Nz=128, flags=O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0 | O.FLAG_DIURNAL | O.FLAG_DIURNAL_MINUS_SCALE0)
+    B = 37
+    x0, bc = O.synthetic_columns(B, p, diurnal=True)
+    x0 = (x0 + 0.01 * np.random.default_rng(6).normal(size=x0.shape)).astype(np.float32)
+    sizes = (384, 256, 256, 127)
+    m = O.make_model(sizes, O.ACT_RELU, seed=0, out_scale=0.1, bias_scale=0.05)
+    model = product_model(opz, m, Nz=128)
+    pp = product_params(opz, p)
+    assert model.P == O.n_params(sizes)
+    dt = (30.0 / 16.0) / p.tau        # dz is 4x finer: the explicit diffusion limit shrinks 16x
+    n_steps, save_every = 48, 12
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, n_steps, save_every, t0=0.1)
+    ref = O.rollout(x0, bc, m, p, O.SCHEME_RK4, dt, n_steps, save_every, t0=0.1)
+    assert out.shape == (B, 5, 384) and np.isfinite(out).all()
+    err = O.profile_error(out, ref, 128)
+    print(f"Nz=128 diurnal FP32 rollout: max relative profile error {err:.2e}")
+    assert err < 1e-4
+    k, fl = opz.rhs(model, pp, x0, bc, 0.3, with_fluxes=True)
+    assert rel_err(k, O.rhs(x0, bc, 0.3, m, p)) < 2e-5
+    uw, vw, wT = O.predict_flux(x0, bc, 0.3, m, p)
+    assert fl.shape == (B, 3, 129) and rel_err(fl, np.stack([uw, vw, wT], axis=1)) < 2e-5
+    y = opz.mlp_forward(model, 2, x0)
+    assert rel_err(y, O.mlp_forward(x0, m.w_wT, sizes, m.act)) < 2e-5
+    with pytest.raises(opz.OpzError) as e:
+        opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 4, 2, precision=opz.PREC_FP16)
+    assert e.value.code == opz.OPZ_EUNSUP
+    model.close()
