@@ -381,6 +381,10 @@ def main():
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = flop_per_launch / (avg_kernel_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one `ncu --set full` capture of this command with the
+    # default workload (profiles/r01_tc2_ncu_summary.txt: 448.4 MB + 364.7 MB; algorithmic 436.2 MB in + 402.7 MB out); the
+    # figure belongs to that shape only
+    traffic = 813111040 if (cols == (1 << 20) and args.window == 16 and prec_name == "fp16") else None
     line = {
         "metric": "NDE column-timesteps/sec at Nz=32", "value": value, "unit": "column-timesteps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
@@ -389,7 +393,7 @@ def main():
         "config": config_dict(args, cols),
         "clocks": clocks, "gpu_launches": int(launches), "finite": finite,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu)", "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
                      "kernel": ("rollout_fp32_kernel" if prec_name == "fp32" else "rollout_tc2_kernel (tcgen05 cta_group::2, " + prec_name + " operands, fp32 accumulate)"),
                      "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_kernel_ms,
                      "fp32_fma_peak_tflops_at_max_clock": 74.4},
