@@ -323,6 +323,10 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 const uint64_t bd0 = ptx::smem_desc(sbase, (rows / 2) * 16u, 128);  // this CTA holds rows / 2 rows: [k/8][rows/2][8]
                 const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
                 const uint32_t d = tmem + kColD0 + buf * kCW;
+                // Only the first chunk of a layer fed by HF paces itself on the H1 barriers.  The second chunk (possibly the
+                // other issuing warp's) is covered by its D-empty wait: chunk g - 2 is then the LAST first-layer chunk, whose
+                // drained arrival comes after its tcgen05.st and after all earlier drains — so D-empty must keep being signalled
+                // after the store, not right after the accumulator load.
                 const bool wait_h1 = (j > 0) && (c0 == 0);
                 const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
                 const uint32_t a0 = tmem + a_base;
