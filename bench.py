@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bptt", action="store_true", help="skip the BPTT grad-steps/s leg")
+    ap.add_argument("--no-small", action="store_true", help="skip the informational small-net leg")
     ap.add_argument("--bptt-steps", type=int, default=2, help="timed gradient steps of the BPTT leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -333,6 +334,42 @@ def main():
     final = bufs[(args.warmup + args.steps) & 1]
     finite = bool(torch.isfinite(final).all().item())
 
+    # ---- the reference's production net on the same ensemble (96-50-20-31 mish, train_NDE.jl:103): informational ----
+    small = None
+    if not args.no_small:
+        from oracle import nde_oracle as O2
+        ms_small = O2.make_model((96, 50, 20, 31), O2.ACT_MISH, seed=0, out_scale=0.1)
+        model_s = product_model(opz, ms_small, ctx=ctx)
+
+        def window_s(i, src, dst):
+            opz.rollout_forward_dev(model_s, pp, src.data_ptr(), bcd.data_ptr(), cols, opz.SCHEME_RK4, dt, args.window, 0,
+                                    dst.data_ptr(), t0=i * args.window * dt, precision=prec)
+        xs0 = torch.from_numpy(x0).cuda()
+        xs1 = torch.empty_like(xs0)
+        sb = [xs0, xs1]
+        for i in range(2):
+            window_s(i, sb[i & 1], sb[(i + 1) & 1])
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record(stream)
+        for i in range(2, 2 + args.steps):
+            window_s(i, sb[i & 1], sb[(i + 1) & 1])
+        es1.record(stream)
+        barrier()
+        sms = es0.elapsed_time(es1) / args.steps
+        if dist is not None:
+            tts = torch.tensor([sms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tts, op=dist.ReduceOp.MAX)
+            sms = float(tts[0])
+        fl_small = 2 * 3 * (96 * 50 + 50 * 20 + 20 * 31) + 1800
+        small = {"net": "96-50-20-31 mish x3 (train_NDE.jl:103)", "value": cols * world * args.window / (sms * 1e-3),
+                 "unit": "column-timesteps/s", "ms_per_step": sms, "precision": prec_name,
+                 "achieved_tflops": cols * args.window * STAGES * fl_small / (sms * 1e-3) / 1e12,
+                 "finite": bool(torch.isfinite(sb[(2 + args.steps) & 1]).all().item()),
+                 "note": "physics- and latency-bound (0.16 MFLOP per column-timestep): not the roofline kernel of this line"}
+        model_s.close()
+        del xs0, xs1
+
     # ---- end-to-end through the host-buffer C ABI ----
     e2e = None
     if not args.no_e2e:
@@ -403,6 +440,8 @@ def main():
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e_ms}
     if bptt:
         line["bptt"] = bptt
+    if small:
+        line["small_net"] = small
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as CO
         cores = CO.max_threads()

@@ -65,6 +65,7 @@ struct Plan {                     // host-side, cached on the model
   int hpad[2] = {0, 0};
   int act = 0;
   bool fp16 = false;
+  bool interleave = false;
   int n_stages = 0;
   uint32_t st_off[kMaxStages];    // ring offset of the stage (bytes)
   uint32_t st_bytes[kMaxStages];  // bytes PER CTA
@@ -87,6 +88,8 @@ struct Args {
   int n_steps, save_every, n_save;
   int L, n_stages;
   int n_mma_warps;   // 1 or 2 issuing warps in the leader CTA
+  int interleave;    // 1: layer-major schedule (all three nets' first layers, then their second layers), see build_plan
+  int nc1;           // accumulator chunks of the first hidden layer
   int hpad[2];
   float b3[96];   // output-layer biases [net][32] (the hidden-layer biases ride in the weight tape)
   uint32_t st_off[kMaxStages];
@@ -293,15 +296,21 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             ptx::tc_commit2(bars + B_H2EMPTY);
           };
           wait_phase<PROF>(bars, B_XFULL, rhs_ctr, wacc, W_X);
+          // net-major schedule (net 0: layers ..., net 1: ...) or, for narrow nets, layer-major (the three nets' first layers,
+          // then their second layers): there the three nets' HF images sit side by side and the right-hand side is three
+          // overlapping MMA -> drain -> MMA chains instead of six consecutive ones
 #pragma unroll 1
-          for (int net = 0; net < 3; ++net) {
-            const uint32_t h1_phase = 3u * rhs_ctr + (uint32_t)net;   // H1[h] completes once per net and right-hand side
-#pragma unroll 1
-            for (int j = 0; j < L - 1; ++j) {
+          for (int idx = 0; idx < 3 * (L - 1); ++idx) {
+            const int net = a.interleave ? idx % 3 : idx / (L - 1);
+            {
+              const int j = a.interleave ? idx / 3 : idx % (L - 1);
+              const uint32_t h1_phase = a.interleave ? rhs_ctr : 3u * rhs_ctr + (uint32_t)net;   // completions of an H1 barrier so far
+              const int h1_base = a.interleave ? net * a.nc1 : 0;
+              const uint32_t hf_base = kColHF + (a.interleave ? (uint32_t)(net * (a.hpad[0] / 2)) : 0u);
               const bool fused = (j == L - 2);
               const int kin = (j == 0) ? kS / 16 : a.hpad[j - 1] / 16;
               const int hp = a.hpad[j];
-              const uint32_t a_base = (j == 0) ? kColX : kColHF;
+              const uint32_t a_base = (j == 0) ? kColX : hf_base;
 #pragma unroll 1
               for (int c0 = 0; c0 < hp; c0 += kCW, ++s, ++gs) {
                 const uint32_t rows = (uint32_t)min(kCW, hp - c0);
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 // other issuing warp's) is covered by its D-empty wait: chunk g - 2 is then the LAST first-layer chunk, whose
                 // drained arrival comes after its tcgen05.st and after all earlier drains — so D-empty must keep being signalled
                 // after the store, not right after the accumulator load.
-                const bool wait_h1 = (j > 0) && (c0 == 0);
+                const bool wait_h1 = (j > 0) && (c0 == 0 || a.interleave);
                 const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
                 const uint32_t a0 = tmem + a_base;
                 const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25 || kin == 6);
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll 1
                   for (int grp = 0; grp < 3; ++grp) {
                     const int h0 = grp == 0 ? 0 : (grp == 1 ? 3 : 5), h1 = grp == 0 ? 3 : (grp == 1 ? 5 : 7);
-                    for (int h = h0; h < h1; ++h) wait_phase<PROF>(bars, B_H1 + h, h1_phase, wacc, W_H1);
+                    for (int h = h0; h < h1; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
                       if (grp == 0 && more) out_mmas(out_off, q1_net, q1_c, q1_ks);
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll
                   for (int h = 0; h < kMaxKs / 4; ++h) {
                     if (h * 4 < kin) {
-                      if (wait_h1) wait_phase<PROF>(bars, B_H1 + h, h1_phase, wacc, W_H1);
+                      if (wait_h1) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
                       ptx::tc_fence_after();  // orders the MMAs after the epilogue's tcgen05.st seen through the barriers above
                       if (ptx::elect_one()) {
 #pragma unroll
@@ -522,9 +531,12 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
         for (int st = 0; st < stages; ++st, ++rhs_idx) {
           // ---- drain the accumulator chunks of the hidden layers ----
 #pragma unroll 1
-          for (int net = 0; net < 3; ++net) {
-#pragma unroll 1
-            for (int j = 0; j < a.L - 1; ++j) {
+          for (int idx = 0; idx < 3 * (a.L - 1); ++idx) {
+            const int net = a.interleave ? idx % 3 : idx / (a.L - 1);
+            {
+              const int j = a.interleave ? idx / 3 : idx % (a.L - 1);
+              const int h1_base = a.interleave ? net * a.nc1 : 0;
+              const uint32_t hf_base = kColHF + (a.interleave ? (uint32_t)(net * (a.hpad[0] / 2)) : 0u);
               const bool fused = (j == a.L - 2);
               const int hp = a.hpad[j];
 #pragma unroll 1
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 ptx::tc_fence_after();
                 const long long t_ld = prof_me ? clock64() : 0;
                 const uint32_t src = tmem + lane_addr + kColD0 + buf * kCW + (uint32_t)(ps * CPW);
-                const uint32_t dst = tmem + lane_addr + (fused ? kColH2 : kColHF + (uint32_t)c * (kCW / 2)) + (uint32_t)(ps * CPW / 2);
+                const uint32_t dst = tmem + lane_addr + (fused ? kColH2 : hf_base + (uint32_t)c * (kCW / 2)) + (uint32_t)(ps * CPW / 2);
                 uint32_t rr[CPW / 16][16];
 #pragma unroll
                 for (int grp = 0; grp < CPW / 16; ++grp)
@@ -562,7 +574,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
 #pragma unroll
                 for (int grp = 0; grp < CPW / 16; ++grp)
                   if (grp * 16 < ncols) ptx::tmem_st8(dst + grp * 8, pk[grp]);
-                if (net == 0 && j == 0 && c == 0) {
+                if (idx == 0 && c == 0) {
                   // first chunk of a right-hand side: zero this thread's share of Y (every output-layer MMA accumulates).  All
                   // threads have read the previous Y (this chunk's MMAs were issued behind the X-full barrier), and the first
                   // output-layer MMA waits for a LATER chunk's drained arrival of these same warps.
@@ -575,7 +587,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 __syncwarp();
                 if (lane == 0) {
                   arrive_issuer(B_DEMPTY + buf);          // accumulator drained AND (fused chunk) H2c written
-                  if (!fused) arrive_issuer(B_H1 + c);
+                  if (!fused) arrive_issuer(B_H1 + h1_base + c);
                 }
                 if (prof_me) eacc[E_ST - 8] += clock64() - t_st;
               }
@@ -778,10 +790,18 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
     half[0].clear();
     half[1].clear();
   };
+  // narrow three-layer nets: layer-major schedule (three first-layer HF images of <= 64 columns fit the 200-column region,
+  // 3 x 2 H1 barriers fit the 7 there are)
+  pl.interleave = (L == 3) && pl.hpad[0] <= 128 && getenv("OPZ_TC_INTERLEAVE") != nullptr;   // opt-in until measured
   for (int net = 0; net < 3; ++net) {
     const float* wn = w.data() + (size_t)net * nd.P;
     for (int i = 0; i < nd.sizes[L]; ++i) pl.b3[net * 32 + i] = wn[nd.b_off[L - 1] + i];
-    for (int j = 0; j < L - 1; ++j) {
+  }
+  for (int idx = 0; idx < 3 * (L - 1); ++idx) {
+    const int net = pl.interleave ? idx % 3 : idx / (L - 1);
+    const float* wn = w.data() + (size_t)net * nd.P;
+    {
+      const int j = pl.interleave ? idx / 3 : idx % (L - 1);
       const bool fused = (j == L - 2);
       const int kin = (j == 0) ? kS : pl.hpad[j - 1];
       const int hp = pl.hpad[j];
@@ -884,6 +904,8 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   a.hpad[0] = pl->hpad[0]; a.hpad[1] = pl->hpad[1];
   std::memcpy(a.b3, pl->b3, sizeof(a.b3));
   a.n_mma_warps = 2;
+  a.interleave = pl->interleave ? 1 : 0;
+  a.nc1 = (pl->hpad[0] + kCW - 1) / kCW;
   if (const char* e = getenv("OPZ_TC_MMA_WARPS")) a.n_mma_warps = atoi(e) == 1 ? 1 : 2;
   std::memcpy(a.st_off, pl->st_off, sizeof(a.st_off));
   std::memcpy(a.st_bytes, pl->st_bytes, sizeof(a.st_bytes));

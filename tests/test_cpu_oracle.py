@@ -263,3 +263,60 @@ def test_twin_mpp_parameter_gradient_matches_finite_differences():
         Lp = OT.loss_and_grad(x0, bc, m, dataclasses.replace(p, **{nme: v + h}), O.SCHEME_RK4, dt, n_steps, se, tgt, lw)[0]
         Lm = OT.loss_and_grad(x0, bc, m, dataclasses.replace(p, **{nme: v - h}), O.SCHEME_RK4, dt, n_steps, se, tgt, lw)[0]
         assert (Lp - Lm) / (2 * h) == pytest.approx(gm[i], rel=2e-5), nme
+
+
+def test_twin_flux_pretraining_gradient_matches_finite_differences():
+    """Ground truth of opz_flux_loss_grad (train_NN / NN_loss, NN_training.jl:207-249): the twin's gradient of the
+    supervised flux loss of one net against central differences, and zero gradient for the other two nets."""
+    from oracle import nde_oracle_torch as OT
+    flags = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    p = O.Params(flags=flags)
+    N = 6
+    x, bc = O.synthetic_columns(N, p, dtype=np.float64)
+    x = x + 0.05 * np.random.default_rng(8).normal(size=x.shape)
+    sizes = (96, 12, 31)
+    m = O.make_model(sizes, O.ACT_SWISH, seed=1, out_scale=0.1, dtype=np.float64, bias_scale=0.1)
+    tgt = O.predict_flux(x, bc, 0.0, O.make_model(sizes, O.ACT_SWISH, seed=2, out_scale=0.1, dtype=np.float64), p)[1]
+    gs = 3.2e-3
+    total, l1, l2, g, g_all = OT.flux_loss_and_grad(x, bc, m, p, 1, tgt, gs)
+    assert total == pytest.approx(l1 + gs * l2, rel=1e-12)
+    P = m.P
+    assert np.all(g_all[:P] == 0) and np.all(g_all[2 * P:] == 0)
+    # numpy restatement of the loss
+    def L(w_vw):
+        mm = O.Model(m.sizes, m.act, m.w_uw, w_vw, m.w_wT)
+        F = O.predict_flux(x, bc, 0.0, mm, p)[1]
+        d = (F[:, 1:] - F[:, :-1]) * 32.0 - (tgt[:, 1:] - tgt[:, :-1]) * 32.0
+        return float((((F - tgt) ** 2).mean(axis=1) + gs * (d ** 2).mean(axis=1)).mean())
+    assert L(m.w_vw) == pytest.approx(total, rel=1e-10)
+    rng = np.random.default_rng(0)
+    for idx in rng.choice(P, size=6, replace=False):
+        wp, wm = m.w_vw.copy(), m.w_vw.copy()
+        h = 1e-6
+        wp[idx] += h
+        wm[idx] -= h
+        assert (L(wp) - L(wm)) / (2 * h) == pytest.approx(g[idx], rel=1e-5, abs=1e-12)
+
+
+def test_optimise_mpp_host_loop_with_a_stub_gradient(monkeypatch):
+    """Host logic of api.optimise_modified_pacanowski_philander without a GPU: scaled parameters p / p_initial
+    (diffusivity_parameter_optimisation.jl:44-48), box [0, 10] (:197), gradient chain rule, params updated in place."""
+    import opz_import
+    opz = opz_import.load()
+    api = opz.api
+    target = np.array([2e-4, 0.05, 0.2, 0.3, 1.5])
+
+    def fake(model, params, x0, bc, tgt, lw, scheme, dt, n_steps, save_every, **kw):
+        pv = np.array([params.nu0, params.nu_m, params.dRi, params.Ric, params.Pr], dtype=np.float64)
+        r = pv / target - 1.0
+        return float((r ** 2).sum()), np.zeros(6, np.float32), np.zeros(1, np.float32), (2 * r / target).astype(np.float32)
+
+    monkeypatch.setattr(api, "loss_grad_mpp", fake)
+    pp = opz.OpzParams()
+    pp.nu0, pp.nu_m, pp.dRi, pp.Ric, pp.Pr = 1e-4, 0.1, 0.1, 0.25, 1.0
+    seen = []
+    pfin, hist = api.optimise_modified_pacanowski_philander(None, pp, None, None, None, None, api.RK4(1e-4), 8, 4, [api.ADAM(5e-2)],
+                                                            maxiters=300, callback=lambda p, t, c, i: seen.append(t))
+    assert len(hist) == 300 and len(seen) == 300 and hist[-1] < 1e-2 * hist[0]
+    assert np.allclose(pfin, target, rtol=0.1)
+    assert pp.nu_m == pytest.approx(float(pfin[1]), rel=1e-6) and np.all(pfin >= 0) and np.all(pfin <= 10 * np.array([1e-4, 0.1, 0.1, 0.25, 1.0]))
