@@ -47,6 +47,10 @@ extern "C" {
 #define OPZ_EULER 0
 #define OPZ_RK2 1 /* Heun */
 #define OPZ_RK4 2
+/* Split step of the reference's production path (NDE_oceananigans.jl:61-101): explicit Euler for the NN fluxes, boundary fluxes
+ * and Coriolis, then backward-Euler vertical diffusion (tridiagonal solve per variable) with the diffusivities of the updated
+ * state; lifts the explicit limit dt <= ~0.7 dz^2 / kappa of convective adjustment.  opz_rollout_forward[_dev], OPZ_PREC_FP32. */
+#define OPZ_IMEX_EULER 3
 
 /* activation of the hidden Dense layers (NNlib names); the last layer is linear */
 #define OPZ_ACT_IDENTITY 0

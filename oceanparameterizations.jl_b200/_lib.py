@@ -20,7 +20,7 @@ FLAG_DIURNAL_MINUS_SCALE0 = 1 << 5
 FLAG_RI_EPS = 1 << 6
 FLAG_SMOOTH_NN = 1 << 7
 FLAG_SMOOTH_RI = 1 << 8
-SCHEME_EULER, SCHEME_RK2, SCHEME_RK4 = 0, 1, 2
+SCHEME_EULER, SCHEME_RK2, SCHEME_RK4, SCHEME_IMEX = 0, 1, 2, 3
 ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_MISH, ACT_SWISH, ACT_LEAKYRELU = range(6)
 PREC_FP32, PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3, 4
 BC_STRIDE = 8

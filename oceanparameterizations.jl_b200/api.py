@@ -370,6 +370,12 @@ def RK4(dt, precision=L.PREC_FP32):
     return _Stepper(dt, L.SCHEME_RK4, precision)
 
 
+def IMEXEuler(dt):
+    """Explicit Euler for the NN / boundary fluxes and Coriolis + backward-Euler vertical diffusion: the split step of the
+    reference's Oceananigans path (NDE_oceananigans.jl:61-101).  FP32 only."""
+    return _Stepper(dt, L.SCHEME_IMEX, L.PREC_FP32)
+
+
 def _steps_from_ts(ts, dt):
     ts = np.asarray(ts, dtype=np.float64)
     if ts.size < 2:

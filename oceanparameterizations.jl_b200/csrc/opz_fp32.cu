@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fp32_kernel(const __grid_
   const int64_t n_tiles = (a.B + M - 1) / M;
   const float h = a.dt;
   const int stages = a.scheme == OPZ_RK4 ? 4 : (a.scheme == OPZ_RK2 ? 2 : 1);
+  DevParams P_ex = a.P;   // OPZ_IMEX_EULER: the explicit part leaves the vertical diffusion out
+  P_ex.flags &= ~(uint32_t)(OPZ_FLAG_MPP | OPZ_FLAG_CA | OPZ_FLAG_SMOOTH_RI);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t col0 = tile * M;
@@ -124,7 +126,60 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fp32_kernel(const __grid_
               const float xv = xo + h * k; s.xn[o] = xv; xnext[o] = xv;
             }
           };
-          column_rhs(a.P, bc, ts, X, Y, K, NoFlux());
+          if (scheme == OPZ_IMEX_EULER) {
+            // explicit part: everything but the vertical diffusion (flags masked), Euler update through K (the else branch)
+            column_rhs(P_ex, bc, ts, X, Y, K, NoFlux());
+            // implicit part: backward-Euler diffusion with the diffusivities of the updated state, one tridiagonal system per
+            // variable solved by the Thomas algorithm, bottom to top (NDE_oceananigans.jl:61-101); s.kacc is free in this
+            // scheme and holds the c' coefficients, the modified right-hand side overwrites the state in place
+            if (a.P.flags & OPZ_FLAG_MPP) {
+              const DevParams& P = a.P;
+              const float coef_u = h * (-P.A_u) * P.c_u * P.nzf * P.nzf;   // = dt nu / dz^2 per unit nu
+              const float coef_v = h * (-P.A_v) * P.c_v * P.nzf * P.nzf;
+              const float coef_T = h * (-P.A_T) * P.c_T * P.nzf * P.nzf;
+              auto XS = [&](int i) -> float& { return xnext[i * M + tid]; };
+              auto CP = [&](int i) -> float& { return s.kacc[i * M + tid]; };
+              float Dlo_u = 0.0f, Dlo_v = 0.0f, Dlo_T = 0.0f;     // D on the face below cell c
+              float u_lo = XS(0), v_lo = XS(nz), T_lo = XS(2 * nz);   // ORIGINAL values of cell c (read before they are overwritten)
+              for (int c = 0; c < nz; ++c) {
+                float Dhi_u = 0.0f, Dhi_v = 0.0f, Dhi_T = 0.0f;   // face c + 1 (zero on the top boundary)
+                float u_hi = 0.0f, v_hi = 0.0f, T_hi = 0.0f;
+                if (c + 1 < nz) {
+                  u_hi = XS(c + 1); v_hi = XS(nz + c + 1); T_hi = XS(2 * nz + c + 1);
+                  const float gu = (u_hi - u_lo) * P.nzf, gv = (v_hi - v_lo) * P.nzf, gT = (T_hi - T_lo) * P.nzf;
+                  const float nu = nu_of_ri(P, richardson(P, gu, gv, gT));
+                  const float nuT = nuT_of(P, nu, gu, gT);
+                  Dhi_u = coef_u * nu; Dhi_v = coef_v * nu; Dhi_T = coef_T * nuT;
+                }
+                // row c: -Dlo phi_{c-1} + (1 + Dlo + Dhi) phi_c - Dhi phi_{c+1} = phi*_c
+                {
+                  const float den = (1.0f + Dlo_u + Dhi_u) + Dlo_u * (c > 0 ? CP(c - 1) : 0.0f);
+                  CP(c) = -Dhi_u / den;
+                  XS(c) = (u_lo + Dlo_u * (c > 0 ? XS(c - 1) : 0.0f)) / den;
+                }
+                {
+                  const float den = (1.0f + Dlo_v + Dhi_v) + Dlo_v * (c > 0 ? CP(nz + c - 1) : 0.0f);
+                  CP(nz + c) = -Dhi_v / den;
+                  XS(nz + c) = (v_lo + Dlo_v * (c > 0 ? XS(nz + c - 1) : 0.0f)) / den;
+                }
+                {
+                  const float den = (1.0f + Dlo_T + Dhi_T) + Dlo_T * (c > 0 ? CP(2 * nz + c - 1) : 0.0f);
+                  CP(2 * nz + c) = -Dhi_T / den;
+                  XS(2 * nz + c) = (T_lo + Dlo_T * (c > 0 ? XS(2 * nz + c - 1) : 0.0f)) / den;
+                }
+                Dlo_u = Dhi_u; Dlo_v = Dhi_v; Dlo_T = Dhi_T;
+                u_lo = u_hi; v_lo = v_hi; T_lo = T_hi;
+              }
+              for (int c = nz - 2; c >= 0; --c) {
+                XS(c) = XS(c) - CP(c) * XS(c + 1);
+                XS(nz + c) = XS(nz + c) - CP(nz + c) * XS(nz + c + 1);
+                XS(2 * nz + c) = XS(2 * nz + c) - CP(2 * nz + c) * XS(2 * nz + c + 1);
+              }
+              for (int i = 0; i < 3 * nz; ++i) s.xn[i * M + tid] = XS(i);
+            }
+          } else {
+            column_rhs(a.P, bc, ts, X, Y, K, NoFlux());
+          }
         }
         cur ^= 1;
         __syncthreads();

@@ -40,8 +40,8 @@ FLAG_RI_EPS = 1 << 6            # add eps to each gradient inside Ri (NDE_traini
 FLAG_SMOOTH_NN = 1 << 7         # 3-point box filter on NN output (NDE_training.jl:98-102)
 FLAG_SMOOTH_RI = 1 << 8         # 3-point box filter on Ri (NDE_training.jl:121-123)
 
-SCHEME_EULER, SCHEME_RK2, SCHEME_RK4 = 0, 1, 2
-STAGES = {SCHEME_EULER: 1, SCHEME_RK2: 2, SCHEME_RK4: 4}
+SCHEME_EULER, SCHEME_RK2, SCHEME_RK4, SCHEME_IMEX = 0, 1, 2, 3
+STAGES = {SCHEME_EULER: 1, SCHEME_RK2: 2, SCHEME_RK4: 4, SCHEME_IMEX: 1}
 
 ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_MISH, ACT_SWISH, ACT_LEAKYRELU = 0, 1, 2, 3, 4, 5
 
@@ -411,7 +411,51 @@ def step(x, bc, t, h, model, p, scheme, quant=None):
         k3 = rhs(x + (h * dt(0.5)) * k2, bc, t + h * dt(0.5), model, p, quant)
         k4 = rhs(x + h * k3, bc, t + h, model, p, quant)
         return x + (h / dt(6)) * (k1 + dt(2) * k2 + dt(2) * k3 + k4)
+    if scheme == SCHEME_IMEX:
+        return step_imex(x, bc, t, h, model, p, quant)
     raise ValueError(scheme)
+
+
+def step_imex(x, bc, t, h, model, p, quant=None):
+    """Split step of the reference's production (Oceananigans) path, NDE_oceananigans.jl:61-101: an explicit Euler step
+    with everything but the vertical diffusion (NN fluxes, boundary fluxes, Coriolis), then a backward-Euler solve of the
+    modified Pacanowski-Philander / convective-adjustment diffusion, one tridiagonal system per variable,
+        (1 + D_c + D_{c+1}) phi_c - D_c phi_{c-1} - D_{c+1} phi_{c+1} = phi*_c ,   D_f = dt nu_f / dz^2  (0 on the two
+    boundary faces), with the diffusivities evaluated on the state after the explicit part (:40-58 computes them from
+    the model state at that point).  In the scaled variables D_f = h (tau / H^2) Nz^2 nu_f.  The reference's
+    `T'[1] = T_bottom` pin (:95) is NOT applied (it overrides the no-flux bottom boundary of the column model)."""
+    dt = x.dtype.type
+    Nz = p.Nz
+    h = dt(h)
+    p_ex = dataclasses.replace(p, flags=p.flags & ~(FLAG_MPP | FLAG_CA | FLAG_SMOOTH_RI))
+    xs = x + h * rhs(x, bc, t, model, p_ex, quant)
+    if not (p.flags & FLAG_MPP):
+        return xs
+    _, _, _, diag = predict_flux(xs, bc, t, model, p, quant, return_diag=True)
+    coef = h * (dt(p.tau) / dt(p.H) / dt(p.H)) * dt(Nz) * dt(Nz)
+    out = np.empty_like(xs)
+    for v, nu in enumerate((diag["nu"], diag["nu"], diag["nuT"])):
+        D = np.zeros((x.shape[0], Nz + 1), dtype=x.dtype)
+        D[:, 1:Nz] = coef * nu[:, 1:Nz].astype(x.dtype)
+        phi = xs[:, v * Nz:(v + 1) * Nz]
+        # Thomas algorithm, bottom (c = 0) to top
+        cp = np.empty_like(phi)
+        dp = np.empty_like(phi)
+        b0 = dt(1) + D[:, 0] + D[:, 1]
+        cp[:, 0] = -D[:, 1] / b0
+        dp[:, 0] = phi[:, 0] / b0
+        for c in range(1, Nz):
+            a_c = -D[:, c]
+            b_c = dt(1) + D[:, c] + D[:, c + 1]
+            den = b_c - a_c * cp[:, c - 1]
+            cp[:, c] = -D[:, c + 1] / den
+            dp[:, c] = (phi[:, c] - a_c * dp[:, c - 1]) / den
+        sol = np.empty_like(phi)
+        sol[:, Nz - 1] = dp[:, Nz - 1]
+        for c in range(Nz - 2, -1, -1):
+            sol[:, c] = dp[:, c] - cp[:, c] * sol[:, c + 1]
+        out[:, v * Nz:(v + 1) * Nz] = sol
+    return out
 
 
 def rollout(x0, bc, model, p, scheme, dt_nd, n_steps, save_every, t0=0.0, quant=None):

@@ -313,3 +313,35 @@ def test_nz128_diurnal_fp32_matches_oracle(opz, oracle):
         opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 4, 2, precision=opz.PREC_FP16)
     assert e.value.code == opz.OPZ_EUNSUP
     model.close()
+
+
+def test_imex_euler_matches_oracle_and_is_stable_at_kappa_10(opz, oracle):
+    """OPZ_IMEX_EULER (explicit Euler + backward-Euler vertical diffusion, NDE_oceananigans.jl:61-101) on the
+    FP32 path against the oracle's step_imex; one day at dt = 60 s with kappa = 10, where the explicit schemes need dt <= 4 s."""
+    O = oracle
+    p = O.Params(flags=O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0, kappa=10.0)
+    B = 70
+    x0, bc = O.synthetic_columns(B, p)
+    x0 = (x0 + 0.02 * np.random.default_rng(5).normal(size=x0.shape)).astype(np.float32)
+    m = O.make_model((96, 50, 20, 31), O.ACT_MISH, seed=2, out_scale=0.1, bias_scale=0.05)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 60.0 / p.tau
+    n_steps, save_every = 1440, 360
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_IMEX, dt, n_steps, save_every)
+    ref = O.rollout(x0, bc, m, p, O.SCHEME_IMEX, dt, n_steps, save_every)
+    err = O.profile_error(out, ref, 32)
+    print(f"IMEX Euler, kappa = 10, dt = 60 s, one day: max relative profile error vs the oracle {err:.2e}; |x|max {np.abs(out).max():.2f}")
+    assert np.isfinite(out).all() and np.abs(out).max() < 50
+    assert err < 1e-4
+    # the host mirror's stepper object; tensor-core precisions and the gradient decline the scheme
+    st = opz.IMEXEuler(dt)
+    assert st.scheme == opz.SCHEME_IMEX
+    for prec in (opz.PREC_FP16, opz.PREC_BF16):
+        with pytest.raises(opz.OpzError) as e:
+            opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_IMEX, dt, 4, 2, precision=prec)
+        assert e.value.code == opz.OPZ_EUNSUP
+    with pytest.raises(opz.OpzError) as e:
+        opz.loss_grad(model, pp, x0, bc, ref[:, :3], np.ones(6, np.float32), opz.SCHEME_IMEX, dt, 8, 4)
+    assert e.value.code == opz.OPZ_EUNSUP
+    model.close()
