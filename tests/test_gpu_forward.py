@@ -327,13 +327,24 @@ def test_imex_euler_matches_oracle_and_is_stable_at_kappa_10(opz, oracle):
     model = product_model(opz, m)
     pp = product_params(opz, p)
     dt = 60.0 / p.tau
+    # short rollout: FP32 tolerance of the north star
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_IMEX, dt, 48, 12)
+    ref = O.rollout(x0, bc, m, p, O.SCHEME_IMEX, dt, 48, 12)
+    err = O.profile_error(out, ref, 32)
+    assert np.isfinite(out).all() and err < 1e-4, err
+    # one day: the convective-adjustment switch amplifies rounding (float32 vs float64 oracle: ~5e-3), so the bound is the
+    # oracle's own float32 noise floor
     n_steps, save_every = 1440, 360
     out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_IMEX, dt, n_steps, save_every)
     ref = O.rollout(x0, bc, m, p, O.SCHEME_IMEX, dt, n_steps, save_every)
-    err = O.profile_error(out, ref, 32)
-    print(f"IMEX Euler, kappa = 10, dt = 60 s, one day: max relative profile error vs the oracle {err:.2e}; |x|max {np.abs(out).max():.2f}")
+    m64 = O.Model(m.sizes, m.act, m.w_uw.astype(np.float64), m.w_vw.astype(np.float64), m.w_wT.astype(np.float64))
+    ref64 = O.rollout(x0.astype(np.float64), bc.astype(np.float64), m64, p, O.SCHEME_IMEX, dt, n_steps, save_every)
+    floor = O.profile_error(ref, ref64, 32)
+    err_day = O.profile_error(out, ref64, 32)
+    print(f"IMEX Euler, kappa = 10, dt = 60 s: 48 steps err {err:.2e}; one day err vs float64 oracle {err_day:.2e} "
+          f"(float32 oracle: {floor:.2e}); |x|max {np.abs(out).max():.2f}")
     assert np.isfinite(out).all() and np.abs(out).max() < 50
-    assert err < 1e-4
+    assert err_day < max(1e-4, 2.0 * floor)
     # the host mirror's stepper object; tensor-core precisions and the gradient decline the scheme
     st = opz.IMEXEuler(dt)
     assert st.scheme == opz.SCHEME_IMEX
