@@ -322,3 +322,58 @@ def test_flux_loss_grad_matches_autograd_twin(opz, oracle, ctx, which, sizes, ac
     with pytest.raises(opz.OpzError):
         opz.flux_loss_grad(model, product_params(opz, p), 3, x, bc, target, gs)
     model.close()
+
+
+def test_train_NDE_host_loop_learns_on_synthetic_les_shaped_data(opz, oracle, ctx):
+    """The reference-shaped training entry point (train_NDE, NDE_training.jl:167-374) end to end: an LES-shaped dataset
+    object (scaled profiles of 4 simulations at 600 s spacing, fluxes, scalings, times) generated by the oracle with a
+    'true' model; ADAM steps with libopz gradients reduce the profile + gradient loss, and the first evaluation agrees
+    with the autograd twin."""
+    from types import SimpleNamespace as NS
+    from helpers import chains_from_oracle_model
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    n_sim, nt, dt_data = 4, 7, 600.0
+    tau = dt_data * (nt - 1)
+    flags = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    p = O.Params(tau=tau, flags=flags, dRi=1.0)          # train_NDE's default dRi = 1 (NDE_training.jl:168)
+    x0, bc = O.synthetic_columns(n_sim, p)
+    x0 = (x0 + 0.02 * np.random.default_rng(1).normal(size=x0.shape)).astype(np.float32)
+    sizes = (96, 50, 20, 31)
+    m_true = O.make_model(sizes, O.ACT_MISH, seed=21, out_scale=0.1)
+    m0 = O.make_model(sizes, O.ACT_MISH, seed=22, out_scale=0.1)
+    dt = 30.0 / tau
+    per = int(round(dt_data / 30.0))
+    data = O.rollout(x0, bc, m_true, p, O.SCHEME_RK4, dt, per * (nt - 1), per)       # [n_sim, nt, 96]
+    uvT_scaled = np.concatenate([data[i].T for i in range(n_sim)], axis=1)              # [96, nt * n_sim]
+    t = np.concatenate([np.arange(nt) * dt_data for _ in range(n_sim)])
+    def flux_field(k):   # only rows 0 / -1 of the first column of every simulation are read (the boundary fluxes)
+        a = np.zeros((33, nt * n_sim), dtype=np.float32)
+        for i in range(n_sim):
+            a[0, nt * i:nt * (i + 1)] = bc[i, 2 * k]
+            a[-1, nt * i:nt * (i + 1)] = bc[i, 2 * k + 1]
+        return NS(scaled=a, z=np.linspace(-p.H, 0.0, 33))
+    sc = {n: opz.ZeroMeanUnitVarianceScaling(p.mu[i], p.sigma[i]) for i, n in enumerate(("u", "v", "T", "uw", "vw", "wT"))}
+    D = NS(uvT_scaled=uvT_scaled, t=t, uw=flux_field(0), vw=flux_field(1), wT=flux_field(2), u=NS(z=np.linspace(-p.H, 0, 33)[:-1] + 4.0),
+           scalings=sc, n_simulations=n_sim)
+    uw_NN, vw_NN, wT_NN = chains_from_oracle_model(opz, m0)
+    tsteps = np.arange(0, nt, 2)
+    seen = []
+    out = opz.train_NDE(uw_NN, vw_NN, wT_NN, D, tsteps, opz.RK4(dt), [opz.ADAM(2e-3)], 1, maxiters=12,
+                        modified_pacanowski_philander=True, zero_weights=True, train_gradient=True, gradient_scaling=5e-3,
+                        f=p.f, α=p.alpha, g=p.g, ν0=p.nu0, ν_m=p.nu_m, Riᶜ=p.Ric, ΔRi=p.dRi, Pr=p.Pr,
+                        cb=lambda w, total, comps, lw: seen.append(total))
+    uw2, vw2, wT2, history = out
+    assert len(history) == 12 and len(seen) == 12
+    losses = [h[0] for h in history]
+    print("train_NDE losses:", ["%.4e" % v for v in losses])
+    assert losses[-1] < 0.8 * losses[0] and np.isfinite(losses).all()
+    # first evaluation = the twin's loss on the same problem
+    target = data[:, tsteps]
+    lw = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
+    t_ref, _, _ = OT.loss_and_grad(x0, bc, m0, p, O.SCHEME_RK4, dt, per * (nt - 1), 2 * per, target, lw)
+    assert losses[0] == pytest.approx(t_ref, rel=2e-4)
+    # the returned chains carry the trained weights
+    w_new, _ = opz.destructure(uw2)
+    w_old, _ = opz.destructure(uw_NN)
+    assert w_new.shape == w_old.shape and not np.array_equal(w_new, w_old)
