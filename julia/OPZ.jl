@@ -6,7 +6,7 @@ module OPZ
 
 using Flux
 
-export Context, Model, Params, Euler, Heun, RK4, solve_NDE_mutating, predict_NDE, predict_flux,
+export Context, Model, Params, Euler, Heun, RK4, IMEXEuler, solve_NDE_mutating, predict_NDE, predict_flux,
        loss_and_gradient, predict
 
 const libopz = get(ENV, "LIBOPZ", "libopz.so")
@@ -15,7 +15,7 @@ const libopz = get(ENV, "LIBOPZ", "libopz.so")
 const FLAG_MPP, FLAG_CA, FLAG_CA_SELECT_DUDZ, FLAG_BC_MINUS_SCALE0 = UInt32(1) << 0, UInt32(1) << 1, UInt32(1) << 2, UInt32(1) << 3
 const FLAG_DIURNAL, FLAG_DIURNAL_MINUS_SCALE0, FLAG_RI_EPS = UInt32(1) << 4, UInt32(1) << 5, UInt32(1) << 6
 const FLAG_SMOOTH_NN, FLAG_SMOOTH_RI = UInt32(1) << 7, UInt32(1) << 8
-const SCHEME_EULER, SCHEME_RK2, SCHEME_RK4 = Cint(0), Cint(1), Cint(2)
+const SCHEME_EULER, SCHEME_RK2, SCHEME_RK4, SCHEME_IMEX = Cint(0), Cint(1), Cint(2), Cint(3)
 const PREC_FP32, PREC_BF16, PREC_FP16 = Cint(0), Cint(1), Cint(4)
 const ACT = Dict(identity => 0, relu => 1, tanh => 2, mish => 3, swish => 4, leakyrelu => 5)
 
@@ -89,6 +89,8 @@ struct Stepper; dt::Float32; scheme::Cint; precision::Cint; end
 Euler(dt; precision=PREC_FP32) = Stepper(dt, SCHEME_EULER, precision)
 Heun(dt; precision=PREC_FP32) = Stepper(dt, SCHEME_RK2, precision)
 RK4(dt; precision=PREC_FP32) = Stepper(dt, SCHEME_RK4, precision)
+# explicit Euler + backward-Euler vertical diffusion: the split step of NDE_oceananigans.jl:61-101 (FP32 only)
+IMEXEuler(dt) = Stepper(dt, SCHEME_IMEX, PREC_FP32)
 
 function steps_from_ts(ts, dt)
     length(ts) < 2 && return 0, 1, Float32(first(ts))

@@ -312,25 +312,31 @@ int opz_rollout_forward(opz_ctx* ctx, const opz_model* m, const opz_params* p, c
   OPZ_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ctx->slab_ev[0], 0));
   OPZ_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->slab_ev[0], 0));
   int rc_slab = OPZ_OK;
-  for (int i = 0; i < n_slabs; ++i) {
+  cudaError_t ce = cudaSuccess;
+  const char* ce_what = "";
+  // no early return inside the loop: whatever has been enqueued must drain before the caller gets its buffers back
+#define OPZ_SLAB(expr) do { if (ce == cudaSuccess && rc_slab == OPZ_OK) { ce = (expr); if (ce != cudaSuccess) ce_what = #expr; } } while (0)
+  for (int i = 0; i < n_slabs && ce == cudaSuccess && rc_slab == OPZ_OK; ++i) {
     const int64_t c0 = (int64_t)i * slab, nb = std::min<int64_t>(slab, B - c0);
     cudaEvent_t ev_in = ctx->slab_ev[1 + 2 * i], ev_done = ctx->slab_ev[2 + 2 * i];
-    OPZ_CUDA(cudaMemcpyAsync(dx + c0 * S, x0 + c0 * S, sizeof(float) * nb * S, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    OPZ_CUDA(cudaMemcpyAsync(dbc + c0 * OPZ_BC_STRIDE, bc + c0 * OPZ_BC_STRIDE, sizeof(float) * nb * OPZ_BC_STRIDE,
+    OPZ_SLAB(cudaMemcpyAsync(dx + c0 * S, x0 + c0 * S, sizeof(float) * nb * S, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    OPZ_SLAB(cudaMemcpyAsync(dbc + c0 * OPZ_BC_STRIDE, bc + c0 * OPZ_BC_STRIDE, sizeof(float) * nb * OPZ_BC_STRIDE,
                              cudaMemcpyHostToDevice, ctx->h2d_stream));
-    OPZ_CUDA(cudaEventRecord(ev_in, ctx->h2d_stream));
-    OPZ_CUDA(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
-    rc_slab = opz_rollout_forward_dev(ctx, m, p, dx + c0 * S, dbc + c0 * OPZ_BC_STRIDE, nb, scheme, dt_nd, t0, n_steps, save_every,
-                                      precision, dout + c0 * n_save * S);
-    if (rc_slab) break;
-    OPZ_CUDA(cudaEventRecord(ev_done, ctx->stream));
-    OPZ_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev_done, 0));
-    OPZ_CUDA(cudaMemcpyAsync(out + c0 * n_save * S, dout + c0 * n_save * S, sizeof(float) * nb * n_save * S, cudaMemcpyDeviceToHost,
+    OPZ_SLAB(cudaEventRecord(ev_in, ctx->h2d_stream));
+    OPZ_SLAB(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+    if (ce == cudaSuccess)
+      rc_slab = opz_rollout_forward_dev(ctx, m, p, dx + c0 * S, dbc + c0 * OPZ_BC_STRIDE, nb, scheme, dt_nd, t0, n_steps, save_every,
+                                        precision, dout + c0 * n_save * S);
+    OPZ_SLAB(cudaEventRecord(ev_done, ctx->stream));
+    OPZ_SLAB(cudaStreamWaitEvent(ctx->d2h_stream, ev_done, 0));
+    OPZ_SLAB(cudaMemcpyAsync(out + c0 * n_save * S, dout + c0 * n_save * S, sizeof(float) * nb * n_save * S, cudaMemcpyDeviceToHost,
                              ctx->d2h_stream));
   }
+#undef OPZ_SLAB
   // blocking call: nothing of it is in flight when it returns (also after an error in the middle)
   cudaError_t e1 = cudaStreamSynchronize(ctx->h2d_stream), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->d2h_stream);
   if (rc_slab) return rc_slab;
+  if (ce != cudaSuccess) return cuda_fail(ce, ce_what);
   OPZ_CUDA(e1);
   OPZ_CUDA(e2);
   OPZ_CUDA(e3);
