@@ -157,3 +157,26 @@ def test_tc_rejects_unsupported(opz, oracle, ctx):
         opz.rollout_forward(model, product_params(opz, p), x0, bc, opz.SCHEME_RK4, 1e-4, 4, 2, precision=opz.PREC_FP16)
     assert e.value.code == opz.OPZ_EUNSUP
     model.close()
+
+
+def test_tc_full_size_ensemble_periodicity(opz, oracle, ctx):
+    """BASELINE configs[2] size (2^20 columns on one GPU) on the tensor-core path: the synthetic forcing sweep repeats
+    every 4096 columns, so the result must repeat bit for bit (column independence and determinism across all 8192 tiles,
+    the slab pipeline of the host-buffer call included), and a sample of columns must sit on the oracle."""
+    p = oracle.Params()
+    B = 1 << 20
+    x0s, bcs = oracle.synthetic_columns(4096, p)
+    x0 = np.ascontiguousarray(np.tile(x0s, (B // 4096, 1)))
+    bc = np.ascontiguousarray(np.tile(bcs, (B // 4096, 1)))
+    m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=0, out_scale=0.1, bias_scale=0.1)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 4, 0, precision=opz.PREC_FP16)
+    assert out.shape == (B, 1, 96) and np.isfinite(out).all()
+    blocks = out.reshape(B // 4096, 4096, 96)
+    assert np.array_equal(blocks, np.broadcast_to(blocks[0], blocks.shape))
+    pick = np.array([0, 63, 64, 4095])
+    ref = oracle.rollout(x0s[pick], bcs[pick], m, p, oracle.SCHEME_RK4, dt, 4, 4)[:, -1:]
+    assert oracle.profile_error(blocks[0][pick][:, None, :], ref, 32) < 1e-3
+    model.close()
