@@ -39,7 +39,8 @@ constexpr int kM = 128;              // columns per tile (one tile per CTA, two 
 constexpr int kCW = 64;              // accumulator chunk width (TMEM columns)
 constexpr int kMaxHidden = 400;      // HF region: 200 TMEM columns
 constexpr int kNB = 8;               // stage barrier pairs (stages in flight <= kNB - 1)
-constexpr int kMaxStages = 48;       // stages per right-hand side
+constexpr int kMaxStages = 72;       // stages per right-hand side
+constexpr int kSplitK = 12;          // a 64-row x 25-k-step chunk is staged as two weight stages: k-steps [0, 12) and [12, 25) + bias + W_out
 constexpr int kRingBytes = 84480;    // 3 x (32 rows x (400 + 8) k + 16 rows x 64 k) x 2 B
 constexpr int kMaxKs = 28;           // 7 HF chunks x 4 k-steps
 
@@ -312,15 +313,17 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               const int hp = a.hpad[j];
               const uint32_t a_base = (j == 0) ? kColX : hf_base;
 #pragma unroll 1
-              for (int c0 = 0; c0 < hp; c0 += kCW, ++s, ++gs) {
+              for (int c0 = 0; c0 < hp; c0 += kCW) {
                 const uint32_t rows = (uint32_t)min(kCW, hp - c0);
                 const uint32_t buf = g & 1u;
                 const uint32_t gi = g;                       // global index of this accumulator chunk
                 ++g;
-                const bool mine = (nw == 1u) || ((gs & 1u) == me);
-                if (!mine) {   // the other issuing warp's stage: only the bookkeeping
+                const bool split = (rows == (uint32_t)kCW) && (kin == 25);   // two weight stages (see build_plan)
+                const bool mine = (nw == 1u) || ((gi & 1u) == me);            // a warp owns one accumulator buffer
+                if (!mine) {   // the other issuing warp's chunk: only the bookkeeping
                   q1_net = q0_net; q1_c = q0_c; q1_ks = q0_ks;
                   q0_net = (uint32_t)net; q0_c = (uint32_t)(c0 / kCW); q0_ks = fused ? (rows >> 4) : 0u;
+                  s += split ? 2 : 1; gs += split ? 2u : 1u;
                   continue;
                 }
                 wait_full();
@@ -346,7 +349,34 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 const uint32_t a_one = tmem + kColOne;
                 const uint32_t out_off = a.st_off[s] + (rows / 2) * ((uint32_t)kin * 32u + 16u);
                 const int ebar = B_EMPTY + (int)(gs % kNB);
-                if (static_shape && !wait_h1) {
+                if (split) {
+                  // ---- 64 rows x 25 k-steps in two weight stages, so that the first 12 KB of the ring are free again after
+                  //      12 MMAs: stage A = k-steps [0, 12) (HF chunks 0..2), stage B = [12, 25) + bias + W_out of chunk g - 2
+                  if (wait_h1)
+                    for (int h = 0; h < 3; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
+                  ptx::tc_fence_after();
+                  if (ptx::elect_one()) {
+                    issue_range<kCW, 0, kSplitK>(d, a0, blo, bhi, idesc);
+                    ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                  }
+                  __syncwarp();
+                  ++s; ++gs;
+                  wait_full();
+                  if (wait_h1)
+                    for (int h = 3; h < 7; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
+                  const uint64_t bdB = ptx::smem_desc(ring_u32 + a.st_off[s], (kCW / 2) * 16u, 128);
+                  const uint32_t bloB = (uint32_t)bdB;
+                  const uint32_t out_offB = a.st_off[s] + (kCW / 2) * ((uint32_t)(25 - kSplitK) * 32u + 16u);
+                  ptx::tc_fence_after();
+                  if (ptx::elect_one()) {
+                    if (more) out_mmas(out_offB, q1_net, q1_c, q1_ks);
+                    issue_range<kCW, kSplitK, 25>(d, a0, bloB - (uint32_t)(kSplitK * kCW), bhi, idesc);   // B offsets restart at the stage
+                    ptx::mma_ts2_lohi(d, a_one, bloB + (kCW / 2) * (uint32_t)(25 - kSplitK) * 2u, bhi, idesc, true);
+                    ptx::tc_commit2(bars + B_DFULL + buf);
+                    ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                  }
+                  __syncwarp();
+                } else if (static_shape && !wait_h1) {
                   // hot path: the A operand is already complete; one straight immediate-offset run
                   ptx::tc_fence_after();
                   if (ptx::elect_one()) {
@@ -411,13 +441,14 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                   }
                   __syncwarp();
                 }
+                ++s; ++gs;
                 q1_net = q0_net; q1_c = q0_c; q1_ks = q0_ks;
                 q0_net = (uint32_t)net; q0_c = (uint32_t)(c0 / kCW); q0_ks = fused ? (rows >> 4) : 0u;
               }
             }
           }
           // tail stage: the output-layer MMAs of the last two chunks, each behind the "drained" arrival of its buffer
-          if (nw == 1u || (gs & 1u) == me) {
+          if (nw == 1u || (g & 1u) == me) {
             wait_full();
             uint32_t off = a.st_off[s];
             wait_phase<PROF>(bars, B_DEMPTY + (int)((g - 2u) & 1u), (g - 2u) >> 1, wacc, W_H2FULL);   // chunk g - 2
@@ -807,8 +838,18 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
       const int hp = pl.hpad[j];
       for (int c = 0; c * kCW < hp; ++c) {
         const int rows = std::min(kCW, hp - c * kCW);
-        for (int hf = 0; hf < 2; ++hf)
-          append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kin / 16);
+        const bool split = (rows == kCW) && (kin / 16 == 25);   // two stages: k-steps [0, kSplitK) | [kSplitK, 25) + bias + W_out
+        if (split) {
+          for (int hf = 0; hf < 2; ++hf)
+            append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kSplitK);
+          close_stage();
+          for (int hf = 0; hf < 2; ++hf)
+            append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, kSplitK * 16,
+                        25 - kSplitK);
+        } else {
+          for (int hf = 0; hf < 2; ++hf)
+            append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kin / 16);
+        }
         for (int hf = 0; hf < 2; ++hf)   // bias block: one k-group, row r = [b_r, 0, 0, 0, 0, 0, 0, 0]
           for (int r = 0; r < rows / 2; ++r) {
             const int n = c * kCW + hf * (rows / 2) + r;
