@@ -87,18 +87,33 @@ __device__ __forceinline__ float act_fn(float z) {
   else if constexpr (ACT == OPZ_ACT_LEAKYRELU) return fmaxf(0.01f * z, z);
   else return z;
 }
-// Fast variants for the reduced-precision tensor-core path (results feed a 16-bit operand):
-// one MUFU.EX2 + one MUFU.RCP each, ~1e-6 relative.
+// Fast variants for the reduced-precision tensor-core path (results feed a 16-bit operand): one MUFU.EX2 + one MUFU.RCP
+// each, ~1e-6 relative, flush-to-zero forms (no denormal range fix-ups) and NO data-dependent select: nvcc turns
+// `z > 20 ? z : f(z)` into a branch per element, which serialised the 16 elements a thread converts per chunk
+// (measured: 150 cycles per element on the 50/20 mish net).  The clamps make the formulas exact in their tails instead.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int ACT>
 __device__ __forceinline__ float act_fast(float z) {
+  constexpr float kLog2e = 1.4426950408889634f;
   if constexpr (ACT == OPZ_ACT_RELU) return fmaxf(z, 0.0f);
-  else if constexpr (ACT == OPZ_ACT_TANH) return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
-  else if constexpr (ACT == OPZ_ACT_MISH) {  // tanh(log(1+n)) = w/(w+2), w = n(n+2), n = e^z
-    const float n = __expf(fminf(z, 20.0f));
+  else if constexpr (ACT == OPZ_ACT_TANH) {  // 1 - 2 / (1 + e^{2z}); the exponent is clamped so that e^{2z} stays finite
+    return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(fminf(2.0f * kLog2e * z, 120.0f)));
+  } else if constexpr (ACT == OPZ_ACT_MISH) {  // tanh(log(1+n)) = w/(w+2), w = n(n+2), n = e^z; for z >= 20 the ratio is 1.0f exactly
+    const float n = ex2_ftz(fminf(z, 20.0f) * kLog2e);
     const float w = n * (n + 2.0f);
-    return z > 20.0f ? z : z * __fdividef(w, w + 2.0f);
-  } else if constexpr (ACT == OPZ_ACT_SWISH) return __fdividef(z, 1.0f + __expf(-z));
-  else if constexpr (ACT == OPZ_ACT_LEAKYRELU) return fmaxf(0.01f * z, z);
+    return z * (w * rcp_ftz(w + 2.0f));
+  } else if constexpr (ACT == OPZ_ACT_SWISH) {  // z / (1 + e^{-z}); clamped exponent: for z <= -83 the result is z * 2^-120 ~ -0
+    return z * rcp_ftz(1.0f + ex2_ftz(fminf(-kLog2e * z, 120.0f)));
+  } else if constexpr (ACT == OPZ_ACT_LEAKYRELU) return fmaxf(0.01f * z, z);
   else return z;
 }
 __device__ __forceinline__ float act_dyn(float z, int act) {

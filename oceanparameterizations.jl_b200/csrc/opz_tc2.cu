@@ -658,8 +658,10 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               const float Bz = P.cBz * (gT + P.eps);
               const float sa = P.s_u * (gu + P.eps);
               const float sb = P.s_v * (gv + P.eps);
-              const float Ri = __fdividef(Bz, sa * sa + sb * sb);
-              const float nu = P.nu0 + __fdividef(P.nu_m, 1.0f + __expf((Ri - P.Ric) * P.two_inv_dRi));
+              // flush-to-zero approximations without range fix-ups: 0 / 0 stays NaN (0 * inf), the exponent is clamped so that
+              // e^{..} stays finite (nu -> nu0 in that tail to FP32 precision anyway)
+              const float Ri = Bz * rcp_ftz(sa * sa + sb * sb);
+              const float nu = P.nu0 + P.nu_m * rcp_ftz(1.0f + ex2_ftz(fminf((Ri - P.Ric) * (P.two_inv_dRi * 1.4426950408889634f), 120.0f)));
               const float sel = ca_du ? gu : gT;
               const float nuT = (ca && !(sel > 0.0f)) ? P.kappa : nu * P.inv_Pr;
               Du[i] = interior ? P.c_u * nu * gu : 0.0f;
