@@ -961,10 +961,10 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   if ((int)smem > ctx->smem_optin) { set_error("tensor-core path: shared memory budget exceeded"); return OPZ_EUNSUP; }
   const bool profile = getenv("OPZ_TC_PROFILE") != nullptr && (pl->act == OPZ_ACT_RELU || (pl->act == OPZ_ACT_MISH && fp16));
   using KernelT = void (*)(const Args);
-  // epilogue warps per CTA: 8 for wide nets (the drain is tensor-memory traffic, more warps only add barrier arrivals);
-  // 16 for narrow ones, where the right-hand side is dominated by the physics and the activation (measured: small
-  // 50/20 mish net 2.8e8 vs 2.1e8 col-steps/s, construct_NN 1.4e8 vs 1.6e8)
-  int E = std::max(pl->hpad[0], pl->hpad[1]) <= 64 ? 16 : 8;
+  // epilogue warps per CTA: 8 (two threads per ocean column).  16 measured slower on wide nets (1.4e8 vs 1.6e8: the drain
+  // is tensor-memory traffic, more warps only add barrier arrivals) and, since the activations are branch-free, no faster on
+  // narrow ones (4.34e8 vs 4.45e8 on the 50/20 mish net); OPZ_TC_EPI_WARPS=16 keeps it selectable
+  int E = 8;
   if (const char* e = getenv("OPZ_TC_EPI_WARPS")) E = atoi(e) == 16 ? 16 : 8;
 #define OPZ_TC2_ROW(F, EW) {rollout_tc2_kernel<F, 0, EW, false>, rollout_tc2_kernel<F, 1, EW, false>, rollout_tc2_kernel<F, 2, EW, false>, \
                             rollout_tc2_kernel<F, 3, EW, false>, rollout_tc2_kernel<F, 4, EW, false>, rollout_tc2_kernel<F, 5, EW, false>}
