@@ -674,7 +674,7 @@ void bptt_release(opz_ctx* ctx) {
 namespace {
 
 // Shared-memory plan of the cluster kernel for CP column slots per cluster; returns false if it cannot run.
-bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, bptt::cl::Layout& lay) {
+bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, int CS, bptt::cl::Layout& lay) {
   using namespace bptt;
   const int L = nd.n_layers, S3 = 3 * nz, nout = nz - 1, NO3 = 3 * nout;
   std::memset(&lay, 0, sizeof(lay));
@@ -682,7 +682,7 @@ bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, bptt::c
   int off = 0, ulmax = 0;
   auto take = [&](int n) { const int o = off; off += (n + 3) / 4 * 4; return o; };
   for (int l = 0; l < L - 1; ++l) {
-    const int UL = (nd.sizes[l + 1] + cl::kCS - 1) / cl::kCS;
+    const int UL = (nd.sizes[l + 1] + CS - 1) / CS;
     if (3 * UL * CP > cl::kThreads) return false;
     lay.UL[l] = UL;
     ulmax = std::max(ulmax, UL);
@@ -701,21 +701,21 @@ bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, bptt::c
   lay.xn = take(S3 * CP); lay.xs = take(S3 * CP); lay.kacc = take(S3 * CP); lay.lam = take(S3 * CP);
   lay.kbar = take(S3 * CP); lay.xsum = take(S3 * CP); lay.xphys = take(S3 * CP);
   lay.Fs = take(3 * (nz + 1) * CP);
-  lay.recv_big_size = (cl::kCS * 3 * ulmax * CP + 3) / 4 * 4;
+  lay.recv_big_size = (CS * 3 * ulmax * CP + 3) / 4 * 4;
   off = (off + 3) / 4 * 4;   // 16-byte aligned: the reduce-scatter stores CP columns per transaction
   lay.recv_big = take(lay.recv_big_size * (L >= 4 ? 2 : 1));
-  lay.SL = (std::max(NO3, S3) * CP + cl::kCS - 1) / cl::kCS;
-  lay.recv_small = take(cl::kCS * lay.SL);
-  lay.rbase = take(cl::kCS);
+  lay.SL = (std::max(NO3, S3) * CP + CS - 1) / CS;
+  lay.recv_small = take(CS * lay.SL);
+  lay.rbase = take(CS);
   lay.total = off;
   return (size_t)off * sizeof(float) <= (size_t)ctx->smem_optin;
 }
 
 // groups == 0: only queries how many clusters can be resident at once
-template <int CP>
+template <int CP, int CS>
 int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int cg, int64_t groups, int* max_active) {
   using namespace bptt;
-  auto kern = cl::sweep_kernel<CP>;
+  auto kern = cl::sweep_kernel<CP, CS>;
   const size_t smem = (size_t)lay.total * sizeof(float);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
@@ -723,13 +723,13 @@ int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& la
     return OPZ_EUNSUP;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(std::max<int64_t>(groups, 1) * cl::kCS));
+  cfg.gridDim = dim3((unsigned)(std::max<int64_t>(groups, 1) * CS));
   cfg.blockDim = dim3(cl::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl::kCS;
+  attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -749,11 +749,18 @@ int launch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& la
 
 int slots_for(int cg) { return cg <= 1 ? 1 : (cg <= 2 ? 2 : 4); }
 
-int dispatch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int cg, int64_t groups, int* max_active) {
+int dispatch_cluster(opz_ctx* ctx, const bptt::Args& a, const bptt::cl::Layout& lay, int cs, int cg, int64_t groups, int* max_active) {
+  if (cs == 1) {
+    switch (slots_for(cg)) {
+      case 1: return launch_cluster<1, 1>(ctx, a, lay, cg, groups, max_active);
+      case 2: return launch_cluster<2, 1>(ctx, a, lay, cg, groups, max_active);
+      default: return launch_cluster<4, 1>(ctx, a, lay, cg, groups, max_active);
+    }
+  }
   switch (slots_for(cg)) {
-    case 1: return launch_cluster<1>(ctx, a, lay, cg, groups, max_active);
-    case 2: return launch_cluster<2>(ctx, a, lay, cg, groups, max_active);
-    default: return launch_cluster<4>(ctx, a, lay, cg, groups, max_active);
+    case 1: return launch_cluster<1, bptt::cl::kCS>(ctx, a, lay, cg, groups, max_active);
+    case 2: return launch_cluster<2, bptt::cl::kCS>(ctx, a, lay, cg, groups, max_active);
+    default: return launch_cluster<4, bptt::cl::kCS>(ctx, a, lay, cg, groups, max_active);
   }
 }
 
@@ -891,21 +898,31 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   // ---- cluster path: the whole sweep of a column group inside one 16-CTA cluster (weights in shared memory) ----
   if (single && n_steps > 0 && !getenv("OPZ_BPTT_NO_CLUSTER")) {
     cl::Layout lay;
-    int CG = 0, max_active = 0;
-    // fewest columns per cluster that still lets all groups run concurrently; else the widest that fits
-    auto try_cg = [&](int cg) -> bool {
+    int CG = 0, CS = 0, max_active = 0;
+    // fewest columns per cluster that still lets all groups run concurrently; else the widest that fits.  Nets whose FP32
+    // weights fit ONE SM's shared memory (the 50/20 production net: 78 KB) run with a "cluster" of one CTA: no DSMEM
+    // exchange, __syncthreads instead of cluster barriers, one CTA per column group.
+    auto try_cg = [&](int cs, int cg) -> bool {
       cl::Layout tmp;
       int ma = 0;
-      if (!plan_cluster(ctx, nd, nz, slots_for(cg), tmp)) return false;
-      if (dispatch_cluster(ctx, a, tmp, cg, 0, &ma) != OPZ_OK) return false;
-      CG = cg; lay = tmp; max_active = ma;
+      if (!plan_cluster(ctx, nd, nz, slots_for(cg), cs, tmp)) return false;
+      if (dispatch_cluster(ctx, a, tmp, cs, cg, 0, &ma) != OPZ_OK) return false;
+      CG = cg; CS = cs; lay = tmp; max_active = ma;
       return true;
     };
-    for (int cg = 1; cg <= 4; ++cg)
-      if (try_cg(cg) && (B + cg - 1) / cg <= max_active) break;
+    const bool allow_single = !getenv("OPZ_BPTT_NO_SINGLE_CTA");
+    bool chosen = false;
+    if (allow_single)
+      for (int cg = 1; cg <= 4 && !chosen; ++cg)
+        if (try_cg(1, cg) && (B + cg - 1) / cg <= max_active) chosen = true;
+    if (!chosen) {
+      CG = 0;
+      for (int cg = 1; cg <= 4; ++cg)
+        if (try_cg(cl::kCS, cg) && (B + cg - 1) / cg <= max_active) break;
+    }
     if (const char* e = getenv("OPZ_BPTT_CLUSTER_COLUMNS")) {
       const int cg = atoi(e);
-      if (cg >= 1 && cg <= 4) try_cg(cg);
+      if (cg >= 1 && cg <= 4) try_cg(CS ? CS : cl::kCS, cg);
     }
     if (CG > 0) {
       cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -915,7 +932,7 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
       ac.record = 1;
       const int64_t groups = (B + CG - 1) / CG;
       int ma = 0;
-      if ((rc = dispatch_cluster(ctx, ac, lay, CG, groups, &ma))) return rc;
+      if ((rc = dispatch_cluster(ctx, ac, lay, CS, CG, groups, &ma))) return rc;
       if (prof) cudaEventRecord(ev[1], st);
       loss_partial_kernel<<<(unsigned)B, 128, 0, st>>>(a);
       loss_final_kernel<<<1, 32, 0, st>>>(a);
@@ -927,8 +944,8 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
         float f = 0, g = 0;
         cudaEventElapsedTime(&f, ev[0], ev[1]);
         cudaEventElapsedTime(&g, ev[1], ev[2]);
-        fprintf(stderr, "opz bptt profile (cluster path): sweep %.2f ms (%d columns/cluster, %lld clusters, %d resident), "
-                "loss + dW %.2f ms, shared memory %.1f KB, records %.2f GB\n", f, CG, (long long)groups, max_active, g,
+        fprintf(stderr, "opz bptt profile (cluster path, %d CTA(s) per cluster): sweep %.2f ms (%d columns/cluster, %lld clusters, %d resident), "
+                "loss + dW %.2f ms, shared memory %.1f KB, records %.2f GB\n", CS, f, CG, (long long)groups, max_active, g,
                 lay.total * 4 / 1024.0, (double)(sizeof(float) * rec_floats * (size_t)rows_cap) / 1e9);
         for (auto& e : ev) cudaEventDestroy(e);
         unsigned long long ph[24];

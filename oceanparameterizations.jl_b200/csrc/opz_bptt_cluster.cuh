@@ -25,7 +25,7 @@
 
 namespace cl {
 
-constexpr int kCS = 16;         // CTAs per cluster
+constexpr int kCS = 16;         // CTAs per cluster for nets that do not fit one SM's shared memory (CS = 1 otherwise)
 constexpr int kThreads = 512;
 constexpr int kMaxKSL = 8;      // split of a slice's reduction dimension over threads
 
@@ -72,9 +72,19 @@ __device__ __forceinline__ void st_remote_cols(uint32_t addr, const float (&v)[C
     for (int c = 0; c < CP; ++c) st_remote(addr + 4u * c, v[c]);
   }
 }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+// CS = 1 (the whole net in one CTA): the "exchanges" are local shared-memory stores and the barrier is __syncthreads — none of the
+// MEMBAR.ALL.GPU / CCTL.IVALL that the release / acquire cluster barrier costs
+template <int CS>
+__device__ __forceinline__ void cluster_arrive() {
+  if constexpr (CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+template <int CS>
+__device__ __forceinline__ void cluster_wait() {
+  if constexpr (CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  else __syncthreads();
+}
+template <int CS>
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive<CS>(); cluster_wait<CS>(); }
 
 // acc[0..CP) += w * p[0..CP)  with one broadcast vector load
 template <int CP>
@@ -98,13 +108,13 @@ __device__ unsigned long long g_phase_cycles[24];
     if (timing) { const long long now_ = clock64(); ph[i] += now_ - tlast; tlast = now_; } \
   } while (0)
 
-template <int CP>
+template <int CP, int CS>
 __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constant__ Args a, const __grid_constant__ Layout lay, int cg) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x;
   const int tc = t % CP, tq = t / CP;   // column slot / item index of the "one thread per (item, column)" phases
-  const int rank = (int)cluster_rank();
-  const int64_t group = blockIdx.x / kCS;
+  const int rank = CS > 1 ? (int)cluster_rank() : 0;
+  const int64_t group = blockIdx.x / CS;
   const int64_t col0 = group * cg;
   const int ncol = (int)min((int64_t)cg, a.B - col0);
   const bool col_ok = tc < ncol;
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
   long long tlast = clock64();
 
   // ---- one-time setup: remote bases, weight slices, initial state ----
-  if (t < kCS) rbase[t] = map_to_rank(my_base, (uint32_t)t);
+  if (t < CS) rbase[t] = map_to_rank(my_base, (uint32_t)t);
   for (int l = 0; l < L - 1; ++l) {
     const int K = a.nd.sizes[l], N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
     float* W = sm + lay.W[l];
@@ -164,32 +174,32 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     xn[t] = v;
     xs[t] = v;
   }
-  cluster_sync_all();  // rbase of every CTA is mapped; nobody writes remotely before everyone is here
+  cluster_sync_all<CS>();  // rbase of every CTA is mapped; nobody writes remotely before everyone is here
 
   // two-phase all-reduce of `count` (<= kThreads) per-CTA partials held by threads t < count:
   // reduce-scatter to owner = e % 16; the owner adds bias[e / CP] and broadcasts into dst[e] of every CTA.
   // `between()` runs between the first arrive and wait (HBM record stores go there).
   auto all_reduce = [&](float value, int count, float* dst, const float* bias_by_item, auto&& between) {
     if (t < count) {
-      const int owner = t % kCS, slot = t / kCS;
+      const int owner = t % CS, slot = t / CS;
       st_remote(rbase[owner] + 4u * (uint32_t)(lay.recv_small + rank * lay.SL + slot), value);
     }
-    cluster_arrive();
+    cluster_arrive<CS>();
     between();
-    cluster_wait();
+    cluster_wait<CS>();
     if (t < lay.SL) {
-      const int e = t * kCS + rank;
+      const int e = t * CS + rank;
       if (e < count) {
         float s = 0.0f;
 #pragma unroll
-        for (int src = 0; src < kCS; ++src) s += recv_small[src * lay.SL + t];
+        for (int src = 0; src < CS; ++src) s += recv_small[src * lay.SL + t];
         if (bias_by_item) s += bias_by_item[e / CP];
         const uint32_t off = 4u * (uint32_t)((int)(dst - sm) + e);
 #pragma unroll
-        for (int d = 0; d < kCS; ++d) st_remote(rbase[d] + off, s);
+        for (int d = 0; d < CS; ++d) st_remote(rbase[d] + off, s);
       }
     }
-    cluster_sync_all();
+    cluster_sync_all<CS>();
   };
 
   // hidden layer l, forward, this CTA's slice; `in` is laid out [net][K][CP] (net_stride 0 for the shared
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     for (int s = 0; s < stages; ++s) {
       const int q = n * stages + s;
       const int64_t row0 = (int64_t)q * a.B + col0;
-      const bool recorder = (rank == (q & (kCS - 1)));   // the replicated records are written by one CTA, in rotation
+      const bool recorder = (rank == (q & (CS - 1)));   // the replicated records are written by one CTA, in rotation
       for (int l = 0; l < L - 1; ++l) {
         const int N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
         const float z = slice_forward(l, l == 0 ? xs : sm + lay.hfull[l - 1], l == 0 ? 0 : a.nd.sizes[l] * CP);
@@ -240,9 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           if (live) {
             const uint32_t off = 4u * (uint32_t)(lay.hfull[l] + (net * N + u0 + u) * CP + tc);
 #pragma unroll
-            for (int d = 0; d < kCS; ++d) st_remote(rbase[d] + off, hv);
+            for (int d = 0; d < CS; ++d) st_remote(rbase[d] + off, hv);
           }
-          cluster_arrive();
+          cluster_arrive<CS>();
         } else if (mine) {
           hs[t] = live ? hv : 0.0f;
         }
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           a.G[l][o] = act_grad_dyn(z, a.nd.act);
         }
         if (l == 0 && recorder && t < S3 * CP && col_ok) a.X[(row0 + tc) * S3 + tq] = xs[t];
-        if (l < L - 2) cluster_wait();
+        if (l < L - 2) cluster_wait<CS>();
         else __syncthreads();
         OPZ_PH(1);
       }
@@ -368,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     }
     x_next = (q >= 0 && t < S3 * CP && col_ok) ? __ldcg(a.X + (row0 + tc) * S3 + tq) : 0.0f;
   };
-  cluster_sync_all();  // the recorders' checkpoint / record stores are visible to the whole cluster
+  cluster_sync_all<CS>();  // the recorders' checkpoint / record stores are visible to the whole cluster
   if (t < S3 * CP) {
     const float l0 = col_ok ? loss_cotangent(a.n_steps, tq, tc) : 0.0f;
     lam[t] = l0;
@@ -383,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     for (int s = stages - 1; s >= 0; --s) {
       const int q = n * stages + s;
       const int64_t row0 = (int64_t)q * a.B + col0;
-      const bool recorder = (rank == (q & (kCS - 1)));
+      const bool recorder = (rank == (q & (CS - 1)));
       // land the prefetched records in shared memory, then prefetch the next right-hand side's
 #pragma unroll
       for (int l = 0; l < kMaxLayers - 1; ++l)
@@ -485,15 +495,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           st_remote_cols<CP>(off, acc);
         }
         OPZ_PH(11);
-        cluster_arrive();
+        cluster_arrive<CS>();
         flush();
-        cluster_wait();
+        cluster_wait<CS>();
         OPZ_PH(12);
         if (t < 3 * ULp * CP) {
           const int net = tq / ULp, u = tq - net * ULp;
           float sacc = 0.0f;
 #pragma unroll
-          for (int src = 0; src < kCS; ++src) sacc += rb[(src * 3 * ULp) * CP + t];
+          for (int src = 0; src < CS; ++src) sacc += rb[(src * 3 * ULp) * CP + t];
           const float dz = sacc * (sm + lay.gs[l - 1])[t];
           dzs[t] = dz;
           const int N = a.nd.sizes[l];
@@ -549,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
   if (a.gphys && rank == 0) mpp_param_flush(gp, a.gphys);   // every thread of the CTA takes part (zeros outside the face threads)
   if (timing)
     for (int i = 0; i < 24; ++i) g_phase_cycles[i] = (unsigned long long)ph[i];
-  cluster_sync_all();  // no CTA exits while a peer may still address its shared memory
+  cluster_sync_all<CS>();  // no CTA exits while a peer may still address its shared memory
 }
 
 }  // namespace cl
