@@ -343,7 +343,6 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
                 const uint32_t a0 = tmem + a_base;
                 const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25 || kin == 6);
-                const bool narrow = (kin == 4 || kin == 8) && (rows == 16u || rows == 32u || rows == 48u || rows == 64u);
                 // bias MMA: D += [1, 0, ..] x [b; don't care]: the block of rows / 2 x 8 halves right behind the weights; its
                 // second k-group reads what follows inside the stage (zeros or finite weights), multiplied by the zeros of A
                 const uint32_t bias_lo = blo + (rows / 2) * (uint32_t)kin * 2u;   // descriptor address units of 16 B
@@ -377,20 +376,20 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                     ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
                   }
                   __syncwarp();
-                } else if ((static_shape && !wait_h1) || narrow) {
-                  // hot path: one straight immediate-offset run.  Wide layers come here when their A operand is already complete;
-                  // narrow ones (<= 8 k-steps: at most two HF chunks) wait for those chunks up front.
-                  if (wait_h1)
-                    for (int h = 0; h * 4 < kin; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
+                } else if (static_shape && !wait_h1) {
+                  // hot path: the A operand is already complete; one straight immediate-offset run.  (A wider dispatch that also
+                  // covered the narrow layers' shapes, 12 instantiations in this region, cost construct_NN 3 % and gained the
+                  // narrow nets nothing: they are bound by the epilogue.)
                   ptx::tc_fence_after();
                   if (ptx::elect_one()) {
                     if (more) out_mmas(out_off, q1_net, q1_c, q1_ks);
-#define OPZ_ISSUE_CASE(R, K) else if (rows == (uint32_t)(R) && kin == (K)) issue_range<R, 0, K>(d, a0, blo, bhi, idesc);
-                    if (false) {}
-                    OPZ_ISSUE_CASE(64, 25) OPZ_ISSUE_CASE(64, 6) OPZ_ISSUE_CASE(16, 25) OPZ_ISSUE_CASE(16, 6)
-                    OPZ_ISSUE_CASE(64, 4) OPZ_ISSUE_CASE(48, 4) OPZ_ISSUE_CASE(32, 4) OPZ_ISSUE_CASE(16, 4)
-                    OPZ_ISSUE_CASE(64, 8) OPZ_ISSUE_CASE(48, 8) OPZ_ISSUE_CASE(32, 8) OPZ_ISSUE_CASE(16, 8)
-#undef OPZ_ISSUE_CASE
+                    if (rows == (uint32_t)kCW) {
+                      if (kin == 25) issue_range<kCW, 0, 25>(d, a0, blo, bhi, idesc);
+                      else issue_range<kCW, 0, 6>(d, a0, blo, bhi, idesc);
+                    } else {
+                      if (kin == 25) issue_range<16, 0, 25>(d, a0, blo, bhi, idesc);
+                      else issue_range<16, 0, 6>(d, a0, blo, bhi, idesc);
+                    }
                     ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
                     ptx::tc_commit2(bars + B_DFULL + buf);
                     ptx::tc_commit2(bars + ebar);
