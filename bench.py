@@ -138,7 +138,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, columns_per_gpu):
@@ -244,7 +244,29 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
             "note": "latency-bound: 18 columns x 46080 sequential right-hand sides; see DESIGN.md section 6"}
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """Everything any library writes to file descriptor 1 during the run (NCCL prints its version banner there when
+    NCCL_DEBUG is set on the box) goes to stderr; the one JSON line is written to the original stdout by emit()."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -373,16 +395,18 @@ def main():
     # ---- end-to-end through the host-buffer C ABI ----
     e2e = None
     if not args.no_e2e:
-        hx = torch.from_numpy(x0).pin_memory()
+        # two pinned host profile buffers used alternately: the caller's next window starts from the profiles the previous
+        # call returned, so they swap roles instead of being copied on the host (torchrun pins OMP_NUM_THREADS=1, which made
+        # that 403 MB host memcpy cost more than the host<->device copies it sat between)
+        hp = [torch.from_numpy(x0).pin_memory(), torch.empty((cols, 96), dtype=torch.float32).pin_memory()]
         hb = torch.from_numpy(bc).pin_memory()
-        ho = torch.empty((cols, 1, 96), dtype=torch.float32).pin_memory()
         import ctypes as C
 
         def e2e_step(i):
+            hx, ho = hp[i % 2], hp[(i + 1) % 2]
             opz.check(opz.lib.opz_rollout_forward(ctx._h, model._h, C.byref(pp), C.c_void_p(hx.data_ptr()),
                                                   C.c_void_p(hb.data_ptr()), cols, opz.SCHEME_RK4, dt, i * args.window * dt,
                                                   args.window, 0, prec, C.c_void_p(ho.data_ptr())))
-            hx.copy_(ho.view(cols, 96))  # the caller's next window starts from the returned profiles (host side)
 
         e2e_step(0)
         barrier()
@@ -456,7 +480,7 @@ def main():
         line["cpu_baseline"] = {"value": cb_cols * cb_steps / el, "unit": "column-timesteps/s", "cores": cores, "kind": "port",
                                 "sample": f"first {cb_cols} columns x {cb_steps} RK4 steps, oracle/nde_oracle.c (C port; Julia absent), "
                                           f"{el:.1f} s"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
