@@ -93,6 +93,7 @@ struct Args {
   int nc1;           // accumulator chunks of the first hidden layer
   int hpad[2];
   float b3[96];   // output-layer biases [net][32] (the hidden-layer biases ride in the weight tape)
+  float pk[18];   // products of the physics constants folded on the host (see PK_* below): one FFMA per use in the kernel
   uint32_t st_off[kMaxStages];
   uint32_t st_bytes[kMaxStages];
   uint32_t st_src[kMaxStages];
@@ -144,6 +145,11 @@ __device__ __forceinline__ void wait_phase(uint64_t* bars, int id, uint32_t phas
     ptx::mbar_wait(bars + id, phase & 1u);
   }
 }
+
+// Args::pk: the physics of this kernel works on raw cell differences d = x[i+1] - x[i]; the 1/Delta = Nz factor and the
+// feature scalings are folded into these constants (the FP32 parity path keeps the oracle's operation order)
+enum { PK_KBZ = 0, PK_EBZ, PK_KSA, PK_ESA, PK_KSB, PK_ESB, PK_C2, PK_R2, PK_CUN, PK_CVN, PK_CTN, PK_AU, PK_AV, PK_AT,
+       PK_CCU, PK_DCU, PK_CCV, PK_DCV };
 
 template <bool FP16, int ACT>
 __device__ __forceinline__ uint32_t pack_act(float a, float b) {
@@ -650,27 +656,28 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             for (int i = 0; i <= LV; ++i) {
               const int f = c0 + i;
               const bool interior = mpp && f >= 1 && f < kNz;
-              const float gu = (xu[i + 1] - xu[i]) * P.nzf;
-              const float gv = (xw[i + 1] - xw[i]) * P.nzf;
-              const float gT = (xT[i + 1] - xT[i]) * P.nzf;
-              // = richardson<true>, nu_of_ri<true>, nuT_of<true> of opz_device.cuh with the flag tests hoisted
-              const float Bz = P.cBz * (gT + P.eps);
-              const float sa = P.s_u * (gu + P.eps);
-              const float sb = P.s_v * (gv + P.eps);
+              const float du = xu[i + 1] - xu[i];
+              const float dv = xw[i + 1] - xw[i];
+              const float dT = xT[i + 1] - xT[i];
+              // = richardson<true>, nu_of_ri<true>, nuT_of<true> of opz_device.cuh with the flag tests hoisted and the constant
+              // factors folded (Args::pk): Bz = cBz (Nz dT + eps), sa = s_u (Nz du + eps), sb likewise
+              const float Bz = fmaf(a.pk[PK_KBZ], dT, a.pk[PK_EBZ]);
+              const float sa = fmaf(a.pk[PK_KSA], du, a.pk[PK_ESA]);
+              const float sb = fmaf(a.pk[PK_KSB], dv, a.pk[PK_ESB]);
               // flush-to-zero approximations without range fix-ups: 0 / 0 stays NaN (0 * inf), the exponent is clamped so that
               // e^{..} stays finite (nu -> nu0 in that tail to FP32 precision anyway)
               const float Ri = Bz * rcp_ftz(sa * sa + sb * sb);
-              const float nu = P.nu0 + P.nu_m * rcp_ftz(1.0f + ex2_ftz(fminf((Ri - P.Ric) * (P.two_inv_dRi * 1.4426950408889634f), 120.0f)));
-              const float sel = ca_du ? gu : gT;
+              const float nu = P.nu0 + P.nu_m * rcp_ftz(1.0f + ex2_ftz(fminf(fmaf(Ri, a.pk[PK_C2], a.pk[PK_R2]), 120.0f)));
+              const float sel = ca_du ? du : dT;   // Nz > 0: the raw difference has the gradient's sign
               const float nuT = (ca && !(sel > 0.0f)) ? P.kappa : nu * P.inv_Pr;
-              Du[i] = interior ? P.c_u * nu * gu : 0.0f;
-              Dv[i] = interior ? P.c_v * nu * gv : 0.0f;
-              DT[i] = interior ? P.c_T * nuT * gT : 0.0f;
+              Du[i] = interior ? a.pk[PK_CUN] * nu * du : 0.0f;
+              Dv[i] = interior ? a.pk[PK_CVN] * nu * dv : 0.0f;
+              DT[i] = interior ? a.pk[PK_CTN] * nuT * dT : 0.0f;
             }
 #pragma unroll
             for (int i = 0; i < LV; ++i) {
-              cu[i] = P.cor_u * (P.s_v * xw[i + 1] + P.mu_v);
-              cv[i] = P.cor_v * (P.s_u * xu[i + 1] + P.mu_u);
+              cu[i] = fmaf(a.pk[PK_CCU], xw[i + 1], a.pk[PK_DCU]);   //  cor_u (s_v v + mu_v)
+              cv[i] = fmaf(a.pk[PK_CCV], xu[i + 1], a.pk[PK_DCV]);   // -cor_v (s_u u + mu_u)
             }
           }
           float ts = tn;
@@ -711,12 +718,10 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
                 F[i] = f == 0 ? Fb[v] : (f == kNz ? Ft[v] : y - D[i]);
               }
             }
-            const float A = v == 0 ? P.A_u : (v == 1 ? P.A_v : P.A_T);
 #pragma unroll
             for (int i = 0; i < LV; ++i) {
-              float k = A * ((F[i + 1] - F[i]) * P.nzf);
-              if (v == 0) k += cu[i];
-              else if (v == 1) k -= cv[i];
+              const float dF = F[i + 1] - F[i];
+              const float k = v == 0 ? fmaf(a.pk[PK_AU], dF, cu[i]) : (v == 1 ? fmaf(a.pk[PK_AV], dF, cv[i]) : a.pk[PK_AT] * dF);
               const int idx = v * kNz + c0 + i;
               const int o = idx * kM + m, on = xn_idx(idx, m);
               const float xo = s_xn[on];
@@ -942,6 +947,14 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   if (!pl || pl->fp16 != fp16) { set_error("tensor-core path: model not prepared for this precision"); return OPZ_EINVAL; }
   Args a{};
   a.P = c.P;
+  {
+    const DevParams& P = c.P;
+    const double nzf = P.nzf, c2 = (double)P.two_inv_dRi * 1.4426950408889634;
+    const double pk[18] = {P.cBz * nzf, (double)P.cBz * P.eps, P.s_u * nzf, (double)P.s_u * P.eps, P.s_v * nzf, (double)P.s_v * P.eps,
+                           c2, -(double)P.Ric * c2, P.c_u * nzf, P.c_v * nzf, P.c_T * nzf, P.A_u * nzf, P.A_v * nzf, P.A_T * nzf,
+                           (double)P.cor_u * P.s_v, (double)P.cor_u * P.mu_v, -(double)P.cor_v * P.s_u, -(double)P.cor_v * P.mu_u};
+    for (int i = 0; i < 18; ++i) a.pk[i] = (float)pk[i];
+  }
   a.tape = pl->tape_dev;
   a.x0 = c.x0; a.bc = c.bc; a.out = c.out; a.B = c.B; a.scheme = c.scheme; a.dt = c.dt; a.t0 = c.t0;
   a.n_steps = c.n_steps; a.save_every = c.save_every; a.n_save = c.n_save;
