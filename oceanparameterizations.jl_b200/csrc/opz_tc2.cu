@@ -650,12 +650,12 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               xT[i] = s_xs[(2 * kNz + cell) * kM + m];
             }
             const bool mpp = P.flags & OPZ_FLAG_MPP;
-            const bool ca = P.flags & OPZ_FLAG_CA;
+            const bool ca = mpp && (P.flags & OPZ_FLAG_CA);
             const bool ca_du = P.flags & OPZ_FLAG_CA_SELECT_DUDZ;
 #pragma unroll
             for (int i = 0; i <= LV; ++i) {
               const int f = c0 + i;
-              const bool interior = mpp && f >= 1 && f < kNz;
+              const int jb = max(f - 1, 0);   // NN output (and its bias) on this face
               const float du = xu[i + 1] - xu[i];
               const float dv = xw[i + 1] - xw[i];
               const float dT = xT[i + 1] - xT[i];
@@ -667,12 +667,15 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               // flush-to-zero approximations without range fix-ups: 0 / 0 stays NaN (0 * inf), the exponent is clamped so that
               // e^{..} stays finite (nu -> nu0 in that tail to FP32 precision anyway)
               const float Ri = Bz * rcp_ftz(sa * sa + sb * sb);
-              const float nu = P.nu0 + P.nu_m * rcp_ftz(1.0f + ex2_ftz(fminf(fmaf(Ri, a.pk[PK_C2], a.pk[PK_R2]), 120.0f)));
+              const float nu_raw = P.nu0 + P.nu_m * rcp_ftz(1.0f + ex2_ftz(fminf(fmaf(Ri, a.pk[PK_C2], a.pk[PK_R2]), 120.0f)));
+              const float nu = mpp ? nu_raw : 0.0f;   // a select, not a factor: a NaN Ri must not leak when mPP is off
               const float sel = ca_du ? du : dT;   // Nz > 0: the raw difference has the gradient's sign
               const float nuT = (ca && !(sel > 0.0f)) ? P.kappa : nu * P.inv_Pr;
-              Du[i] = interior ? a.pk[PK_CUN] * nu * du : 0.0f;
-              Dv[i] = interior ? a.pk[PK_CVN] * nu * dv : 0.0f;
-              DT[i] = interior ? a.pk[PK_CTN] * nuT * dT : 0.0f;
+              // diffusive flux minus the output-layer bias: the total flux of an interior face is then y_raw - D (the values
+              // computed for a boundary face are discarded by the flux select below)
+              Du[i] = fmaf(a.pk[PK_CUN] * nu, du, -a.b3[jb]);
+              Dv[i] = fmaf(a.pk[PK_CVN] * nu, dv, -a.b3[32 + jb]);
+              DT[i] = fmaf(a.pk[PK_CTN] * nuT, dT, -a.b3[64 + jb]);
             }
 #pragma unroll
             for (int i = 0; i < LV; ++i) {
@@ -705,17 +708,16 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             float F[LV + 1];
             {
               const uint32_t ybase = tmem + lane_addr + kColY + (uint32_t)(v * 32);
-              uint32_t ylo[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, yhi[LV];
-              if (c0 > 0) ptx::tmem_ld8(ybase + (uint32_t)(c0 - 8), ylo);   // ylo[7] = output c0 - 1 (face c0)
+              uint32_t ylo = 0u, yhi[LV];
+              if (c0 > 0) ylo = ptx::tmem_ld1(ybase + (uint32_t)(c0 - 1));   // output c0 - 1 (face c0)
               if constexpr (LV == 16) ptx::tmem_ld16(ybase + (uint32_t)c0, yhi);
               else ptx::tmem_ld8(ybase + (uint32_t)c0, yhi);
               ptx::tmem_wait_ld();
               const float* D = v == 0 ? Du : (v == 1 ? Dv : DT);
 #pragma unroll
               for (int i = 0; i <= LV; ++i) {
-                const int f = c0 + i;
-                const float y = (i == 0 ? __uint_as_float(ylo[7]) : __uint_as_float(yhi[i == 0 ? 0 : i - 1])) + a.b3[v * 32 + max(f - 1, 0)];
-                F[i] = f == 0 ? Fb[v] : (f == kNz ? Ft[v] : y - D[i]);
+                const float y = i == 0 ? __uint_as_float(ylo) : __uint_as_float(yhi[i == 0 ? 0 : i - 1]);
+                F[i] = (i == 0 && c0 == 0) ? Fb[v] : ((i == LV && c0 + LV == kNz) ? Ft[v] : y - D[i]);
               }
             }
 #pragma unroll
