@@ -638,13 +638,16 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
           const long long t_a = PROF ? clock64() : 0;
           float Du[LV + 1], Dv[LV + 1], DT[LV + 1];   // diffusive part of the flux on faces c0 .. c0 + LV
           float cu[LV], cv[LV];                        // Coriolis terms of the owned cells
-          {
+          // one copy per first-cell index when a column is split over two threads (c0 = 0 or 16): cell clamps, bias indices
+          // and shared-memory offsets become immediates
+          auto phase_a = [&](auto c0c) {
+            const int c0s = decltype(c0c)::value >= 0 ? decltype(c0c)::value : c0;
             // branch-free on purpose (clamped loads, selects): the LV + 1 faces are independent dependency chains that the
             // scheduler can only interleave inside one basic block; values computed for a boundary face are discarded
             float xu[LV + 2], xw[LV + 2], xT[LV + 2];
 #pragma unroll
             for (int i = 0; i < LV + 2; ++i) {
-              const int cell = min(max(c0 - 1 + i, 0), kNz - 1);
+              const int cell = min(max(c0s - 1 + i, 0), kNz - 1);
               xu[i] = s_xs[cell * kM + m];
               xw[i] = s_xs[(kNz + cell) * kM + m];
               xT[i] = s_xs[(2 * kNz + cell) * kM + m];
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const bool ca_du = P.flags & OPZ_FLAG_CA_SELECT_DUDZ;
 #pragma unroll
             for (int i = 0; i <= LV; ++i) {
-              const int f = c0 + i;
+              const int f = c0s + i;
               const int jb = max(f - 1, 0);   // NN output (and its bias) on this face
               const float du = xu[i + 1] - xu[i];
               const float dv = xw[i + 1] - xw[i];
@@ -682,6 +685,12 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               cu[i] = fmaf(a.pk[PK_CCU], xw[i + 1], a.pk[PK_DCU]);   //  cor_u (s_v v + mu_v)
               cv[i] = fmaf(a.pk[PK_CCV], xu[i + 1], a.pk[PK_DCV]);   // -cor_v (s_u u + mu_u)
             }
+                    };
+          if constexpr (LV == 16) {
+            if (c0 == 0) phase_a(std::integral_constant<int, 0>{});
+            else phase_a(std::integral_constant<int, 16>{});
+          } else {
+            phase_a(std::integral_constant<int, -1>{});
           }
           float ts = tn;
           if (a.scheme == OPZ_RK4) ts = (st == 0) ? tn : (st == 3 ? tn + h : tn + h * 0.5f);
