@@ -106,22 +106,33 @@ def workload(columns, seed=0):
     return O, p, m, x0, bc
 
 
+def host_cores(CO):
+    """Threads the CPU legs use: all cores this process may run on (not OMP_NUM_THREADS, which torchrun pins to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, CO.num_procs()))
+
+
 def run_reference(args):
     """CPU arm: the C port of the reference's per-column solve on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import c_oracle as CO
-    cores = CO.max_threads()
+    # every core of the box, whatever OMP_NUM_THREADS says: torchrun exports OMP_NUM_THREADS=1 to its workers, which in
+    # round 1 made this arm a 1-core number at N > 1
+    cores = host_cores(CO)
     cols = args.ref_columns or 64 * cores
     O, p, m, x0, bc = workload(cols)
     dt = DT_SECONDS / p.tau
     x = x0
-    CO.rollout(x[:cores], bc[:cores], m, p, 2, dt, 1, 0)
+    CO.rollout(x[:cores], bc[:cores], m, p, 2, dt, 1, 0, n_threads=cores)
     times = []
     for i in range(args.warmup + args.steps):
         t = time.perf_counter()
-        out = CO.rollout(x, bc, m, p, 2, dt, args.window, 0, t0=i * args.window * dt)
+        out = CO.rollout(x, bc, m, p, 2, dt, args.window, 0, t0=i * args.window * dt, n_threads=cores)
         el = time.perf_counter() - t
         x = out[:, 0]
         if i >= args.warmup:
@@ -132,7 +143,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "NDE column-timesteps/sec at Nz=32", "value": value, "unit": "column-timesteps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, cols),
         "cpu_baseline": {"value": value, "unit": "column-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -143,12 +154,14 @@ def run_reference(args):
 
 def config_dict(args, columns_per_gpu):
     return {
-        "workload": "BASELINE configs[2]: ensemble of 2^20 columns per GPU sharded by column, 8-day rollout "
+        "workload": "BASELINE configs[2]: ensemble of 2^20 columns " + ("per GPU" if args.scaling == "weak" else "in total") +
+                    " sharded by column, 8-day rollout "
                     "(tau=691200 s), construct_NN 96-400-400-31 relu x3 random init (last layer x0.1), mPP + convective "
                     "adjustment (kappa=1), RK4 dt=30 s; one step = a window of RK4 timesteps of that rollout",
         "columns_per_gpu": columns_per_gpu, "nz": 32, "scheme": "RK4", "dt_seconds": DT_SECONDS,
         "window_timesteps": args.window, "precision": args.precision,
         "l2_policy": "inputs larger than L2 (profiles alone are 384 B x columns)",
+        "scaling": args.scaling,
         "parallelism": f"columns sharded over {args.gpus} GPU(s), no communication",
     }
 
@@ -186,11 +199,12 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
     buf = torch.zeros(P3 + 8, device=dev)
     lw = np.array([1, 1, 1, 5e-3, 5e-3, 5e-3], dtype=np.float32)
 
+    if dist is not None and ctx.comm_info[0] == 1:
+        opz.init_library_comm(ctx, dist)   # libopz's own NCCL communicator: the all-reduce happens inside opz_loss_grad_dev
+
     def step():
         opz.loss_grad_dev(model, pp, xd.data_ptr(), bd.data_ptr(), nb, BPTT_CASES, td.data_ptr(), lw, opz.SCHEME_RK4, dt,
                           BPTT_STEPS, BPTT_SAVE_EVERY, buf.data_ptr() + 4 * P3, buf.data_ptr())
-        if dist is not None:
-            dist.all_reduce(buf)
 
     def barrier():
         if dist is not None:
@@ -224,6 +238,8 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
         import torch as _torch
         from oracle import nde_oracle_torch as OT
         ns = BPTT_CPU_STEPS
+        from oracle import c_oracle as _CO
+        _torch.set_num_threads(host_cores(_CO))   # not torchrun's OMP_NUM_THREADS=1
         tg = target[:, :ns // BPTT_SAVE_EVERY + 1]
         t0 = _time.perf_counter()
         OT.loss_and_grad(x0, bc, m, p, O.SCHEME_RK4, dt, ns, BPTT_SAVE_EVERY, tg, lw, dtype=_torch.float32)
@@ -239,7 +255,9 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
             "gpu_launches_per_step": int(launches), "loss": loss, "grad_norm": gnorm,
             "finite": bool(np.isfinite(loss) and np.isfinite(gnorm)),
             "achieved_tflops": flops / (ms * 1e-3) / 1e12,
-            "collective": "none (1 GPU)" if dist is None else f"NCCL all-reduce(sum) of {P3 + 8} fp32 per step",
+            "collective": "none (1 GPU)" if dist is None else
+                          f"NCCL all-reduce(sum) of {P3} + 7 fp32 per step, enqueued INSIDE opz_loss_grad_dev (libopz binds NCCL; "
+                          f"{ctx.comm_info[2]} groups so far)",
             "cpu_baseline": cpu,
             "note": "latency-bound: 18 columns x 46080 sequential right-hand sides; see DESIGN.md section 6"}
 
@@ -265,6 +283,63 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
+def time_windows(opz, torch, dist, stream, ctx, model, pp, x0, bc_dev, cols, window_steps, prec, dt, steps, warmup,
+                 sampler=None):
+    """`warmup` untimed + `steps` timed windows of `window_steps` RK4 timesteps over `cols` device-resident columns,
+    continuing one rollout (ping-pong between two profile buffers).  CUDA events on the launching stream, barrier +
+    synchronize on both sides.  Returns (total_ms, per-launch ms, final profiles (device), launches, clocks)."""
+    xa = torch.from_numpy(x0[:cols]).cuda()
+    xb = torch.empty_like(xa)
+    bufs = [xa, xb]
+
+    def window(i):
+        opz.rollout_forward_dev(model, pp, bufs[i & 1].data_ptr(), bc_dev.data_ptr(), cols, opz.SCHEME_RK4, dt, window_steps, 0,
+                                bufs[(i + 1) & 1].data_ptr(), t0=i * window_steps * dt, precision=prec)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        window(i)
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    n0 = ctx.launch_count
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record(stream)
+    for k in range(steps):
+        window(warmup + k)
+        evs[k + 1].record(stream)
+    barrier()
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if sampler is not None else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(steps)]
+    return total_ms, kernel_ms, bufs[(warmup + steps) & 1], launches, clocks
+
+
+def max_over_ranks(torch, dist, *vals):
+    if dist is None:
+        return vals if len(vals) > 1 else vals[0]
+    tt = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out = tuple(float(v) for v in tt)
+    return out if len(vals) > 1 else out[0]
+
+
+def traffic_table():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures of this
+    command committed under profiles/ (profiles/traffic.json: key "<columns>x<window>:<precision>" -> bytes, source file).
+    The figure belongs to the kernel build and shape it was captured on; absent key -> null."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -272,7 +347,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--columns", type=int, default=1 << 20, help="columns per GPU")
+    ap.add_argument("--columns", type=int, default=1 << 20, help="columns per GPU (weak) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --columns per GPU (the headline line); strong: --columns in total, sharded over the GPUs "
+                         "(BASELINE configs[2]'s own wording).  At N > 1 the other mode is measured too and reported in the same line.")
     ap.add_argument("--window", type=int, default=0, help="RK4 timesteps per bench step (0 = per-precision default)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp16", "bf16"])
     ap.add_argument("--ref-columns", type=int, default=0)
@@ -280,11 +358,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bptt", action="store_true", help="skip the BPTT grad-steps/s leg")
     ap.add_argument("--no-small", action="store_true", help="skip the informational small-net leg")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the FP32 (CUDA-core parity path) leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     ap.add_argument("--bptt-steps", type=int, default=2, help="timed gradient steps of the BPTT leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
+        # the CPU arm is rank 0's alone: the other ranks of a torchrun launch exit without work
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
         if args.window == 0:
             args.window = 64
         run_reference(args)
@@ -315,82 +398,102 @@ def main():
     args.precision = prec_name
     if args.window == 0:
         args.window = 1 if prec_name == "fp32" else 16
-    cols = args.columns
-    O, p, m, x0, bc = workload(cols, seed=0)
+    # columns this rank steps: weak = --columns each; strong = its contiguous shard of --columns (no communication either way)
+    cols_weak = args.columns
+    lo, hi = opz.shard_range(args.columns, rank, world)
+    cols_strong = hi - lo
+    cols = cols_weak if args.scaling == "weak" else cols_strong
+    O, p, m, x0, bc = workload(cols_weak, seed=0)
     model = product_model(opz, m, ctx=ctx)
     pp = product_params(opz, p)
     dt = DT_SECONDS / p.tau
-
-    xa = torch.from_numpy(x0).cuda()
-    xb = torch.empty_like(xa)
     bcd = torch.from_numpy(bc).cuda()
-
-    def window(i, src, dst):
-        opz.rollout_forward_dev(model, pp, src.data_ptr(), bcd.data_ptr(), cols, opz.SCHEME_RK4, dt, args.window, 0,
-                                dst.data_ptr(), t0=i * args.window * dt, precision=prec)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ----
-    bufs = [xa, xb]
-    for i in range(args.warmup):
-        window(i, bufs[i & 1], bufs[(i + 1) & 1])
+    # ---- device-resident timing (the headline `value`) ----
     sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    n0 = ctx.launch_count
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    evs[0].record(stream)
-    for k in range(args.steps):
-        i = args.warmup + k
-        window(i, bufs[i & 1], bufs[(i + 1) & 1])
-        evs[k + 1].record(stream)
-    barrier()
-    launches = ctx.launch_count - n0
-    clocks = sampler.stop()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
-    final = bufs[(args.warmup + args.steps) & 1]
+    total_ms, kernel_ms, final, launches, clocks = time_windows(opz, torch, dist, stream, ctx, model, pp, x0, bcd, cols, args.window,
+                                                                prec, dt, args.steps, args.warmup, sampler)
     finite = bool(torch.isfinite(final).all().item())
 
-    # ---- the reference's production net on the same ensemble (96-50-20-31 mish, train_NDE.jl:103): informational ----
+    # ---- parity of the TIMED result: the columns of one period of the forcing sweep that the C oracle re-solves on the host
+    #      over exactly the (warmup + steps) x window timesteps the GPU just took (outside every timed region) ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import c_oracle as CO
+        n_done = (args.warmup + args.steps) * args.window
+        pick = np.arange(0, min(cols, 4096), 64)
+        got = final[torch.from_numpy(pick).cuda()].cpu().numpy()[:, None, :]
+        t = time.perf_counter()
+        ref = CO.rollout(x0[pick], bc[pick], m, p, 2, dt, n_done, 0, n_threads=host_cores(CO))
+        parity = {"err": float(O.profile_error(got, ref, 32)), "columns": int(pick.size), "timesteps": int(n_done),
+                  "norm": "max over columns and variables of max_k|x - ref| / max_k|ref| on the scaled final state (SURVEY 8d)",
+                  "against": "oracle/nde_oracle.c Float32 solve of the same columns (every 64th of the 4096-column forcing sweep)",
+                  "tolerance": 1e-4 if prec_name == "fp32" else 1e-2, "oracle_seconds": round(time.perf_counter() - t, 2),
+                  "full_rollout": "profiles/r02_parity_8day.json: the same comparison over all 23 040 steps (tests/test_gpu_long.py)"}
+
+    # ---- the other scaling mode (N > 1 only; at N = 1 the two are the same run) ----
+    other = None
+    if world > 1:
+        ocols = cols_strong if args.scaling == "weak" else cols_weak
+        o_ms, _, ofinal, _, _ = time_windows(opz, torch, dist, stream, ctx, model, pp, x0, bcd, ocols, args.window, prec, dt,
+                                             max(3, args.steps // 2), 3)
+        o_ms = max_over_ranks(torch, dist, o_ms / max(3, args.steps // 2))
+        tot_cols = args.columns if args.scaling == "weak" else args.columns * world
+        other = {"scaling": "strong" if args.scaling == "weak" else "weak", "columns_total": tot_cols,
+                 "columns_this_rank": ocols, "value": tot_cols * args.window / (o_ms * 1e-3), "unit": "column-timesteps/s",
+                 "ms_per_step": o_ms, "finite": bool(torch.isfinite(ofinal).all().item()),
+                 "note": "BASELINE configs[2] wording (2^20 columns in total sharded over the GPUs)" if args.scaling == "weak" else
+                         "fixed columns per GPU"}
+        del ofinal
+
+    # ---- FP32 leg: the CUDA-core parity path (<= 1e-4 contract) on the same workload, FP32-FMA roofline ----
+    fp32 = None
+    if not args.no_fp32 and prec_name != "fp32":
+        fcols = min(cols, 1 << 19)   # 201 MB of profiles: larger than L2
+        f_steps = 3
+        f_ms, f_k, ffinal, _, _ = time_windows(opz, torch, dist, stream, ctx, model, pp, x0, bcd, fcols, 1, opz.PREC_FP32, dt, f_steps, 1)
+        f_ms = max_over_ranks(torch, dist, f_ms / f_steps)
+        f_flops = fcols * STAGES * FLOP_PER_RHS
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        f_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        fp32 = {"kernel": "rollout_fp32_kernel (FP32 FMA on CUDA cores)", "value": fcols * world / (f_ms * 1e-3),
+                "unit": "column-timesteps/s", "columns_per_gpu": fcols, "window_timesteps": 1, "ms_per_step": f_ms,
+                "roofline": {"bound": "fp32_fma", "achieved": f_flops / (f_ms * 1e-3) / 1e12, "peak": f_peak, "unit": "TFLOP/s",
+                             "frac": f_flops / (f_ms * 1e-3) / 1e12 / f_peak,
+                             "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (max SM clock)"},
+                "finite": bool(torch.isfinite(ffinal).all().item())}
+        del ffinal
+
+    # ---- the reference's production net on the same ensemble (96-50-20-31 mish, train_NDE.jl:103) ----
     small = None
     if not args.no_small:
-        from oracle import nde_oracle as O2
-        ms_small = O2.make_model((96, 50, 20, 31), O2.ACT_MISH, seed=0, out_scale=0.1)
+        ms_small = O.make_model((96, 50, 20, 31), O.ACT_MISH, seed=0, out_scale=0.1)
         model_s = product_model(opz, ms_small, ctx=ctx)
-
-        def window_s(i, src, dst):
-            opz.rollout_forward_dev(model_s, pp, src.data_ptr(), bcd.data_ptr(), cols, opz.SCHEME_RK4, dt, args.window, 0,
-                                    dst.data_ptr(), t0=i * args.window * dt, precision=prec)
-        xs0 = torch.from_numpy(x0).cuda()
-        xs1 = torch.empty_like(xs0)
-        sb = [xs0, xs1]
-        for i in range(2):
-            window_s(i, sb[i & 1], sb[(i + 1) & 1])
-        barrier()
-        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        es0.record(stream)
-        for i in range(2, 2 + args.steps):
-            window_s(i, sb[i & 1], sb[(i + 1) & 1])
-        es1.record(stream)
-        barrier()
-        sms = es0.elapsed_time(es1) / args.steps
-        if dist is not None:
-            tts = torch.tensor([sms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tts, op=dist.ReduceOp.MAX)
-            sms = float(tts[0])
+        s_steps = max(3, min(args.steps, 10))
+        s_ms, _, sfinal, _, _ = time_windows(opz, torch, dist, stream, ctx, model_s, pp, x0, bcd, cols, args.window, prec, dt, s_steps, 3)
+        sms = max_over_ranks(torch, dist, s_ms / s_steps)
         fl_small = 2 * 3 * (96 * 50 + 50 * 20 + 20 * 31) + 1800
-        small = {"net": "96-50-20-31 mish x3 (train_NDE.jl:103)", "value": cols * world * args.window / (sms * 1e-3),
+        tot = cols * world if args.scaling == "weak" else args.columns
+        small = {"net": "96-50-20-31 mish x3 (train_NDE.jl:103)", "value": tot * args.window / (sms * 1e-3),
                  "unit": "column-timesteps/s", "ms_per_step": sms, "precision": prec_name,
                  "achieved_tflops": cols * args.window * STAGES * fl_small / (sms * 1e-3) / 1e12,
-                 "finite": bool(torch.isfinite(sb[(2 + args.steps) & 1]).all().item()),
-                 "note": "physics- and latency-bound (0.16 MFLOP per column-timestep): not the roofline kernel of this line"}
+                 "finite": bool(torch.isfinite(sfinal).all().item()),
+                 "note": "0.16 MFLOP per column-timestep: bound by the activation / physics instruction issue, not by the tensor pipe"}
+        if rank == 0 and not args.no_parity:
+            from oracle import c_oracle as CO
+            n_done = (3 + s_steps) * args.window
+            pick = np.arange(0, min(cols, 4096), 64)
+            got = sfinal[torch.from_numpy(pick).cuda()].cpu().numpy()[:, None, :]
+            ref = CO.rollout(x0[pick], bc[pick], ms_small, p, 2, dt, n_done, 0, n_threads=host_cores(CO))
+            small["parity_err"] = float(O.profile_error(got, ref, 32))
+            small["parity_timesteps"] = int(n_done)
         model_s.close()
-        del xs0, xs1
+        del sfinal
 
     # ---- end-to-end through the host-buffer C ABI ----
     e2e = None
@@ -398,8 +501,8 @@ def main():
         # two pinned host profile buffers used alternately: the caller's next window starts from the profiles the previous
         # call returned, so they swap roles instead of being copied on the host (torchrun pins OMP_NUM_THREADS=1, which made
         # that 403 MB host memcpy cost more than the host<->device copies it sat between)
-        hp = [torch.from_numpy(x0).pin_memory(), torch.empty((cols, 96), dtype=torch.float32).pin_memory()]
-        hb = torch.from_numpy(bc).pin_memory()
+        hp = [torch.from_numpy(x0[:cols]).pin_memory(), torch.empty((cols, 96), dtype=torch.float32).pin_memory()]
+        hb = torch.from_numpy(bc[:cols]).pin_memory()
         import ctypes as C
 
         def e2e_step(i):
@@ -416,7 +519,7 @@ def main():
             e2e_step(1 + k)
         barrier()
         e2e_ms = (time.perf_counter() - t) * 1e3 / e_steps
-        e2e = {"ms": e2e_ms, "h2d": int(x0.nbytes + bc.nbytes), "d2h": int(x0.nbytes)}
+        e2e = {"ms": e2e_ms, "h2d": int(x0[:cols].nbytes + bc[:cols].nbytes), "d2h": int(x0[:cols].nbytes)}
 
     # ---- BPTT leg: BASELINE configs[3], 18 cases sharded over the ranks, one NCCL all-reduce per step ----
     bptt = None
@@ -424,58 +527,67 @@ def main():
         bptt = run_bptt(args, opz, ctx, torch, dist, rank, world, stream)
 
     # ---- max over ranks ----
-    t_ms = total_ms
-    e_ms = e2e["ms"] if e2e else 0.0
-    if dist is not None:
-        tt = torch.tensor([t_ms, e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_ms, e_ms = float(tt[0]), float(tt[1])
+    t_ms, e_ms = max_over_ranks(torch, dist, total_ms, e2e["ms"] if e2e else 0.0)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     peaks, peak_kind = measured_peaks()
-    colsteps_per_step = cols * args.window * world
+    total_cols = cols * world if args.scaling == "weak" else args.columns
+    colsteps_per_step = total_cols * args.window
     value = colsteps_per_step * args.steps / (t_ms * 1e-3)
     flop_per_launch = cols * args.window * STAGES * FLOP_PER_RHS
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = flop_per_launch / (avg_kernel_ms * 1e-3) / 1e12
-    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one `ncu --set full` capture of this command with the
-    # default workload (profiles/r01_tc2_ncu_summary.txt: 448.4 MB + 364.7 MB; algorithmic 436.2 MB in + 402.7 MB out); the
-    # figure belongs to that shape only
-    traffic = 813111040 if (cols == (1 << 20) and args.window == 16 and prec_name == "fp16") else None
+    if prec_name == "fp32":
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        bound, peak_source = "fp32_fma", f"148 SMs x 128 FMA lanes x 2 x {sm_mhz:.0f} MHz (max SM clock)"
+        kernel_name = "rollout_fp32_kernel (FP32 FMA on CUDA cores)"
+    else:
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        bound = "tensor"
+        peak_source = (f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)" if peak_kind == "measured" else
+                       "of fallback: MEASURED_PEAKS.json absent, B200_PROFILING.md's stated fallback")
+        kernel_name = "rollout_tc2_kernel (tcgen05 cta_group::2, " + prec_name + " operands, fp32 accumulate)"
+    tr = traffic_table().get(f"{cols}x{args.window}:{prec_name}")
     line = {
         "metric": "NDE column-timesteps/sec at Nz=32", "value": value, "unit": "column-timesteps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": args.scaling, "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[prec_name], "data": "synthetic",
         "config": config_dict(args, cols),
         "clocks": clocks, "gpu_launches": int(launches), "finite": finite,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu)", "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "kernel": ("rollout_fp32_kernel" if prec_name == "fp32" else "rollout_tc2_kernel (tcgen05 cta_group::2, " + prec_name + " operands, fp32 accumulate)"),
-                     "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_kernel_ms,
-                     "fp32_fma_peak_tflops_at_max_clock": 74.4},
+        "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": tr["bytes"] if tr else None, "traffic_unit": "bytes of DRAM traffic per launch (ncu)",
+                     "traffic_source": tr["source"] if tr else None, "peak_source": peak_source, "kernel": kernel_name,
+                     "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_kernel_ms},
     }
+    if parity:
+        line["parity_err"] = parity["err"]
+        line["parity"] = parity
     if e2e:
         line["e2e"] = {"value": colsteps_per_step / (e_ms * 1e-3), "unit": "column-timesteps/s",
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e_ms}
+    if other:
+        line["other_scaling"] = other
+    if fp32:
+        line["fp32"] = fp32
     if bptt:
         line["bptt"] = bptt
     if small:
         line["small_net"] = small
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle as CO
-        cores = CO.max_threads()
+        cores = host_cores(CO)
         cb_cols = 64 * cores
         t = time.perf_counter()
-        CO.rollout(x0[:cb_cols], bc[:cb_cols], m, p, 2, dt, 4, 0)  # pilot: sizes the sample to ~12 s
+        CO.rollout(x0[:cb_cols], bc[:cb_cols], m, p, 2, dt, 4, 0, n_threads=cores)  # pilot: sizes the sample to ~12 s
         pilot = time.perf_counter() - t
         cb_steps = int(min(1024, max(8, 4 * 12.0 / max(pilot, 1e-3))))
         t = time.perf_counter()
-        CO.rollout(x0[:cb_cols], bc[:cb_cols], m, p, 2, dt, cb_steps, 0)
+        CO.rollout(x0[:cb_cols], bc[:cb_cols], m, p, 2, dt, cb_steps, 0, n_threads=cores)
         el = time.perf_counter() - t
         line["cpu_baseline"] = {"value": cb_cols * cb_steps / el, "unit": "column-timesteps/s", "cores": cores, "kind": "port",
                                 "sample": f"first {cb_cols} columns x {cb_steps} RK4 steps, oracle/nde_oracle.c (C port; Julia absent), "

@@ -10,8 +10,11 @@
  *   - the caller owns all host buffers; Julia column-major `3Nz x Nt x B` is C `[B][Nt][3Nz]`;
  *   - host-pointer calls are blocking (stream-synchronised before return);  `_dev` calls take
  *     DEVICE pointers, enqueue on the context's stream and return without synchronising;
- *   - one opz_ctx drives one GPU (one process per GPU); there is NO CPU fallback: creating a
- *     context on a machine without an sm_100 device fails with OPZ_ENODEV.
+ *   - one opz_ctx drives one GPU (one process or host thread per GPU); there is NO CPU fallback:
+ *     creating a context on a machine without an sm_100 device fails with OPZ_ENODEV;
+ *   - forward ensembles shard by column with no communication; the training step's one exchange (the
+ *     sum of the NN-parameter gradient over the case shards) happens INSIDE opz_loss_grad* once the
+ *     context carries a communicator (opz_ctx_comm_init / opz_ctx_comm_adopt below).
  */
 #ifndef OPZ_H
 #define OPZ_H
@@ -31,6 +34,7 @@ extern "C" {
 #define OPZ_ECUDA (-3)   /* CUDA runtime error (message has the detail) */
 #define OPZ_ENOMEM (-4)  /* device allocation failed */
 #define OPZ_EUNSUP (-5)  /* configuration not supported by the requested precision path */
+#define OPZ_ENCCL (-6)   /* NCCL could not be loaded, or a NCCL call failed (message has the detail) */
 
 /* conditions NamedTuple -> flag bits (wind_mixing/src/NDE_training.jl:205-207) */
 #define OPZ_FLAG_MPP (1u << 0)                  /* modified_pacanowski_philander */
@@ -107,6 +111,29 @@ int opz_ctx_set_stream(opz_ctx* ctx, void* cuda_stream);
 int opz_ctx_synchronize(opz_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t opz_ctx_launch_count(const opz_ctx* ctx);
+/* Destroying a context that still has live models is deferred until the last of them is destroyed (host garbage
+ * collectors and finalizers give no destruction order): the handle must not be used after opz_ctx_destroy either way. */
+
+/* ---- multi-GPU: the gradient all-reduce of the training step, inside the boundary --------------------------------
+ * Replaces the mean over simulations of loss_NDE / loss_gradient_NDE (NDE_training.jl:290-301) when the simulations
+ * are sharded over GPUs: rank r passes ITS cases (opz_shard_range) with B_total = the global count, and
+ * opz_loss_grad[_mpp][_dev] returns the global loss_out / grad_out / grad_mpp_out on every rank (NCCL all-reduce, sum,
+ * FP32, enqueued on the context's stream behind the BPTT kernels; NVLink / NVSwitch between the GPUs of a node).
+ * NCCL is bound at run time (libnccl.so.2, or the path in OPZ_NCCL_LIB): single-GPU use needs no NCCL.
+ *   rank 0:      opz_comm_get_unique_id(id)  -> ship the 128 bytes to the other ranks by any host means
+ *   every rank:  opz_ctx_comm_init(ctx, id, n_ranks, rank)        (collective: blocks until all ranks have called)
+ * or hand over a communicator the host already owns (ncclComm_t):  opz_ctx_comm_adopt(ctx, comm, n_ranks, rank).
+ * A rank that owns no case (B = 0) still calls opz_loss_grad* and contributes zeros. */
+#define OPZ_COMM_ID_BYTES 128
+int opz_comm_get_unique_id(void* id_out /* OPZ_COMM_ID_BYTES */);
+int opz_ctx_comm_init(opz_ctx* ctx, const void* id, int n_ranks, int rank);
+int opz_ctx_comm_adopt(opz_ctx* ctx, void* nccl_comm, int n_ranks, int rank);
+int opz_ctx_comm_destroy(opz_ctx* ctx);
+/* any output may be NULL; collectives = all-reduce groups enqueued so far */
+int opz_ctx_comm_info(const opz_ctx* ctx, int* n_ranks, int* rank, int64_t* collectives);
+int opz_comm_nccl_version(int* version);
+/* contiguous shard [lo, hi) of B cases / columns owned by `rank`: the first B % n_ranks ranks own one more */
+int opz_shard_range(int64_t B, int rank, int n_ranks, int64_t* lo, int64_t* hi);
 
 /* ---- model: three Flux Chains uw_NN, vw_NN, wT_NN of one architecture ----------------------
  * Replaces `Flux.destructure(NN)` / `re(weights)` (NDE_training.jl:11-13,62-64;
@@ -152,7 +179,9 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
  * target[B][n_save][3nz]; loss_w[6] = weights of (u, v, T, du/dz, dv/dz, dT/dz) MSE terms
  * (loss.jl:1-42); loss_out[7] = total then the six weighted components; grad_out[3P].
  * The sums are over THIS context's B columns with the mean taken over `B_total` simulations
- * (pass B_total = B on one GPU); multi-GPU callers all-reduce grad_out and loss_out (sum). */
+ * (pass B_total = B on one GPU).  With a communicator on the context (opz_ctx_comm_init) the outputs are
+ * all-reduced (sum) inside the call and every rank receives the global loss and gradient; without
+ * one, multi-GPU callers all-reduce grad_out and loss_out themselves. */
 int opz_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
                   const float* bc, int64_t B, int64_t B_total, int scheme, float dt_nd, float t0,
                   int n_steps, int save_every, const float* target, const float* loss_w,
@@ -171,7 +200,7 @@ int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, con
  * that factor stays on the host).  The reference's DE is this library's right-hand side with a
  * zero-weight model and flags OPZ_FLAG_MPP | OPZ_FLAG_RI_EPS | OPZ_FLAG_BC_MINUS_SCALE0; with a
  * non-zero model the NN fluxes are simply part of the differentiated solve.  Needs OPZ_FLAG_MPP.
- * Obtained in the same backward sweep as grad_out; multi-GPU callers all-reduce it with grad_out. */
+ * Obtained in the same backward sweep as grad_out and all-reduced with it. */
 int opz_loss_grad_mpp(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0,
                       const float* bc, int64_t B, int64_t B_total, int scheme, float dt_nd,
                       float t0, int n_steps, int save_every, const float* target,

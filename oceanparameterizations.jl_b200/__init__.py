@@ -7,4 +7,4 @@ from . import _lib  # noqa: F401  (fails loudly if libopz.so is missing)
 from ._lib import *  # noqa: F401,F403
 from .api import *  # noqa: F401,F403
 from . import api  # noqa: F401
-from .parallel import shard_range, make_allreduce_comm, sharded_loss_grad  # noqa: F401
+from .parallel import shard_range, make_allreduce_comm, sharded_loss_grad, init_library_comm, HostComm  # noqa: F401

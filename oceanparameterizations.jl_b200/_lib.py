@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libopz.so")
 
 # ---- constants mirrored from include/opz.h -------------------------------------------------------
-OPZ_OK, OPZ_EINVAL, OPZ_ENODEV, OPZ_ECUDA, OPZ_ENOMEM, OPZ_EUNSUP = 0, -1, -2, -3, -4, -5
+OPZ_OK, OPZ_EINVAL, OPZ_ENODEV, OPZ_ECUDA, OPZ_ENOMEM, OPZ_EUNSUP, OPZ_ENCCL = 0, -1, -2, -3, -4, -5, -6
+COMM_ID_BYTES = 128
 FLAG_MPP = 1 << 0
 FLAG_CA = 1 << 1
 FLAG_CA_SELECT_DUDZ = 1 << 2
@@ -31,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "opz_model_get_weights", "opz_model_set_weights_dev", "opz_model_n_params", "opz_model_destroy",
     "opz_rhs", "opz_rollout_forward", "opz_rollout_forward_dev", "opz_loss_grad", "opz_loss_grad_dev", "opz_loss_grad_mpp", "opz_loss_grad_mpp_dev", "opz_profile_diagnostics", "opz_flux_loss_grad",
     "opz_mlp_forward",
+    "opz_comm_get_unique_id", "opz_ctx_comm_init", "opz_ctx_comm_adopt", "opz_ctx_comm_destroy", "opz_ctx_comm_info",
+    "opz_comm_nccl_version", "opz_shard_range",
 )
 
 
@@ -92,6 +95,13 @@ def _load() -> C.CDLL:
     lib.opz_profile_diagnostics.argtypes = [vp, vp, P, fp, fp, i64, i32, f32, f32, fp, fp, fp, fp, fp]
     lib.opz_flux_loss_grad.argtypes = [vp, vp, P, i32, fp, fp, fp, i64, f32, fp, fp]
     lib.opz_mlp_forward.argtypes = [vp, vp, i32, fp, i64, i32, fp]
+    lib.opz_comm_get_unique_id.argtypes = [vp]
+    lib.opz_ctx_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.opz_ctx_comm_adopt.argtypes = [vp, vp, i32, i32]
+    lib.opz_ctx_comm_destroy.argtypes = [vp]
+    lib.opz_ctx_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    lib.opz_comm_nccl_version.argtypes = [C.POINTER(C.c_int)]
+    lib.opz_shard_range.argtypes = [i64, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)  # raises AttributeError if the symbol is not exported
         if name not in ("opz_last_error", "opz_ctx_launch_count", "opz_model_n_params"):

@@ -162,14 +162,40 @@ def _f32(a, shape=None) -> np.ndarray:
     return a
 
 
+def comm_unique_id() -> bytes:
+    """opz_comm_get_unique_id: the 128-byte NCCL id rank 0 creates and ships to the other ranks by any host means."""
+    buf = C.create_string_buffer(L.COMM_ID_BYTES)
+    L.check(L.lib.opz_comm_get_unique_id(buf))
+    return buf.raw
+
+
 class Context:
-    """opz_ctx: one GPU, one stream."""
+    """opz_ctx: one GPU, one stream; optionally one rank of the training step's communicator."""
 
     def __init__(self, device: int = 0):
         h = C.c_void_p()
         L.check(L.lib.opz_ctx_create(device, C.byref(h)))
         self._h = h
         self.device = device
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        """opz_ctx_comm_init (collective over all ranks): afterwards loss_grad* return the GLOBAL loss and gradient."""
+        if len(unique_id) != L.COMM_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        L.check(L.lib.opz_ctx_comm_init(self._h, C.c_char_p(unique_id), int(n_ranks), int(rank)))
+
+    def comm_adopt(self, nccl_comm_ptr: int, n_ranks: int, rank: int):
+        L.check(L.lib.opz_ctx_comm_adopt(self._h, C.c_void_p(nccl_comm_ptr), int(n_ranks), int(rank)))
+
+    def comm_destroy(self):
+        L.check(L.lib.opz_ctx_comm_destroy(self._h))
+
+    @property
+    def comm_info(self):
+        """(n_ranks, rank, all-reduce groups enqueued so far)"""
+        n, r, c = C.c_int(), C.c_int(), C.c_int64()
+        L.check(L.lib.opz_ctx_comm_info(self._h, C.byref(n), C.byref(r), C.byref(c)))
+        return n.value, r.value, c.value
 
     def set_stream(self, cuda_stream_ptr: int):
         L.check(L.lib.opz_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
@@ -528,12 +554,25 @@ _model_cache: dict = {}
 
 
 def _model_for(uw_NN, vw_NN, wT_NN, Nz) -> NDEModel:
-    key = (id(uw_NN), id(vw_NN), id(wT_NN), Nz)
+    """Device model for three host Chains.  Cached per ARCHITECTURE (layer sizes, activation, Nz, context) — never per
+    object identity: `NDE()` rebuilds its Chains from `p` on every call (NDE_training.jl:62-64) and CPython reuses freed
+    addresses, so an id()-keyed cache would silently evaluate with the weights of an earlier call.  The weights are
+    uploaded on every call (<= 2.5 MB), hit or miss."""
+    ctx = default_context()
+    if not (uw_NN.sizes == vw_NN.sizes == wT_NN.sizes and uw_NN.activation == vw_NN.activation == wT_NN.activation):
+        raise ValueError("the three nets must share one architecture")
+    key = (tuple(uw_NN.sizes), uw_NN.activation, int(Nz), id(ctx))
     m = _model_cache.get(key)
+    if m is not None and (m._h is None or m.ctx is not ctx or m.ctx._h is None):
+        m = None
     if m is None:
         if len(_model_cache) > 8:
+            for old in _model_cache.values():
+                old.close()
             _model_cache.clear()
-        m = _model_cache[key] = NDEModel(uw_NN, vw_NN, wT_NN, Nz)
+        m = _model_cache[key] = NDEModel(uw_NN, vw_NN, wT_NN, Nz, ctx=ctx)
+    else:
+        m.set_weights(np.concatenate([destructure(n)[0] for n in (uw_NN, vw_NN, wT_NN)]))
     return m
 
 
@@ -627,11 +666,18 @@ def train_NDE(uw_NN, vw_NN, wT_NN, 𝒟train, tsteps, timestepper, optimizers, e
               ν_m=1e-1, ΔRi=1.0, Riᶜ=0.25, Pr=1.0, κ=10.0, f=1e-4, α=2e-4, g=9.80665,
               modified_pacanowski_philander=False, convective_adjustment=False, smooth_NN=False, smooth_Ri=False,
               train_gradient=False, zero_weights=False, gradient_scaling=5e-3, training_fractions=None,
-              diurnal=False, Q_diurnal=None, cb=None, comm=None):
+              diurnal=False, Q_diurnal=None, cb=None, comm=None, ctx: Optional[Context] = None, _loss_grad_fn=None):
     """NDE_training.jl:167-374 with the data already in memory (the JLD2 loader is out of scope):
     𝒟train carries .uvT_scaled [3Nz, n_steps*n_sim], .t, .uw/.vw/.wT (.scaled, .z), .scalings, .n_simulations.
     Loss + exact discrete-adjoint gradient come from libopz; ADAM and the callback stay on the host.
-    `comm`, if given, is a callable all-reducing (sum) a numpy array in place across ranks."""
+
+    Multi-GPU (one process per GPU, every rank calls train_NDE with the SAME data): the n_sim simulations are sharded
+    over the ranks (shard_range), every rank passes B_total = n_sim, and the shard losses / gradients are summed
+      * inside libopz when `ctx` carries a communicator (Context.comm_init: NCCL all-reduce behind the BPTT kernels), or
+      * by `comm` (parallel.make_allreduce_comm: an object with .rank, .world and comm(buf) summing a float32 numpy
+        buffer in place), the host-side route used by the gloo tests.
+    Every rank then takes the identical ADAM step.  `_loss_grad_fn` (tests only) stands in for the libopz call."""
+    from .parallel import shard_range
     assert not (modified_pacanowski_philander and convective_adjustment)
     if zero_weights:
         assert modified_pacanowski_philander
@@ -658,13 +704,25 @@ def train_NDE(uw_NN, vw_NN, wT_NN, 𝒟train, tsteps, timestepper, optimizers, e
             bc[i, 6] = Q_diurnal[i]
     params = make_params(constants, scalings, training_flags(conditions))
     n_steps, save_every, t0 = _steps_from_ts(t_train, timestepper.dt)
-    model = NDEModel(uw_NN, vw_NN, wT_NN, Nz)
+    model = None
+    lib_world, lib_rank = 1, 0
+    if _loss_grad_fn is None:
+        model = NDEModel(uw_NN, vw_NN, wT_NN, Nz, ctx=ctx)
+        lib_world, lib_rank, _ = model.ctx.comm_info
+    if lib_world > 1 and comm is not None:
+        raise ValueError("train_NDE: the context already carries a communicator; do not pass `comm` as well")
+    rank, world = (lib_rank, lib_world) if lib_world > 1 else ((comm.rank, comm.world) if comm is not None else (0, 1))
+    lo, hi = shard_range(n_sim, rank, world)
+    x0_s, bc_s, target_s = x0[lo:hi], bc[lo:hi], target[lo:hi]
 
     def evaluate(w, lw):
-        model.set_weights(w)
-        total, comps, grad = loss_grad(model, params, x0, bc, target, lw, timestepper.scheme, timestepper.dt,
-                                       n_steps, save_every, t0=t0, precision=timestepper.precision)
-        if comm is not None:
+        if _loss_grad_fn is not None:
+            total, comps, grad = _loss_grad_fn(w, x0_s, bc_s, target_s, lw, n_sim)
+        else:
+            model.set_weights(w)
+            total, comps, grad = loss_grad(model, params, x0_s, bc_s, target_s, lw, timestepper.scheme, timestepper.dt,
+                                           n_steps, save_every, t0=t0, B_total=n_sim, precision=timestepper.precision)
+        if comm is not None and world > 1:
             buf = np.concatenate([[total], comps, grad]).astype(np.float32)
             comm(buf)
             total, comps, grad = float(buf[0]), buf[1:7], buf[7:]
@@ -688,7 +746,8 @@ def train_NDE(uw_NN, vw_NN, wT_NN, 𝒟train, tsteps, timestepper, optimizers, e
                 if cb is not None:
                     cb(weights, total, comps, lw)
                 weights = opt.apply(weights, grad)
-    model.close()
+    if model is not None:
+        model.close()
     out = tuple(NN_constructions.__dict__[k](weights[NN_ranges.__dict__[k]]) for k in ("uw", "vw", "wT"))
     return out + (history,)
 
@@ -702,6 +761,8 @@ def optimise_modified_pacanowski_philander(model: NDEModel, params: L.OpzParams,
     `model` carries the NN weights that stay fixed (an all-zero model reproduces the reference's NN-free DE, :1-33);
     `params` supplies everything else and is updated in place.  `comm(buf)` sums a float32 buffer over ranks (multi-GPU).
     Returns (p[5], history of total losses)."""
+    if comm is not None and model.ctx.comm_info[0] > 1:
+        raise ValueError("the context already carries a communicator (results are reduced inside libopz); do not pass `comm`")
     p0 = np.array([params.nu0, params.nu_m, params.dRi, params.Ric, params.Pr], dtype=np.float64)
     if np.any(p0 <= 0):
         raise ValueError("the initial parameters must be positive (they are the scalings)")

@@ -96,10 +96,10 @@ int opz_ctx_create(int device, opz_ctx** out) {
   return OPZ_OK;
 }
 
-int opz_ctx_destroy(opz_ctx* ctx) {
-  if (!ctx) return OPZ_OK;
+static void ctx_free(opz_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_release(ctx);
   bptt_release(ctx);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
@@ -109,6 +109,15 @@ int opz_ctx_destroy(opz_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int opz_ctx_destroy(opz_ctx* ctx) {
+  if (!ctx) return OPZ_OK;
+  if (ctx->live_models > 0) {   // models still point at this context: the last opz_model_destroy frees it
+    ctx->destroy_requested = true;
+    return OPZ_OK;
+  }
+  ctx_free(ctx);
   return OPZ_OK;
 }
 
@@ -172,6 +181,7 @@ int opz_model_create(opz_ctx* ctx, int nz, int n_sizes, const int* sizes, int ac
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { cudaFree(m->w_dev); delete m; return cuda_fail(e, "weights H2D sync"); }
   m->tc_pack_valid = false;
+  ctx->live_models += 1;
   *out = m;
   return OPZ_OK;
 }
@@ -207,9 +217,11 @@ int opz_model_destroy(opz_model* m) {
   if (!m) return OPZ_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
-  tc_model_release(m);
+  tc2_model_release(m);
   if (m->w_dev) cudaFree(m->w_dev);
+  opz_ctx* ctx = m->ctx;
   delete m;
+  if (--ctx->live_models == 0 && ctx->destroy_requested) ctx_free(ctx);
   return OPZ_OK;
 }
 
@@ -264,9 +276,12 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
       return OPZ_EUNSUP;
     }
     opz_model* mm = const_cast<opz_model*>(m);  // the packed weight tape is a cache
-    if ((!m->tc_pack_valid || m->tc_pack_precision != precision) && (rc = tc_model_prepare(mm, precision))) return rc;
-    mm->tc_pack_precision = precision;
-    return tc_rollout(ctx, m, c, precision);
+    if (!m->tc_pack_valid || m->tc_pack_precision != precision) {
+      if ((rc = tc2_model_prepare(mm, precision))) return rc;
+      mm->tc_pack_valid = true;
+      mm->tc_pack_precision = precision;
+    }
+    return tc2_rollout(ctx, m, c, precision);
   }
   set_error("unknown precision");
   return OPZ_EINVAL;
@@ -368,7 +383,11 @@ static int loss_grad_dev_impl(opz_ctx* ctx, const opz_model* m, const opz_params
   c.loss_out = loss_out;
   c.grad_out = grad_out;
   c.gphys_out = gphys_out;
-  return fp32_loss_grad(ctx, m, c);
+  if ((rc = fp32_loss_grad(ctx, m, c))) return rc;
+  // the one exchange of the training step: sum of the shard gradients and loss components over the ranks
+  float* bufs[3] = {grad_out, loss_out, gphys_out};
+  const size_t counts[3] = {3 * (size_t)m->nd.P, 7, gphys_out ? 5u : 0u};
+  return comm_allreduce_sum(ctx, bufs, counts, 3);
 }
 
 int opz_loss_grad_dev(opz_ctx* ctx, const opz_model* m, const opz_params* p, const float* x0, const float* bc,
@@ -396,7 +415,8 @@ static int loss_grad_host_impl(opz_ctx* ctx, const opz_model* m, const opz_param
   int rc = check_common(ctx, m, p);
   if (rc) return rc;
   if ((rc = check_rollout(B, scheme, n_steps, save_every))) return rc;
-  if (!x0 || !bc || !target || !loss_w || !loss_out || !grad_out) { set_error("null buffer"); return OPZ_EINVAL; }
+  // a rank that owns no case (B == 0) may pass null data pointers, exactly as in the _dev variant
+  if ((B > 0 && (!x0 || !bc || !target)) || !loss_w || !loss_out || !grad_out) { set_error("null buffer"); return OPZ_EINVAL; }
   if (save_every <= 0) { set_error("opz_loss_grad needs save_every > 0"); return OPZ_EINVAL; }
   OPZ_CUDA(cudaSetDevice(ctx->device));
   const size_t S = 3 * (size_t)m->nz;

@@ -22,6 +22,14 @@ struct opz_ctx {
   // default stream, which cannot be captured) and the cached graph executables
   cudaStream_t capture_stream = nullptr;
   void* bptt_cache = nullptr;
+  // lifetime: models keep their context alive (opz_ctx_destroy is deferred until the last model is gone)
+  int live_models = 0;
+  bool destroy_requested = false;
+  // the training step's collective (opz_comm.cu): ncclComm_t of this rank, or null
+  void* nccl_comm = nullptr;
+  bool owns_comm = false;
+  int comm_ranks = 1, comm_rank = 0;
+  int64_t collectives = 0;
 };
 
 struct opz_model {
@@ -30,13 +38,10 @@ struct opz_model {
   opz::NetDesc nd{};
   int max_hidden = 0;
   float* w_dev = nullptr;        // [3P] FP32, Flux.destructure order, nets uw|vw|wT
-  // tensor-core path: weights re-packed as BF16 (hi, lo) images of the shared-memory B tiles
-  void* tc_pack = nullptr;
-  size_t tc_pack_bytes = 0;
+  // tensor-core path (opz_tc2.cu): the weights re-packed as the stage-ordered 16-bit tape; a cache of w_dev
   bool tc_pack_valid = false;
   int tc_pack_precision = -1;    // OPZ_PREC_* the tape was packed for
-  void* tc_plan = nullptr;       // opaque (opz_tc.cu)
-  void* tc2_pack = nullptr;      // second-generation kernel (opz_tc2.cu): stage-ordered tape + biases
+  void* tc2_pack = nullptr;
   size_t tc2_pack_bytes = 0;
   void* tc2_plan = nullptr;
 };
@@ -53,6 +58,10 @@ int cuda_fail(cudaError_t e, const char* what);  // records the message, returns
   } while (0)
 
 int ensure_scratch(opz_ctx* ctx, int slot, size_t bytes, void** out);
+
+// opz_comm.cu: in-place sum over the ranks of up to n device buffers, one NCCL group on ctx->stream (no-op for 1 rank)
+int comm_allreduce_sum(opz_ctx* ctx, float* const* bufs, const size_t* counts, int n);
+void comm_release(opz_ctx* ctx);
 
 struct RolloutCall {
   DevParams P;
@@ -88,12 +97,8 @@ void bptt_release(opz_ctx* ctx);
 int fp32_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const DevParams& P, int which_net, const float* x, const float* bc,
                         const float* flux_target, int64_t N, float gradient_scaling, float* loss_out_host, float* grad_out);
 
-// tcgen05 tensor-core path (opz_tc.cu)
-int tc_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights
-void tc_model_release(opz_model* m);
-int tc_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
-// second generation (opz_tc2.cu): CTA pairs, chunk-sized weight stages, level-parallel physics; tc_* dispatch to it
-int tc2_model_prepare(opz_model* m, int precision);
+// tcgen05 tensor-core path (opz_tc2.cu): CTA pairs, chunk-sized weight stages, level-parallel physics
+int tc2_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights
 void tc2_model_release(opz_model* m);
 int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
 

@@ -5,8 +5,10 @@
     components (the loss is a mean over simulations, wind_mixing/src/NDE_training.jl:293-295, so
     every rank normalises by the GLOBAL batch `B_total` and the all-reduce is a plain sum).
 
-The collective itself is `torch.distributed.all_reduce` (NCCL over NVLink on GPUs, gloo in the CPU
-tests); nothing here touches the numerics.
+On GPUs the collective lives INSIDE libopz (include/opz.h: opz_ctx_comm_init; api.Context.comm_init /
+init_library_comm below): opz_loss_grad* return the already-reduced global loss and gradient, which is what a
+`ccall` user gets too.  The host-side route in this file (`make_allreduce_comm`: torch.distributed.all_reduce,
+gloo in the CPU tests) carries the same shard + global-B_total contract for hosts that own their collective.
 """
 from __future__ import annotations
 
@@ -25,20 +27,38 @@ def shard_range(B: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def make_allreduce_comm(dist, device=None) -> Callable[[np.ndarray], None]:
-    """Returns comm(buf): in-place sum of a float32 numpy buffer over all ranks (api.train_NDE's `comm`)."""
-    import torch
+class HostComm:
+    """comm(buf): in-place sum of a float32 numpy buffer over all ranks; .rank / .world say which shard is ours
+    (api.train_NDE's `comm`)."""
 
-    def comm(buf: np.ndarray) -> None:
+    def __init__(self, dist, device=None):
+        self.dist, self.device = dist, device
+        self.rank, self.world = int(dist.get_rank()), int(dist.get_world_size())
+
+    def __call__(self, buf: np.ndarray) -> None:
+        import torch
         t = torch.from_numpy(buf)
-        if device is not None:
-            d = t.to(device)
-            dist.all_reduce(d, op=dist.ReduceOp.SUM)
+        if self.device is not None:
+            d = t.to(self.device)
+            self.dist.all_reduce(d, op=self.dist.ReduceOp.SUM)
             t.copy_(d)
         else:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
-    return comm
+
+def make_allreduce_comm(dist, device=None) -> HostComm:
+    return HostComm(dist, device)
+
+
+def init_library_comm(ctx, dist) -> None:
+    """Gives `ctx` its rank of a NCCL communicator owned by libopz (opz_ctx_comm_init), using an initialised
+    torch.distributed process group only to ship rank 0's 128-byte id.  Afterwards api.loss_grad* / train_NDE on this
+    context return globally reduced results with no host-side collective."""
+    from . import api
+    rank, world = int(dist.get_rank()), int(dist.get_world_size())
+    box = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], world, rank)
 
 
 def sharded_loss_grad(loss_grad_fn: Callable, dist, rank: int, world: int, x0, bc, target, *, device=None):

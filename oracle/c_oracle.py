@@ -38,7 +38,10 @@ def lib():
                                      C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p,
                                      C.c_int]
         _lib.orc_rollout.restype = C.c_int
+        _lib.orc_rollout_f64.argtypes = _lib.orc_rollout.argtypes
+        _lib.orc_rollout_f64.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
+        _lib.orc_num_procs.restype = C.c_int
     return _lib
 
 
@@ -54,16 +57,18 @@ def params_struct(p) -> OrcParams:
     return q
 
 
-def rollout(x0, bc, model, p, scheme, dt_nd, n_steps, save_every, t0=0.0, n_threads=0):
+def rollout(x0, bc, model, p, scheme, dt_nd, n_steps, save_every, t0=0.0, n_threads=0, f64=False):
+    """Float32 solve (f64=False) or the same Float32-specified problem solved in double (f64=True: the noise floor)."""
     x0 = np.ascontiguousarray(x0, dtype=np.float32)
     bc = np.ascontiguousarray(bc, dtype=np.float32)
     w = np.ascontiguousarray(model.flat(), dtype=np.float32)
     B = x0.shape[0]
     n_save = n_steps // save_every + 1 if save_every > 0 else 1
-    out = np.empty((B, n_save, x0.shape[1]), dtype=np.float32)
+    out = np.empty((B, n_save, x0.shape[1]), dtype=np.float64 if f64 else np.float32)
     sizes = (C.c_int * len(model.sizes))(*model.sizes)
     q = params_struct(p)
-    rc = lib().orc_rollout(C.byref(q), sizes, len(model.sizes), model.act, w.ctypes.data, x0.ctypes.data, bc.ctypes.data,
+    fn = lib().orc_rollout_f64 if f64 else lib().orc_rollout
+    rc = fn(C.byref(q), sizes, len(model.sizes), model.act, w.ctypes.data, x0.ctypes.data, bc.ctypes.data,
                            B, scheme, dt_nd, t0, n_steps, save_every, out.ctypes.data, n_threads)
     if rc != 0:
         raise RuntimeError("orc_rollout failed")
@@ -72,3 +77,8 @@ def rollout(x0, bc, model, p, scheme, dt_nd, n_steps, save_every, t0=0.0, n_thre
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def num_procs() -> int:
+    """Host cores, independent of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    return int(lib().orc_num_procs())

@@ -4,7 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opz_import
 opz = opz_import.load()
 opz.default_context()
-fn = opz.lib.opz_debug_tmem_read
+import ctypes as _C, os as _os
+_probe = _C.CDLL(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests", "libopz_probe.so"))
+fn = _probe.opz_debug_tmem_read
 fn.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_double)]
 fn.restype = C.c_int
 for x32 in (0, 1):

@@ -4,7 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opz_import
 opz = opz_import.load()
 opz.default_context()
-fn = opz.lib.opz_debug_umma_rate
+import ctypes as _C, os as _os
+_probe = _C.CDLL(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests", "libopz_probe.so"))
+fn = _probe.opz_debug_umma_rate
 fn.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_double)]
 fn.restype = C.c_int
 for mode, mname in ((1, "TS"), (0, "SS")):

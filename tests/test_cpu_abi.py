@@ -133,3 +133,48 @@ def test_adam_and_loss_helpers(opz):
     assert opz.loss(np.ones((3, 4)), np.zeros((3, 4))) == 1.0
     ls = opz.calculate_loss_scalings(NS(u=0.3, v=0.7, T=2.0, dudz=5.0, dvdz=1.0, dTdz=4.0), NS(T=0.8, dTdz=0.8, profile=0.5), True)
     assert ls.T == 1 and (ls.T * 2.0) / (ls.u * 1.0) == pytest.approx(4.0)
+
+
+def test_prepare_BCs_and_pack(opz, oracle):
+    """prepare_BCs (training_postprocessing.jl:35-53): scaled boundary fluxes of the FIRST data column; a
+    wT_top_function makes BCs.wT.top a function of time in seconds (t -> scalings.wT(wT_top_function(t)))."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from helpers import les_shaped_dataset
+    D, p, x0, bc, data, dt, per = les_shaped_dataset(opz, oracle, n_sim=2, nt=3, sizes=(96, 8, 31), act=1)
+    sc = D.scalings
+    BCs = opz.prepare_BCs(D, sc)
+    for k, n in enumerate(("uw", "vw", "wT")):
+        f = getattr(D, n)
+        assert getattr(BCs, n).bottom == pytest.approx(float(sc[n](f.coarse[0, 0])), rel=1e-6)
+        assert getattr(BCs, n).top == pytest.approx(float(sc[n](f.coarse[-1, 0])), rel=1e-6)
+        # the scaled boundary fluxes of simulation 0, the values bc[0] was built from
+        assert getattr(BCs, n).bottom == pytest.approx(float(bc[0, 2 * k]), abs=1e-5)
+        assert getattr(BCs, n).top == pytest.approx(float(bc[0, 2 * k + 1]), abs=1e-5)
+    row = opz.pack_BCs(BCs)
+    assert row.shape == (8,) and row.dtype == np.float32 and np.allclose(row[:6], bc[0, :6], atol=1e-5)
+    # diurnal form (data_containers.jl:131-156): top flux is a closure over time in seconds
+    Q = 1e-7
+    wT_top = lambda t: Q * np.sin(2 * np.pi / 86400.0 * t) / (p.alpha * p.g)
+    BCd = opz.prepare_BCs(D, sc, wT_top)
+    assert callable(BCd.wT.top)
+    assert BCd.wT.top(21600.0) == pytest.approx(float(sc["wT"](Q / (p.alpha * p.g))), rel=1e-6)
+    rowd = opz.pack_BCs(BCd, Q_diurnal=Q)
+    assert rowd[5] == 0.0 and rowd[6] == np.float32(Q)
+
+
+def test_c_shard_range_matches_host_and_nccl_binds(opz):
+    """opz_shard_range (what a ccall host uses to pick its cases) == parallel.shard_range; NCCL is bound at run time."""
+    lo, hi = C.c_int64(), C.c_int64()
+    for B in (0, 1, 5, 18, 4097):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                opz.check(opz.lib.opz_shard_range(B, r, world, C.byref(lo), C.byref(hi)))
+                assert (lo.value, hi.value) == opz.shard_range(B, r, world)
+    assert opz.lib.opz_shard_range(4, 2, 2, C.byref(lo), C.byref(hi)) == opz.OPZ_EINVAL
+    v = C.c_int()
+    rc = opz.lib.opz_comm_nccl_version(C.byref(v))
+    if rc == opz.OPZ_OK:
+        assert v.value >= 21800, v.value          # NCCL >= 2.18
+    else:
+        assert rc == opz.OPZ_ENCCL and b"nccl" in opz.lib.opz_last_error().lower()

@@ -329,33 +329,13 @@ def test_train_NDE_host_loop_learns_on_synthetic_les_shaped_data(opz, oracle, ct
     object (scaled profiles of 4 simulations at 600 s spacing, fluxes, scalings, times) generated by the oracle with a
     'true' model; ADAM steps with libopz gradients reduce the profile + gradient loss, and the first evaluation agrees
     with the autograd twin."""
-    from types import SimpleNamespace as NS
-    from helpers import chains_from_oracle_model
+    from helpers import chains_from_oracle_model, les_shaped_dataset
     from oracle import nde_oracle_torch as OT
     O = oracle
-    n_sim, nt, dt_data = 4, 7, 600.0
-    tau = dt_data * (nt - 1)
-    flags = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
-    p = O.Params(tau=tau, flags=flags, dRi=1.0)          # train_NDE's default dRi = 1 (NDE_training.jl:168)
-    x0, bc = O.synthetic_columns(n_sim, p)
-    x0 = (x0 + 0.02 * np.random.default_rng(1).normal(size=x0.shape)).astype(np.float32)
+    n_sim, nt = 4, 7
     sizes = (96, 50, 20, 31)
-    m_true = O.make_model(sizes, O.ACT_MISH, seed=21, out_scale=0.1)
+    D, p, x0, bc, data, dt, per = les_shaped_dataset(opz, O, n_sim=n_sim, nt=nt, sizes=sizes, act=O.ACT_MISH)
     m0 = O.make_model(sizes, O.ACT_MISH, seed=22, out_scale=0.1)
-    dt = 30.0 / tau
-    per = int(round(dt_data / 30.0))
-    data = O.rollout(x0, bc, m_true, p, O.SCHEME_RK4, dt, per * (nt - 1), per)       # [n_sim, nt, 96]
-    uvT_scaled = np.concatenate([data[i].T for i in range(n_sim)], axis=1)              # [96, nt * n_sim]
-    t = np.concatenate([np.arange(nt) * dt_data for _ in range(n_sim)])
-    def flux_field(k):   # only rows 0 / -1 of the first column of every simulation are read (the boundary fluxes)
-        a = np.zeros((33, nt * n_sim), dtype=np.float32)
-        for i in range(n_sim):
-            a[0, nt * i:nt * (i + 1)] = bc[i, 2 * k]
-            a[-1, nt * i:nt * (i + 1)] = bc[i, 2 * k + 1]
-        return NS(scaled=a, z=np.linspace(-p.H, 0.0, 33))
-    sc = {n: opz.ZeroMeanUnitVarianceScaling(p.mu[i], p.sigma[i]) for i, n in enumerate(("u", "v", "T", "uw", "vw", "wT"))}
-    D = NS(uvT_scaled=uvT_scaled, t=t, uw=flux_field(0), vw=flux_field(1), wT=flux_field(2), u=NS(z=np.linspace(-p.H, 0, 33)[:-1] + 4.0),
-           scalings=sc, n_simulations=n_sim)
     uw_NN, vw_NN, wT_NN = chains_from_oracle_model(opz, m0)
     tsteps = np.arange(0, nt, 2)
     seen = []

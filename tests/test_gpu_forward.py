@@ -356,3 +356,68 @@ def test_imex_euler_matches_oracle_and_is_stable_at_kappa_10(opz, oracle):
         opz.loss_grad(model, pp, x0, bc, ref[:, :3], np.ones(6, np.float32), opz.SCHEME_IMEX, dt, 8, 4)
     assert e.value.code == opz.OPZ_EUNSUP
     model.close()
+
+
+def test_reference_shaped_calls_never_reuse_stale_weights(opz, oracle, ctx):
+    """NDE(x, p, t, ...) rebuilds its three Chains from `p` on every call (NDE_training.jl:62-64).  The device model behind
+    the reference-shaped entry points is cached per architecture and its weights are uploaded on every call: two calls
+    with different parameter vectors must each match the oracle (an id()-keyed cache returned the first call's weights)."""
+    import gc
+    from types import SimpleNamespace as NS
+    sizes = (96, 50, 20, 31)
+    pt = oracle.Params(flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS)
+    sc = {n: opz.ZeroMeanUnitVarianceScaling(pt.mu[i], pt.sigma[i]) for i, n in enumerate(("u", "v", "T", "uw", "vw", "wT"))}
+    scalings = NS(**sc)
+    constants = NS(H=pt.H, τ=pt.tau, f=pt.f, Nz=32, g=pt.g, α=pt.alpha, ν0=pt.nu0, ν_m=pt.nu_m, Riᶜ=pt.Ric, ΔRi=pt.dRi, Pr=pt.Pr)
+    cond = NS(modified_pacanowski_philander=True, convective_adjustment=False, zero_weights=False, smooth_NN=False, smooth_Ri=False)
+    from helpers import chains_from_oracle_model
+    x0, bc = oracle.synthetic_columns(3, pt)
+    x = (x0[1] + 0.05 * np.random.default_rng(3).normal(size=96)).astype(np.float32)
+    res = []
+    for seed in (1, 2, 3, 1):
+        m = oracle.make_model(sizes, oracle.ACT_MISH, seed=seed)
+        chains = chains_from_oracle_model(opz, m)
+        res_w = [opz.destructure(c) for c in chains]
+        NN_constructions = NS(uw=res_w[0][1], vw=res_w[1][1], wT=res_w[2][1])
+        P = m.P
+        NN_ranges = NS(uw=slice(0, P), vw=slice(P, 2 * P), wT=slice(2 * P, 3 * P))
+        pvec = np.concatenate([m.flat(), bc[1, :6]]).astype(np.float32)
+        del chains, res_w
+        gc.collect()
+        k = opz.NDE(x, pvec, 0.0, NN_ranges, NN_constructions, cond, scalings, constants, None, None)
+        kr = oracle.rhs(x[None], bc[1:2], 0.0, m, pt)[0]
+        for v in range(3):
+            sl = slice(32 * v, 32 * (v + 1))
+            assert rel_err(k[sl], kr[sl]) < 5e-5, (seed, v)
+        res.append(k)
+    assert not np.array_equal(res[0], res[1]) and not np.array_equal(res[1], res[2])
+    assert np.array_equal(res[0], res[3])
+    # in-place edit of a Dense's W between two solve calls is picked up as well
+    m = oracle.make_model(sizes, oracle.ACT_MISH, seed=5, out_scale=0.1)
+    uw_NN, vw_NN, wT_NN = chains_from_oracle_model(opz, m)
+    BCs = NS(uw=NS(bottom=bc[1, 0], top=bc[1, 1]), vw=NS(bottom=bc[1, 2], top=bc[1, 3]), wT=NS(bottom=bc[1, 4], top=bc[1, 5]))
+    k1 = opz.predict_NDE(uw_NN, vw_NN, wT_NN, x, BCs, cond, scalings, constants, None, None)
+    uw_NN.layers[-1].W *= 3.0
+    k2 = opz.predict_NDE(uw_NN, vw_NN, wT_NN, x, BCs, cond, scalings, constants, None, None)
+    assert not np.array_equal(k1[:32], k2[:32]) and np.array_equal(k1[64:], k2[64:])
+
+
+def test_context_destroyed_before_its_models_is_safe(opz, oracle):
+    """Host garbage collectors give no destruction order: opz_ctx_destroy with live models defers the teardown to the last
+    opz_model_destroy (no use-after-free of the context's device / stream)."""
+    import ctypes as C
+    h = C.c_void_p()
+    opz.check(opz.lib.opz_ctx_create(0, C.byref(h)))
+    m = oracle.make_model((96, 16, 31), oracle.ACT_RELU, seed=0)
+    sizes = (C.c_int * 3)(96, 16, 31)
+    mh = [C.c_void_p(), C.c_void_p()]
+    ws = [np.ascontiguousarray(w, dtype=np.float32) for w in (m.w_uw, m.w_vw, m.w_wT)]
+    for k in range(2):
+        opz.check(opz.lib.opz_model_create(h, 32, 3, sizes, 1, ws[0].ctypes.data_as(C.c_void_p), ws[1].ctypes.data_as(C.c_void_p),
+                                           ws[2].ctypes.data_as(C.c_void_p), C.byref(mh[k])))
+    assert opz.lib.opz_ctx_destroy(h) == 0        # deferred
+    back = np.empty(3 * m.P, dtype=np.float32)
+    opz.check(opz.lib.opz_model_get_weights(mh[0], back.ctypes.data_as(C.c_void_p)))   # the context is still alive
+    assert np.array_equal(back, m.flat())
+    assert opz.lib.opz_model_destroy(mh[0]) == 0
+    assert opz.lib.opz_model_destroy(mh[1]) == 0  # frees the context too

@@ -1,5 +1,6 @@
 """Pins the tcgen05 operand conventions of the tensor-core path on real hardware: one-tile BF16 GEMM
-through the debug entry point opz_debug_umma against a float64 product of the same BF16 operands."""
+through the debug entry point opz_debug_umma (tests/libopz_probe.so, built from tests/csrc/opz_tc_probe.cu: test
+infrastructure, not part of libopz.so) against a float64 product of the same BF16 operands."""
 import ctypes as C
 
 import numpy as np
@@ -27,7 +28,9 @@ def test_umma_tile(opz, N, K, mode):
     A = bf16_bits(rng.normal(size=(128, K)))
     B = bf16_bits(rng.normal(size=(N, K)))
     D = np.zeros((128, N), dtype=np.float32)
-    fn = opz.lib.opz_debug_umma
+    import os
+    probe = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libopz_probe.so"))
+    fn = probe.opz_debug_umma
     fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     fn.restype = C.c_int
     opz.check(fn(N, K, mode, A.ctypes.data, B.ctypes.data, D.ctypes.data))
