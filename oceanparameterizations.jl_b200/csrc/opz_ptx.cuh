@@ -270,5 +270,17 @@ __device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {
   return r;
 }
 
+// round-toward-zero packs: the dithered state image adds its threshold to the magnitude bits first, so truncation rounds
+__device__ __forceinline__ uint32_t pack_f16x2_rz(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rz.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rz(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 }  // namespace ptx
 }  // namespace opz

@@ -17,12 +17,24 @@
 //   * hidden-layer biases are read through L1 (prefetched before the accumulator barrier) — the shared memory
 //     they used to occupy now belongs to the weight ring.
 //
-// TMEM map, operand formats, barrier protocol between MMA issuer and epilogue and the numerics are those of v1
-// (see opz_tc.cu); the physics evaluates the same FP32 expressions per face as opz_device.cuh::column_rhs<FAST>.
+// The physics evaluates the same FP32 expressions per face as opz_device.cuh::column_rhs<FAST>.
+//
+// Numerics of the 16-bit operands (measured: tests/test_gpu_long.py, scripts/precision_study.py).  Over the
+// 23 040 steps of the 8-day rollout the error of a plainly rounded FP16 path is NOT the per-step rounding noise but the part of
+// the rounding that is CONSTANT in time: the weights (rounded once: a slightly different model, 1.6e-2 after 8 days) and the
+// slowly varying state image.  Both are therefore dithered in time, at no cost in tensor work:
+//   * the weight tape exists in kTapes = 16 versions; version t holds, per weight, the FP16 neighbour below or above it such that
+//     the MEAN over the 16 versions reproduces the FP32 weight to 4 more bits (ordered dither, thresholds in bit-reversed order,
+//     phase rotated per weight); right-hand side (step n, stage s) streams version (n + s) mod 16, so every version visits every
+//     Runge-Kutta stage slot equally often;
+//   * the 16-bit image of the stage state is rounded with a Weyl-sequence threshold added to the magnitude bits before truncation
+//     (a different threshold every right-hand side): its time average carries the FP32 value.
+// Hidden activations are rounded to nearest as before (their rounding is not persistent).
 //
 // Replaces the batched form of NDE! / predict_flux! (wind_mixing/src/training_postprocessing.jl:105-153)
 // inside a fixed-step solve (solve_NDE_mutating, :55-159).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +55,7 @@ constexpr int kMaxStages = 72;       // stages per right-hand side
 constexpr int kSplitK = 12;          // a 64-row x 25-k-step chunk is staged as two weight stages: k-steps [0, 12) and [12, 25) + bias + W_out
 constexpr int kRingBytes = 84480;    // 3 x (32 rows x (400 + 8) k + 16 rows x 64 k) x 2 B
 constexpr int kMaxKs = 28;           // 7 HF chunks x 4 k-steps
+constexpr int kTapes = 16;           // temporally dithered versions of the weight tape (power of two)
 
 constexpr uint32_t kColD0 = 0, kColY = 128, kColX = 224, kColH2 = 272, kColHF = 304, kColOne = 504;
 // kColOne: one k-step (8 columns) holding [1, 0, ..., 0] per lane: the A operand of the bias MMAs
@@ -72,7 +85,9 @@ struct Plan {                     // host-side, cached on the model
   uint32_t st_bytes[kMaxStages];  // bytes PER CTA
   uint32_t st_src[kMaxStages];    // tape offset of the stage (leader half first, then the peer half)
   uint8_t st_keep[kMaxStages];    // earlier stages that may still be in flight when this one is filled
-  size_t tape_bytes = 0;
+  size_t tape_bytes = 0;          // one version
+  size_t tape_stride = 0;         // distance between versions (bytes)
+  int n_tapes = 1;
   uint8_t* tape_dev = nullptr;
   float b3[96];                   // output-layer biases [net][32]
 };
@@ -91,6 +106,10 @@ struct Args {
   int n_mma_warps;   // 1 or 2 issuing warps in the leader CTA
   int interleave;    // 1: layer-major schedule (all three nets' first layers, then their second layers), see build_plan
   int nc1;           // accumulator chunks of the first hidden layer
+  int tape_mask;     // versions of the tape - 1 (0: a single, plainly rounded tape)
+  uint32_t tape_stride;
+  int n0;            // global index of the first time step of this call (t0 / dt): the dither phases continue across calls
+  int dither_x;      // 1: Weyl-dithered state image
   int hpad[2];
   float b3[96];   // output-layer biases [net][32] (the hidden-layer biases ride in the weight tape)
   float pk[18];   // products of the physics constants folded on the host (see PK_* below): one FFMA per use in the kernel
@@ -229,6 +248,9 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
       uint32_t gs = 0, c = 0;   // stages issued / stages known to be consumed
       for (int64_t item = item0; item < n_items; item += item_stride) {
         for (int r = 0; r < n_rhs; ++r) {
+          // version of the weight tape of right-hand side (step n, stage st): (n + st) mod kTapes
+          const int n_loc = r / stages, st_loc = r - n_loc * stages;
+          const uint8_t* tape = a.tape + (size_t)((a.n0 + n_loc + st_loc) & a.tape_mask) * a.tape_stride;
           for (int s = 0; s < a.n_stages; ++s, ++gs) {
             const uint32_t keep = a.st_keep[s];
             while (c + keep < gs) {  // stage c must have been consumed: its bytes (or its barrier pair) are reused
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const uint32_t bytes = a.st_bytes[s];
             uint64_t* full = bars + B_FULL + (gs % kNB);
             ptx::mbar_arrive_expect_tx(full, bytes);
-            ptx::bulk_g2s(s_ring + a.st_off[s], a.tape + a.st_src[s] + rank * bytes, bytes, full);
+            ptx::bulk_g2s(s_ring + a.st_off[s], tape + a.st_src[s] + rank * bytes, bytes, full);
           }
         }
       }
@@ -534,12 +556,22 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
       };
       if (a.save_every > 0) save(0);
       // 16-bit image of this thread's cells of the stage state -> tensor memory (A operand of the first layers)
-      auto publish_x = [&](const float (&xv)[3][LV]) {
+      // `t_rhs` = global index of the right-hand side that will consume the image: the phase of the rounding dither
+      auto publish_x = [&](const float (&xv)[3][LV], uint32_t t_rhs) {
+        // Weyl-sequence thresholds on the dropped mantissa bits (13 for IEEE half, 16 for BF16), eight per right-hand side;
+        // magnitude bits + threshold, then truncation = a rounding whose mean over consecutive right-hand sides is the FP32 value
+        uint32_t thr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) thr[j] = a.dither_x ? (((t_rhs * 5061u + (uint32_t)j * 1021u) & 8191u) << (FP16 ? 0 : 3)) : (FP16 ? 4096u : 32768u);
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
           uint32_t pk[LV / 2];
 #pragma unroll
-          for (int j = 0; j < LV / 2; ++j) pk[j] = pack_act<FP16, OPZ_ACT_IDENTITY>(xv[v][2 * j], xv[v][2 * j + 1]);
+          for (int j = 0; j < LV / 2; ++j) {
+            const float e0 = __uint_as_float(__float_as_uint(xv[v][2 * j]) + thr[(2 * j) & 7]);
+            const float e1 = __uint_as_float(__float_as_uint(xv[v][2 * j + 1]) + thr[(2 * j + 1) & 7]);
+            pk[j] = FP16 ? ptx::pack_f16x2_rz(e0, e1) : ptx::pack_bf16x2_rz(e0, e1);
+          }
           const uint32_t dst = tmem + lane_addr + kColX + (uint32_t)(v * (kNz / 2) + c0 / 2);
           if constexpr (LV == 16) ptx::tmem_st8(dst, pk);
           else ptx::tmem_st4(dst, pk);
@@ -559,7 +591,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             xv[v][i] = s_xn[xn_idx(idx, m)];
             s_xs[idx * kM + m] = xv[v][i];
           }
-        if (n_rhs > 0) publish_x(xv);
+        if (n_rhs > 0) publish_x(xv, (uint32_t)(a.n0 * stages));
       }
 
       int rhs_idx = 0;
@@ -745,7 +777,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               xnew[v][i] = xv;
             }
           }
-          if (rhs_idx + 1 < n_rhs) publish_x(xnew);  // also tells the MMA warp that Y has been consumed
+          if (rhs_idx + 1 < n_rhs) publish_x(xnew, (uint32_t)(a.n0 * stages + rhs_idx + 1));  // also tells the MMA warp that Y has been consumed
           if (prof_me) eacc[E_PHYS_B - 8] += clock64() - t_b;
         }
         if (a.save_every > 0 && (n + 1) % a.save_every == 0) save((n + 1) / a.save_every);
@@ -790,9 +822,65 @@ static uint16_t bf16_rne(float f) {
   return (uint16_t)(u >> 16);
 }
 
+static float f16_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+  uint32_t u;
+  if (e == 0) {
+    if (m == 0) u = sign;
+    else { int sh = 0; uint32_t mm = m; while (!(mm & 0x400u)) { mm <<= 1; ++sh; } u = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 0x3FFu) << 13); }
+  } else if (e == 31) u = sign | 0x7F800000u | (m << 13);
+  else u = sign | ((e + 112u) << 23) | (m << 13);
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+static float bf16_to_float(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+// neighbours of a 16-bit pattern on the real line (sign-magnitude formats)
+static uint16_t next_below(uint16_t b) { return b == 0x0000u ? 0x8001u : ((b & 0x8000u) ? (uint16_t)(b + 1) : (uint16_t)(b - 1)); }
+static uint16_t next_above(uint16_t b) { return b == 0x8000u ? 0x0001u : ((b & 0x8000u) ? (uint16_t)(b - 1) : (uint16_t)(b + 1)); }
+
+// Temporally dithered rounding of one weight (see the header): version `tape` of `n_tapes` takes the 16-bit neighbour above the
+// weight when the weight's position between its two neighbours exceeds that version's threshold.  `key` identifies the weight
+// (net, layer, input, output) and rotates the threshold order, so that the weights of one dot product do not switch in phase.
+// The same function is restated in oracle/nde_oracle.py (TensorPathEmulation) for the emulating parity tests.
+static uint32_t dither_key(int net, int layer, int k, int n) {
+  return ((uint32_t)k * 2654435761u) ^ ((uint32_t)n * 2246822519u) ^ ((uint32_t)(net * 8 + layer) * 3266489917u);
+}
+static uint16_t quant16(float v, bool fp16, int tape, int n_tapes, uint32_t key) {
+  const uint16_t q = fp16 ? f16_rne(v) : bf16_rne(v);
+  if (n_tapes <= 1 || !std::isfinite(v)) return q;
+  const uint16_t expo = fp16 ? (q & 0x7C00u) : (q & 0x7F80u);
+  if (expo == (fp16 ? 0x7C00u : 0x7F80u) || (fp16 && std::fabs(v) >= 65504.0f)) return q;   // saturated / non-finite
+  auto val = [&](uint16_t b) { return (double)(fp16 ? f16_to_float(b) : bf16_to_float(b)); };
+  uint16_t lo = q;
+  if (val(q) > (double)v) lo = next_below(q);
+  const uint16_t hi = next_above(lo);
+  const double dlo = val(lo), dhi = val(hi);
+  if (!(dhi > dlo) || !std::isfinite(dhi)) return q;
+  const double frac = ((double)v - dlo) / (dhi - dlo);
+  int bits = 0;
+  while ((1 << bits) < n_tapes) ++bits;
+  const uint32_t rot = (key >> 13) & (uint32_t)(n_tapes - 1);
+  const uint32_t idx = ((uint32_t)tape + rot) & (uint32_t)(n_tapes - 1);
+  uint32_t rev = 0;
+  for (int b = 0; b < bits; ++b) rev |= ((idx >> b) & 1u) << (bits - 1 - b);
+  const double thr = ((double)rev + 0.5) / (double)n_tapes;
+  return frac > thr ? hi : lo;
+}
+
+struct TapeQuant {   // what append_half needs to know about the version being built
+  bool fp16;
+  int tape, n_tapes, net, layer;
+};
+
 // One CTA's half (rows [r0, r0 + hrows)) of the K-major no-swizzle block of W (Flux layout: element (k_in, n_out) at
 // w[k * nout + n]) over inputs [k0, k0 + 16 * ksteps): [k/8][row][k%8] 16-bit, zero padded; appended to `dst`.
-static void append_half(std::vector<uint16_t>& dst, bool fp16, const float* w, int nin, int nout, int r0, int hrows, int k0, int ksteps) {
+static void append_half(std::vector<uint16_t>& dst, const TapeQuant& tq, const float* w, int nin, int nout, int r0, int hrows, int k0, int ksteps) {
   const size_t base = dst.size();
   dst.resize(base + (size_t)hrows * ksteps * 16, 0);
   for (int kk = 0; kk < ksteps * 16; ++kk) {
@@ -802,12 +890,13 @@ static void append_half(std::vector<uint16_t>& dst, bool fp16, const float* w, i
       const int n = r0 + r;
       if (n >= nout) continue;
       const float v = w[(size_t)k * nout + n];
-      dst[base + ((size_t)(kk / 8) * hrows + r) * 8 + (kk % 8)] = fp16 ? f16_rne(v) : bf16_rne(v);
+      dst[base + ((size_t)(kk / 8) * hrows + r) * 8 + (kk % 8)] = quant16(v, tq.fp16, tq.tape, tq.n_tapes, dither_key(tq.net, tq.layer, k, n));
     }
   }
 }
 
-static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, Plan& pl, std::vector<uint16_t>& tape) {
+// builds version `tape_idx` of `n_tapes` of the weight tape (the schedule, offsets and sizes are the same for every version)
+static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16, int tape_idx, int n_tapes, Plan& pl, std::vector<uint16_t>& tape) {
   const NetDesc& nd = m->nd;
   const int L = nd.n_layers;
   if (m->nz != kNz) { set_error("tensor-core path: nz must be 32"); return OPZ_EUNSUP; }
@@ -828,8 +917,9 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   bool overflow = false;
   auto out_halves = [&](const Pending& p) {   // 16 rows per CTA of W_out over the 64 (or fewer) inputs of chunk p.c
     const float* wn = w.data() + (size_t)p.net * nd.P;
+    const TapeQuant tq{fp16, tape_idx, n_tapes, p.net, L - 1};
     for (int hf = 0; hf < 2; ++hf)
-      append_half(half[hf], fp16, wn + nd.w_off[L - 1], nd.sizes[L - 1], nd.sizes[L], hf * 16, 16, p.c * kCW, p.cols / 16);
+      append_half(half[hf], tq, wn + nd.w_off[L - 1], nd.sizes[L - 1], nd.sizes[L], hf * 16, 16, p.c * kCW, p.cols / 16);
   };
   auto close_stage = [&]() {
     if (pl.n_stages >= kMaxStages) { overflow = true; half[0].clear(); half[1].clear(); return; }
@@ -856,25 +946,26 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
       const bool fused = (j == L - 2);
       const int kin = (j == 0) ? kS : pl.hpad[j - 1];
       const int hp = pl.hpad[j];
+      const TapeQuant tq{fp16, tape_idx, n_tapes, net, j};
       for (int c = 0; c * kCW < hp; ++c) {
         const int rows = std::min(kCW, hp - c * kCW);
         const bool split = (rows == kCW) && (kin / 16 == 25);   // two stages: k-steps [0, kSplitK) | [kSplitK, 25) + bias + W_out
         if (split) {
           for (int hf = 0; hf < 2; ++hf)
-            append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kSplitK);
+            append_half(half[hf], tq, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kSplitK);
           close_stage();
           for (int hf = 0; hf < 2; ++hf)
-            append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, kSplitK * 16,
+            append_half(half[hf], tq, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, kSplitK * 16,
                         25 - kSplitK);
         } else {
           for (int hf = 0; hf < 2; ++hf)
-            append_half(half[hf], fp16, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kin / 16);
+            append_half(half[hf], tq, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kin / 16);
         }
         for (int hf = 0; hf < 2; ++hf)   // bias block: one k-group, row r = [b_r, 0, 0, 0, 0, 0, 0, 0]
           for (int r = 0; r < rows / 2; ++r) {
             const int n = c * kCW + hf * (rows / 2) + r;
             const float bv = n < nd.sizes[j + 1] ? wn[nd.b_off[j] + n] : 0.0f;
-            half[hf].push_back(fp16 ? f16_rne(bv) : bf16_rne(bv));
+            half[hf].push_back(quant16(bv, fp16, tape_idx, n_tapes, dither_key(net, j, 0xFFFF, n)));
             for (int z = 0; z < 7; ++z) half[hf].push_back(0);
           }
         if (q1.valid) out_halves(q1);
@@ -927,19 +1018,32 @@ int tc2_model_prepare(opz_model* m, int precision) {
   OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
   Plan* pl = static_cast<Plan*>(m->tc2_plan);
   if (!pl) { pl = new Plan(); m->tc2_plan = pl; }
+  // OPZ_TC_TAPES=1 gives the plainly rounded single tape (the 8-day error study runs both), OPZ_TC_NO_XDITHER=1 the
+  // round-to-nearest state image
+  int n_tapes = kTapes;
+  if (const char* e = getenv("OPZ_TC_TAPES")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) n_tapes = v; }
   std::vector<uint16_t> tape;
-  int rc = build_plan(m, w, fp16, *pl, tape);
+  int rc = build_plan(m, w, fp16, 0, n_tapes, *pl, tape);
   if (rc) return rc;
   const size_t tape_al = (pl->tape_bytes + 255) / 256 * 256;
-  const size_t need = tape_al + 256;
+  pl->tape_stride = tape_al;
+  pl->n_tapes = n_tapes;
+  const size_t need = tape_al * n_tapes + 256;
   if (m->tc2_pack_bytes < need) {
     if (m->tc2_pack) { OPZ_CUDA(cudaFree(m->tc2_pack)); m->tc2_pack = nullptr; m->tc2_pack_bytes = 0; }
     if (cudaMalloc(&m->tc2_pack, need) != cudaSuccess) { (void)cudaGetLastError(); set_error("device allocation failed"); return OPZ_ENOMEM; }
     m->tc2_pack_bytes = need;
   }
   pl->tape_dev = static_cast<uint8_t*>(m->tc2_pack);
-  OPZ_CUDA(cudaMemcpyAsync(pl->tape_dev, tape.data(), pl->tape_bytes, cudaMemcpyHostToDevice, m->ctx->stream));
-  OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));  // the host vectors go out of scope
+  for (int t = 0; t < n_tapes; ++t) {
+    if (t > 0) {
+      Plan scratch = *pl;   // same schedule; only the rounding of the entries differs
+      if ((rc = build_plan(m, w, fp16, t, n_tapes, scratch, tape))) return rc;
+      if (scratch.tape_bytes != pl->tape_bytes) { set_error("tensor-core path: tape versions differ in size"); return OPZ_EINVAL; }
+    }
+    OPZ_CUDA(cudaMemcpyAsync(pl->tape_dev + (size_t)t * tape_al, tape.data(), pl->tape_bytes, cudaMemcpyHostToDevice, m->ctx->stream));
+    OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));  // the host vector is rebuilt / goes out of scope
+  }
   return OPZ_OK;
 }
 
@@ -973,6 +1077,10 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   a.hpad[0] = pl->hpad[0]; a.hpad[1] = pl->hpad[1];
   std::memcpy(a.b3, pl->b3, sizeof(a.b3));
   a.n_mma_warps = 2;
+  a.tape_mask = pl->n_tapes - 1;
+  a.tape_stride = (uint32_t)pl->tape_stride;
+  a.n0 = c.dt > 0.0f ? (int)lrintf(c.t0 / c.dt) : 0;   // the dither phases continue where the previous window of the rollout stopped
+  a.dither_x = getenv("OPZ_TC_NO_XDITHER") == nullptr;
   a.interleave = pl->interleave ? 1 : 0;
   a.nc1 = (pl->hpad[0] + kCW - 1) / kCW;
   if (const char* e = getenv("OPZ_TC_MMA_WARPS")) a.n_mma_warps = atoi(e) == 1 ? 1 : 2;

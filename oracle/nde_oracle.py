@@ -201,17 +201,22 @@ def activation(z: np.ndarray, act: int) -> np.ndarray:
 
 
 def mlp_forward(x: np.ndarray, flat: np.ndarray, sizes: Sequence[int], act: int,
-                quant: Optional[Callable] = None) -> np.ndarray:
+                quant: Optional[Callable] = None, net: int = 0) -> np.ndarray:
     """y = W3 act(W2 act(W1 x + b1) + b2) + b3, batched: x[B, in] -> [B, out].
-    `quant` (optional) rounds GEMM operands, emulating a reduced-precision tensor path."""
+    `quant` (optional) rounds GEMM operands, emulating a reduced-precision tensor path: a plain callable rounds every
+    operand; a TensorPathEmulation restates the product kernel's temporally dithered roundings."""
     layers = unpack_weights(flat, sizes)
     h = x
+    emu = isinstance(quant, TensorPathEmulation)
     for li, (W, b) in enumerate(layers):
-        if quant is not None:
+        last = li == len(layers) - 1
+        if emu:
+            z = quant.activations(h, li) @ quant.weights(W, net, li).T + (b if last else quant.bias(b, net, li))
+        elif quant is not None:
             z = quant(h) @ quant(W).T + b
         else:
             z = h @ W.T + b
-        h = activation(z, act) if li < len(layers) - 1 else z
+        h = activation(z, act) if not last else z
     return h
 
 
@@ -234,6 +239,109 @@ def quant_tf32(a: np.ndarray) -> np.ndarray:
     u = a.view(np.uint32)
     r = ((u >> 13) & 1) + np.uint32(0x0FFF)
     return ((u + r) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+class TensorPathEmulation:
+    """CPU restatement of the operand roundings of the tcgen05 rollout kernel (csrc/opz_tc2.cu), for the parity tests that
+    separate "the kernel computes what it is meant to" from "16-bit operands differ from FP32":
+      * weights and hidden biases: version (n + s) mod n_tapes of the temporally dithered 16-bit rounding (quant16 /
+        dither_key of opz_tc2.cu) for the right-hand side of step n, stage s;
+      * the state fed to the first layers: magnitude bits + Weyl threshold of the right-hand side's global index, truncated;
+      * hidden activations: round to nearest (IEEE half saturating).
+    `stages` = right-hand sides per time step of the scheme; `n0` = global index of the first step (t0 / dt).
+    predict_flux() advances the right-hand-side counter after the three nets."""
+
+    def __init__(self, fmt: str = "fp16", stages: int = 4, n_tapes: int = 16, n0: int = 0, dither_x: bool = True):
+        assert fmt in ("fp16", "bf16")
+        self.fp16 = fmt == "fp16"
+        self.stages, self.n_tapes, self.n0, self.dither_x = stages, n_tapes, n0, dither_x
+        self.r = 0
+        self._cache = {}
+
+    # 16-bit grid helpers on float32 arrays
+    def _rn(self, a):
+        return quant_fp16(a) if self.fp16 else quant_bf16(a)
+
+    def _neighbours(self, W):
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        if self.fp16:
+            q = np.clip(W, -65504.0, 65504.0).astype(np.float16)
+            lo = np.where(q.astype(np.float32) > W, np.nextafter(q, np.float16(-np.inf)), q).astype(np.float16)
+            hi = np.nextafter(lo, np.float16(np.inf)).astype(np.float16)
+            return q.astype(np.float32), lo.astype(np.float32), hi.astype(np.float32)
+        q = quant_bf16(W)
+        u = q.view(np.uint32)
+        below = np.where(u == 0, np.uint32(0x80010000), np.where(u & np.uint32(0x80000000), u + np.uint32(0x10000), u - np.uint32(0x10000)))
+        lo_u = np.where(q > W, below, u).astype(np.uint32)
+        above = np.where(lo_u == np.uint32(0x80000000), np.uint32(0x00010000),
+                         np.where(lo_u & np.uint32(0x80000000), lo_u - np.uint32(0x10000), lo_u + np.uint32(0x10000))).astype(np.uint32)
+        return q, lo_u.view(np.float32), above.view(np.float32)
+
+    def _dither(self, W, key, tape):
+        q, lo, hi = self._neighbours(W)
+        if self.n_tapes <= 1:
+            return q
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+            frac = (W.astype(np.float64) - lo.astype(np.float64)) / (hi.astype(np.float64) - lo.astype(np.float64))
+        bits = int(np.log2(self.n_tapes))
+        rot = (key >> np.uint32(13)) & np.uint32(self.n_tapes - 1)
+        idx = (np.uint32(tape) + rot) & np.uint32(self.n_tapes - 1)
+        rev = np.zeros_like(idx)
+        for b in range(bits):
+            rev |= ((idx >> np.uint32(b)) & np.uint32(1)) << np.uint32(bits - 1 - b)
+        thr = (rev.astype(np.float64) + 0.5) / self.n_tapes
+        ok = np.isfinite(W) & (hi > lo) & np.isfinite(hi) & (np.abs(W) < (65504.0 if self.fp16 else np.inf))
+        return np.where(ok, np.where(frac > thr, hi, lo), q).astype(np.float32)
+
+    def _tape(self):
+        n, s = self.n0 + self.r // self.stages, self.r % self.stages
+        return (n + s) % self.n_tapes
+
+    @staticmethod
+    def _key(net, layer, k, n):
+        with np.errstate(over="ignore"):
+            return (k.astype(np.uint32) * np.uint32(2654435761)) ^ (n.astype(np.uint32) * np.uint32(2246822519)) ^ \
+                   np.uint32(((net * 8 + layer) * 3266489917) & 0xFFFFFFFF)
+
+    def weights(self, W, net, layer):
+        """W is out x in (Flux); returns the version of the current right-hand side."""
+        tape = self._tape()
+        ck = (net, layer, tape, W.shape, float(W.flat[0]), float(W.flat[-1]))
+        if ck in self._cache:
+            return self._cache[ck]
+        nout, nin = W.shape
+        n, k = np.meshgrid(np.arange(nout, dtype=np.uint32), np.arange(nin, dtype=np.uint32), indexing="ij")
+        out = self._dither(W, self._key(net, layer, k, n), tape)
+        self._cache[ck] = out
+        return out
+
+    def bias(self, b, net, layer):
+        tape = self._tape()
+        ck = ("b", net, layer, tape, b.shape, float(b.flat[0]) if b.size else 0.0)
+        if ck in self._cache:
+            return self._cache[ck]
+        n = np.arange(b.shape[0], dtype=np.uint32)
+        out = self._dither(b, self._key(net, layer, np.full_like(n, 0xFFFF), n), tape)
+        self._cache[ck] = out
+        return out
+
+    def activations(self, h, layer):
+        h = np.ascontiguousarray(h, dtype=np.float32)
+        if layer > 0:
+            return self._rn(h)
+        drop = 13 if self.fp16 else 16
+        t = np.uint32(((self.n0 * self.stages + self.r) * 5061) & 0xFFFFFFFF)
+        idx = np.arange(h.shape[-1], dtype=np.uint32) & np.uint32(7)
+        thr = ((t + idx * np.uint32(1021)) & np.uint32(8191)) << np.uint32(drop - 13)
+        if not self.dither_x:
+            thr = np.full_like(idx, 1 << (drop - 1))
+        with np.errstate(over="ignore"):
+            u = (h.view(np.uint32) + thr) & np.uint32(~((1 << drop) - 1) & 0xFFFFFFFF)
+        v = u.view(np.float32)
+        return np.clip(v, -65504.0, 65504.0) if self.fp16 else v
+
+    def advance(self):
+        self.r += 1
 
 
 @dataclasses.dataclass
@@ -324,8 +432,10 @@ def predict_flux(x: np.ndarray, bc: np.ndarray, t, model: Model, p: Params,
     s_u, s_v, s_T, s_uw, s_vw, s_wT = (dt(s) for s in p.sigma)
     u, v, T = x[:, :Nz], x[:, Nz:2 * Nz], x[:, 2 * Nz:]
 
-    nn = [mlp_forward(x, w.astype(x.dtype, copy=False), model.sizes, model.act, quant)
-          for w in (model.w_uw, model.w_vw, model.w_wT)]
+    nn = [mlp_forward(x, w.astype(x.dtype, copy=False), model.sizes, model.act, quant, net)
+          for net, w in enumerate((model.w_uw, model.w_vw, model.w_wT))]
+    if isinstance(quant, TensorPathEmulation):
+        quant.advance()
     if p.flags & FLAG_SMOOTH_NN:
         nn = [_box3(a) for a in nn]
 

@@ -21,7 +21,7 @@ def ctx(opz):
                                           ((96, 128, 256, 31), 2, 7), ((96, 31), 0, 5)])
 def test_tc_short_rollout_architectures(opz, oracle, ctx, sizes, act, B, prec):
     PREC = opz.PREC_FP16 if prec == "fp16" else opz.PREC_BF16
-    quant = oracle.quant_fp16 if prec == "fp16" else oracle.quant_bf16
+    quant = oracle.TensorPathEmulation(prec, stages=4)   # the kernel's own operand roundings (temporally dithered), on the CPU
     p = oracle.Params()
     x0, bc = oracle.synthetic_columns(B, p)
     m = oracle.make_model(sizes, act, seed=4, out_scale=0.1)
@@ -71,9 +71,9 @@ def test_tc_schemes_and_final_only(opz, oracle, ctx, scheme):
 
 def test_tc_config1_full_two_day_rollout(opz, oracle, golden_dir, ctx):
     """BASELINE configs[0] length (5760 RK4 steps, construct_NN) on the reduced-precision tensor path
-    (IEEE-half operands, FP32 accumulation): within 1e-2 of the FP32 CPU solve at every saved snapshot.
-    The BF16-operand variant is reported too; its 8x coarser rounding lands AT the 1e-2 line on this
-    rollout (measured 1.06e-2), which is why FP16 is the default reduced-precision mode."""
+    (IEEE-half operands, FP32 accumulation, temporally dithered weight / state rounding): within 1e-2 of the FP32 CPU
+    solve at every saved snapshot.  The BF16-operand variant (8x coarser grid) is reported and bounded too.  The full
+    8-day rollout of the benchmarked configuration is tests/test_gpu_long.py."""
     g = np.load(f"{golden_dir}/config1_rk4_2day.npz")
     p = oracle.Params()
     m = oracle.make_model((96, 400, 400, 31), oracle.ACT_RELU, seed=int(g["seed"]), out_scale=float(g["out_scale"]))
@@ -86,8 +86,8 @@ def test_tc_config1_full_two_day_rollout(opz, oracle, golden_dir, ctx):
     errb = oracle.profile_error(outb, g["sol32"], 32)
     print(f"config1 tensor-core rollout: fp16 err vs fp32 oracle {err:.3e}; bf16 err {errb:.3e}")
     assert np.isfinite(out).all() and np.isfinite(outb).all()
-    assert err < TOL_BF16
-    assert errb < 3e-2
+    assert err < 1e-3       # (plainly rounded FP16 operands: 1.4e-3; dithered: ~1e-4)
+    assert errb < TOL_BF16  # (plainly rounded BF16 operands: 1.06e-2)
     model.close()
 
 
@@ -124,7 +124,7 @@ def test_tc_nonzero_biases(opz, oracle, ctx, sizes, act, B, prec):
     """Flux initialises biases to zero, trained models do not keep them there: every Dense bias non-zero (the tensor-core
     path folds the hidden biases into the weight tape as an extra k-step against a constant-one operand)."""
     PREC = opz.PREC_FP16 if prec == "fp16" else opz.PREC_BF16
-    quant = oracle.quant_fp16 if prec == "fp16" else oracle.quant_bf16
+    quant = oracle.TensorPathEmulation(prec, stages=4)
     p = oracle.Params()
     x0, bc = oracle.synthetic_columns(B, p)
     m = oracle.make_model(sizes, act, seed=11, out_scale=0.1, bias_scale=0.3)
