@@ -30,6 +30,7 @@
 #include <cstring>
 #include <vector>
 #include "opz_internal.h"
+#include "opz_faces.cuh"
 
 namespace opz {
 namespace bptt {
@@ -304,7 +305,11 @@ __global__ void __launch_bounds__(1024) final_fwd_kernel(const __grid_constant__
     float Fu, Fv, FT;
     if (f == 0) { Fu = bc[0] - P.off[0]; Fv = bc[2] - P.off[1]; FT = bc[4] - P.off[2]; }
     else if (f == nz) { Fu = bc[1] - P.off[0]; Fv = bc[3] - P.off[1]; FT = wT_top_value(P, bc, ts); }
-    else {
+    else if (P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {   // box-filtered NN outputs / Richardson numbers (opz_faces.cuh)
+      float F3[3];
+      faces::forward_filtered(P, xs, ypart, 1, 0, f, F3);
+      Fu = F3[0]; Fv = F3[1]; FT = F3[2];
+    } else {
       Fu = ypart[f - 1]; Fv = ypart[nout + f - 1]; FT = ypart[2 * nout + f - 1];
       if (P.flags & OPZ_FLAG_MPP) {
         const float gu = (xs[f] - xs[f - 1]) * P.nzf;
@@ -401,7 +406,15 @@ __global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__
   if (tid <= nz) {
     const int f = tid;
     float gbu = 0.0f, gbv = 0.0f, gbT = 0.0f;
-    if (f > 0 && f < nz) {
+    if (f > 0 && f < nz && (P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI))) {
+      float dy3[3], gb3[3];
+      faces::backward_filtered(P, xs, kb, 1, 0, f, dy3, gb3, a.gphys ? gp : nullptr);
+      dy[f - 1] = dy3[0]; dy[nout + f - 1] = dy3[1]; dy[2 * nout + f - 1] = dy3[2];
+      a.DY[((int64_t)0 * a.rows_cap + row) * nout + f - 1] = dy3[0];
+      a.DY[((int64_t)1 * a.rows_cap + row) * nout + f - 1] = dy3[1];
+      a.DY[((int64_t)2 * a.rows_cap + row) * nout + f - 1] = dy3[2];
+      gbu = gb3[0]; gbv = gb3[1]; gbT = gb3[2];
+    } else if (f > 0 && f < nz) {
       const float Fbu = P.A_u * P.nzf * (kb[f - 1] - kb[f]);
       const float Fbv = P.A_v * P.nzf * (kb[nz + f - 1] - kb[nz + f]);
       const float FbT = P.A_T * P.nzf * (kb[2 * nz + f - 1] - kb[2 * nz + f]);
@@ -775,10 +788,6 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   const size_t P3 = 3 * (size_t)nd.P;
   cudaStream_t st = ctx->stream;
   if (L < 2) { set_error("opz_loss_grad: the nets need at least one hidden layer"); return OPZ_EUNSUP; }
-  if (c.r.P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {
-    set_error("opz_loss_grad: smooth_NN / smooth_Ri are not differentiated yet");
-    return OPZ_EUNSUP;
-  }
   OPZ_CUDA(cudaMemsetAsync(c.grad_out, 0, sizeof(float) * P3, st));
   OPZ_CUDA(cudaMemsetAsync(c.loss_out, 0, sizeof(float) * 7, st));
   if (c.gphys_out) OPZ_CUDA(cudaMemsetAsync(c.gphys_out, 0, sizeof(float) * 5, st));
@@ -1177,11 +1186,24 @@ __global__ void __launch_bounds__(256) flux_sample_kernel(NetDesc nd, DevParams 
   for (int j = tid; j < nout; j += blockDim.x) {
     const int f = j + 1;   // interior face
     const float g = 2.0f * res[f] / (float)(nz + 1) + gscale * (2.0f / (float)nz) * P.nzf * (dcs[f - 1] - dcs[f]);
-    const float v = g * invN;
-    dz[j] = v;
-    DY[r * nout + j] = v;
+    dz[j] = g * invN;    // cotangent of the total flux on interior face f
   }
   __syncthreads();
+  if (P.flags & OPZ_FLAG_SMOOTH_NN) {   // the flux holds the box-filtered NN output: d loss / d y = S^T (d loss / d F)
+    float sv[4];                        // (nout <= 127 < 4 * blockDim.x)
+    int cnt = 0;
+    for (int j = tid; j < nout; j += blockDim.x, ++cnt) {
+      float s2 = faces::box_weight(j, nout) * dz[j];
+      if (j > 0) s2 += faces::box_weight(j - 1, nout) * dz[j - 1];
+      if (j < nout - 1) s2 += faces::box_weight(j + 1, nout) * dz[j + 1];
+      sv[cnt] = s2;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int j = tid; j < nout; j += blockDim.x, ++cnt) dz[j] = sv[cnt];
+    __syncthreads();
+  }
+  for (int j = tid; j < nout; j += blockDim.x) DY[r * nout + j] = dz[j];
   // ---- back through the layers: dz_{l-1} = (W_l dz_l) * act'(z_{l-1}), in place over the act' records ----
   float* cur = dz;
   float* nxt = in;    // the last hidden activation is already recorded

@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
         float Fu, Fv, FT;
         if (f == 0) { Fu = bc[0] - P.off[0]; Fv = bc[2] - P.off[1]; FT = bc[4] - P.off[2]; }
         else if (f == nz) { Fu = bc[1] - P.off[0]; Fv = bc[3] - P.off[1]; FT = wT_top_value(P, bc, ts); }
-        else {
+        else if (P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {   // box-filtered NN outputs / Richardson numbers (opz_faces.cuh)
+          float F3[3];
+          faces::forward_filtered(P, xs, yb, CP, c, f, F3);
+          Fu = F3[0]; Fv = F3[1]; FT = F3[2];
+        } else {
           Fu = yb[(f - 1) * CP + c]; Fv = yb[(nout + f - 1) * CP + c]; FT = yb[(2 * nout + f - 1) * CP + c];
           if (P.flags & OPZ_FLAG_MPP) {
             const float gu = (xs[f * CP + c] - xs[(f - 1) * CP + c]) * P.nzf;
@@ -407,7 +411,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
       if (t < (nz + 1) * CP) {
         const int f = tq, c = tc;
         float gbu = 0.0f, gbv = 0.0f, gbT = 0.0f;
-        if (f > 0 && f < nz) {
+        if (f > 0 && f < nz && (P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI))) {
+          float dy3[3], gb3[3];
+          faces::backward_filtered(P, xs, kbar, CP, c, f, dy3, gb3, (a.gphys && rank == 0 && col_ok) ? gp : nullptr);
+          dy[(f - 1) * CP + c] = dy3[0]; dy[(nout + f - 1) * CP + c] = dy3[1]; dy[(2 * nout + f - 1) * CP + c] = dy3[2];
+          dy_u = dy3[0]; dy_v = dy3[1]; dy_T = dy3[2];
+          gbu = gb3[0]; gbv = gb3[1]; gbT = gb3[2];
+        } else if (f > 0 && f < nz) {
           const float Fbu = P.A_u * P.nzf * (kbar[(f - 1) * CP + c] - kbar[f * CP + c]);
           const float Fbv = P.A_v * P.nzf * (kbar[(nz + f - 1) * CP + c] - kbar[(nz + f) * CP + c]);
           const float FbT = P.A_T * P.nzf * (kbar[(2 * nz + f - 1) * CP + c] - kbar[(2 * nz + f) * CP + c]);

@@ -271,10 +271,6 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
     return OPZ_EUNSUP;
   }
   if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16) {
-    if (c.P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {
-      set_error("tensor-core path: smooth_NN / smooth_Ri are only available with OPZ_PREC_FP32");
-      return OPZ_EUNSUP;
-    }
     opz_model* mm = const_cast<opz_model*>(m);  // the packed weight tape is a cache
     if (!m->tc_pack_valid || m->tc_pack_precision != precision) {
       if ((rc = tc2_model_prepare(mm, precision))) return rc;
@@ -469,7 +465,6 @@ int opz_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const opz_params* p, in
   if (which_net < 0 || which_net > 2) { set_error("which_net must be 0 (uw), 1 (vw) or 2 (wT)"); return OPZ_EINVAL; }
   if (N < 0 || (N > 0 && (!x || !bc || !flux_target)) || !loss_out || !grad_out) { set_error("null buffer or negative N"); return OPZ_EINVAL; }
   if (m->nd.n_layers < 2) { set_error("opz_flux_loss_grad: the nets need at least one hidden layer"); return OPZ_EUNSUP; }
-  if (p->flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) { set_error("opz_flux_loss_grad: smooth_NN / smooth_Ri are not differentiated yet"); return OPZ_EUNSUP; }
   OPZ_CUDA(cudaSetDevice(ctx->device));
   const size_t S = 3 * (size_t)m->nz, nf = (size_t)m->nz + 1, P1 = (size_t)m->nd.P;
   float *dx, *dbc, *dt, *dg;

@@ -194,7 +194,10 @@ __device__ __forceinline__ void issue_hf_group(int grp, uint32_t d, uint32_t a0,
 }
 
 // E epilogue warps per CTA: E / 4 threads share one ocean column (TMEM lane); each owns LV = 128 / E cells.
-template <bool FP16, int ACT, int E, bool PROF>
+// SMOOTH compiles in the 3-point box filters on the NN outputs and on the Richardson numbers (flags OPZ_FLAG_SMOOTH_NN /
+// OPZ_FLAG_SMOOTH_RI; filtering_operators.jl:1-15 at NDE_training.jl:98-102,121-123): a separate instantiation, so that the
+// unfiltered kernel keeps its registers and code size.
+template <bool FP16, int ACT, int E, bool PROF, bool SMOOTH = false>
 __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __grid_constant__ Args a) {
   constexpr int kThreads = (3 + E) * 32;
   constexpr int kMma2Warp = 2 + E;     // second MMA-issuing warp (the epilogue warps keep indices 2 .. 1 + E: warp % 4 = TMEM quadrant)
@@ -676,10 +679,13 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const int c0s = decltype(c0c)::value >= 0 ? decltype(c0c)::value : c0;
             // branch-free on purpose (clamped loads, selects): the LV + 1 faces are independent dependency chains that the
             // scheduler can only interleave inside one basic block; values computed for a boundary face are discarded
-            float xu[LV + 2], xw[LV + 2], xT[LV + 2];
+            // x index i is cell c0 - XO + i (clamped into the column: the differences across a boundary face come out zero,
+            // which is what the first / last row of D^f gives)
+            constexpr int XO = SMOOTH ? 2 : 1;
+            float xu[LV + 2 * XO], xw[LV + 2 * XO], xT[LV + 2 * XO];
 #pragma unroll
-            for (int i = 0; i < LV + 2; ++i) {
-              const int cell = min(max(c0s - 1 + i, 0), kNz - 1);
+            for (int i = 0; i < LV + 2 * XO; ++i) {
+              const int cell = min(max(c0s - XO + i, 0), kNz - 1);
               xu[i] = s_xs[cell * kM + m];
               xw[i] = s_xs[(kNz + cell) * kM + m];
               xT[i] = s_xs[(2 * kNz + cell) * kM + m];
@@ -687,13 +693,25 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const bool mpp = P.flags & OPZ_FLAG_MPP;
             const bool ca = mpp && (P.flags & OPZ_FLAG_CA);
             const bool ca_du = P.flags & OPZ_FLAG_CA_SELECT_DUDZ;
+            // smooth_Ri: raw Richardson numbers of faces c0 - 1 .. c0 + LV + 1 (index g is face c0 - 1 + g), filtered below
+            float Rr[SMOOTH ? LV + 3 : 1];
+            const bool smooth_ri = SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_RI);
+            if constexpr (SMOOTH) {
+#pragma unroll
+              for (int g2 = 0; g2 < LV + 3; ++g2) {
+                const float Bz = fmaf(a.pk[PK_KBZ], xT[g2 + 1] - xT[g2], a.pk[PK_EBZ]);
+                const float sa = fmaf(a.pk[PK_KSA], xu[g2 + 1] - xu[g2], a.pk[PK_ESA]);
+                const float sb = fmaf(a.pk[PK_KSB], xw[g2 + 1] - xw[g2], a.pk[PK_ESB]);
+                Rr[g2] = Bz * rcp_ftz(sa * sa + sb * sb);
+              }
+            }
 #pragma unroll
             for (int i = 0; i <= LV; ++i) {
               const int f = c0s + i;
               const int jb = max(f - 1, 0);   // NN output (and its bias) on this face
-              const float du = xu[i + 1] - xu[i];
-              const float dv = xw[i + 1] - xw[i];
-              const float dT = xT[i + 1] - xT[i];
+              const float du = xu[i + XO] - xu[i + XO - 1];
+              const float dv = xw[i + XO] - xw[i + XO - 1];
+              const float dT = xT[i + XO] - xT[i + XO - 1];
               // = richardson<true>, nu_of_ri<true>, nuT_of<true> of opz_device.cuh with the flag tests hoisted and the constant
               // factors folded (Args::pk): Bz = cBz (Nz dT + eps), sa = s_u (Nz du + eps), sb likewise
               const float Bz = fmaf(a.pk[PK_KBZ], dT, a.pk[PK_EBZ]);
@@ -701,21 +719,24 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               const float sb = fmaf(a.pk[PK_KSB], dv, a.pk[PK_ESB]);
               // flush-to-zero approximations without range fix-ups: 0 / 0 stays NaN (0 * inf), the exponent is clamped so that
               // e^{..} stays finite (nu -> nu0 in that tail to FP32 precision anyway)
-              const float Ri = Bz * rcp_ftz(sa * sa + sb * sb);
+              float Ri = Bz * rcp_ftz(sa * sa + sb * sb);
+              if constexpr (SMOOTH) { if (smooth_ri) Ri = (Rr[i] + Rr[i + 1] + Rr[i + 2]) * (1.0f / 3.0f); }
               const float nu_raw = P.nu0 + P.nu_m * rcp_ftz(1.0f + ex2_ftz(fminf(fmaf(Ri, a.pk[PK_C2], a.pk[PK_R2]), 120.0f)));
               const float nu = mpp ? nu_raw : 0.0f;   // a select, not a factor: a NaN Ri must not leak when mPP is off
               const float sel = ca_du ? du : dT;   // Nz > 0: the raw difference has the gradient's sign
               const float nuT = (ca && !(sel > 0.0f)) ? P.kappa : nu * P.inv_Pr;
               // diffusive flux minus the output-layer bias: the total flux of an interior face is then y_raw - D (the values
-              // computed for a boundary face are discarded by the flux select below)
-              Du[i] = fmaf(a.pk[PK_CUN] * nu, du, -a.b3[jb]);
-              Dv[i] = fmaf(a.pk[PK_CVN] * nu, dv, -a.b3[32 + jb]);
-              DT[i] = fmaf(a.pk[PK_CTN] * nuT, dT, -a.b3[64 + jb]);
+              // computed for a boundary face are discarded by the flux select below).  With smooth_NN the bias is added to the
+              // raw outputs before the filter instead (part B).
+              const bool fold_bias = !(SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_NN));
+              Du[i] = fmaf(a.pk[PK_CUN] * nu, du, fold_bias ? -a.b3[jb] : 0.0f);
+              Dv[i] = fmaf(a.pk[PK_CVN] * nu, dv, fold_bias ? -a.b3[32 + jb] : 0.0f);
+              DT[i] = fmaf(a.pk[PK_CTN] * nuT, dT, fold_bias ? -a.b3[64 + jb] : 0.0f);
             }
 #pragma unroll
             for (int i = 0; i < LV; ++i) {
-              cu[i] = fmaf(a.pk[PK_CCU], xw[i + 1], a.pk[PK_DCU]);   //  cor_u (s_v v + mu_v)
-              cv[i] = fmaf(a.pk[PK_CCV], xu[i + 1], a.pk[PK_DCV]);   // -cor_v (s_u u + mu_u)
+              cu[i] = fmaf(a.pk[PK_CCU], xw[i + XO], a.pk[PK_DCU]);   //  cor_u (s_v v + mu_v)
+              cv[i] = fmaf(a.pk[PK_CCV], xu[i + XO], a.pk[PK_DCV]);   // -cor_v (s_u u + mu_u)
             }
                     };
           if constexpr (LV == 16) {
@@ -753,12 +774,38 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               if (c0 > 0) ylo = ptx::tmem_ld1(ybase + (uint32_t)(c0 - 1));   // output c0 - 1 (face c0)
               if constexpr (LV == 16) ptx::tmem_ld16(ybase + (uint32_t)c0, yhi);
               else ptx::tmem_ld8(ybase + (uint32_t)c0, yhi);
+              uint32_t ylo2 = 0u, ytop = 0u;   // smooth_NN: one more output on either side (j = c0 - 2 and j = c0 + LV)
+              if constexpr (SMOOTH) {
+                if (c0 > 1) ylo2 = ptx::tmem_ld1(ybase + (uint32_t)(c0 - 2));
+                if (c0 + LV < kNz) ytop = ptx::tmem_ld1(ybase + (uint32_t)(c0 + LV));
+              }
               ptx::tmem_wait_ld();
               const float* D = v == 0 ? Du : (v == 1 ? Dv : DT);
+              if (SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_NN)) {
+                // yy[q] = raw output j = c0 - 2 + q plus its bias, q = 0 .. LV + 2; face c0 + i takes the filtered output j = c0 + i - 1
+                float yy[LV + 3];
+                constexpr int n = kNz - 1;
 #pragma unroll
-              for (int i = 0; i <= LV; ++i) {
-                const float y = i == 0 ? __uint_as_float(ylo) : __uint_as_float(yhi[i == 0 ? 0 : i - 1]);
-                F[i] = (i == 0 && c0 == 0) ? Fb[v] : ((i == LV && c0 + LV == kNz) ? Ft[v] : y - D[i]);
+                for (int q2 = 0; q2 < LV + 3; ++q2) {
+                  const int j = c0 - 2 + q2;
+                  const uint32_t raw = q2 == 0 ? ylo2 : (q2 == 1 ? ylo : (q2 == LV + 2 ? ytop : yhi[q2 >= 2 && q2 < LV + 2 ? q2 - 2 : 0]));
+                  yy[q2] = (j >= 0 && j < n) ? __uint_as_float(raw) + a.b3[v * 32 + min(max(j, 0), n - 1)] : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i <= LV; ++i) {
+                  const int j = c0 + i - 1;
+                  float y;
+                  if (j <= 0) y = (yy[i + 1] + yy[i + 2]) * 0.5f;
+                  else if (j >= n - 1) y = (yy[i] + yy[i + 1]) * 0.5f;
+                  else y = (yy[i] + yy[i + 1] + yy[i + 2]) * (1.0f / 3.0f);
+                  F[i] = (i == 0 && c0 == 0) ? Fb[v] : ((i == LV && c0 + LV == kNz) ? Ft[v] : y - D[i]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i <= LV; ++i) {
+                  const float y = i == 0 ? __uint_as_float(ylo) : __uint_as_float(yhi[i == 0 ? 0 : i - 1]);
+                  F[i] = (i == 0 && c0 == 0) ? Fb[v] : ((i == LV && c0 + LV == kNz) ? Ft[v] : y - D[i]);
+                }
               }
             }
 #pragma unroll
@@ -1102,7 +1149,14 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   static const KernelT table[2][2][6] = {{OPZ_TC2_ROW(false, 8), OPZ_TC2_ROW(true, 8)}, {OPZ_TC2_ROW(false, 16), OPZ_TC2_ROW(true, 16)}};
 #undef OPZ_TC2_ROW
   KernelT kern = table[E == 16 ? 1 : 0][fp16 ? 1 : 0][pl->act];
-  if (profile) {
+  if (c.P.flags & (OPZ_FLAG_SMOOTH_NN | OPZ_FLAG_SMOOTH_RI)) {   // box-filter instantiations: 8 epilogue warps only
+#define OPZ_TC2_SROW(F) {rollout_tc2_kernel<F, 0, 8, false, true>, rollout_tc2_kernel<F, 1, 8, false, true>, rollout_tc2_kernel<F, 2, 8, false, true>, \
+                         rollout_tc2_kernel<F, 3, 8, false, true>, rollout_tc2_kernel<F, 4, 8, false, true>, rollout_tc2_kernel<F, 5, 8, false, true>}
+    static const KernelT stable[2][6] = {OPZ_TC2_SROW(false), OPZ_TC2_SROW(true)};
+#undef OPZ_TC2_SROW
+    kern = stable[fp16 ? 1 : 0][pl->act];
+    E = 8;
+  } else if (profile) {
     if (pl->act == OPZ_ACT_MISH) kern = E == 16 ? rollout_tc2_kernel<true, OPZ_ACT_MISH, 16, true> : rollout_tc2_kernel<true, OPZ_ACT_MISH, 8, true>;
     else if (E == 16) kern = fp16 ? rollout_tc2_kernel<true, OPZ_ACT_RELU, 16, true> : rollout_tc2_kernel<false, OPZ_ACT_RELU, 16, true>;
     else kern = fp16 ? rollout_tc2_kernel<true, OPZ_ACT_RELU, 8, true> : rollout_tc2_kernel<false, OPZ_ACT_RELU, 8, true>;

@@ -357,3 +357,86 @@ def test_train_NDE_host_loop_learns_on_synthetic_les_shaped_data(opz, oracle, ct
     w_new, _ = opz.destructure(uw2)
     w_old, _ = opz.destructure(uw_NN)
     assert w_new.shape == w_old.shape and not np.array_equal(w_new, w_old)
+
+
+@pytest.mark.parametrize("path", ["cluster", "graph"])
+@pytest.mark.parametrize("sizes,act,B,which", [((96, 50, 20, 31), 3, 5, "both"), ((96, 400, 400, 31), 1, 18, "both"),
+                                                ((96, 64, 31), 4, 3, "nn"), ((96, 40, 30, 20, 31), 2, 9, "ri")])
+def test_loss_grad_with_box_filters(opz, oracle, ctx, monkeypatch, path, sizes, act, B, which):
+    """smooth_NN / smooth_Ri (3-point box filters of the training path, filtering_operators.jl:1-15 at NDE_training.jl:98-102,
+    121-123) in the forward solve AND in its adjoint, on both BPTT layouts, against the float64 autograd twin; the gradient
+    w.r.t. the five mPP parameters as well (the filtered Richardson number enters d nu / d Ric and d nu / d dRi)."""
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    fl |= {"both": O.FLAG_SMOOTH_NN | O.FLAG_SMOOTH_RI, "nn": O.FLAG_SMOOTH_NN, "ri": O.FLAG_SMOOTH_RI}[which]
+    n_steps, save_every = 12, 4
+    p, x0, bc, m, m_true, dt = _case(O, fl, sizes, act, B, n_steps, save_every, seed=3)
+    target = O.rollout(x0, bc, m_true, p, 2, dt, n_steps, save_every)
+    lw = np.array([1.0, 0.7, 1.3, 5e-3, 4e-3, 6e-3], dtype=np.float32)
+    if path == "graph":
+        monkeypatch.setenv("OPZ_BPTT_NO_CLUSTER", "1")
+    model = product_model(opz, m)
+    total, comps, grad, gm = opz.loss_grad_mpp(model, product_params(opz, p), x0, bc, target, lw, 2, dt, n_steps, save_every)
+    tr, cr, gr, gmr = OT.loss_and_grad(x0, bc, m, p, 2, dt, n_steps, save_every, target, lw, with_mpp=True)
+    # the filters change the answer at the size of this test (otherwise it would prove nothing)
+    p0 = O.Params(flags=fl & ~(O.FLAG_SMOOTH_NN | O.FLAG_SMOOTH_RI), tau=p.tau)
+    t0, _, g0 = OT.loss_and_grad(x0, bc, m, p0, 2, dt, n_steps, save_every, target, lw)
+    print(f"{path} {sizes} filters={which}: loss {total:.6e} (twin {tr:.6e}, unfiltered {t0:.6e}); grad rel err {_rel_l2(grad, gr):.2e}, "
+          f"mPP grad rel err {_rel_l2(gm, gmr):.2e}; filter effect on grad {_rel_l2(g0, gr):.2e}")
+    assert _rel_l2(g0, gr) > 20 * TOL_GRAD
+    assert abs(total - tr) <= TOL_LOSS * abs(tr)
+    assert np.isfinite(grad).all() and _rel_l2(grad, gr) < TOL_GRAD
+    assert _rel_l2(gm, gmr) < 5e-3
+    model.close()
+
+
+def test_flux_loss_grad_with_smooth_NN(opz, oracle, ctx):
+    """Supervised flux pre-training with the box-filtered NN output (NN_training.jl predict_* with smooth_NN)."""
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    p = O.Params(flags=O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0 | O.FLAG_SMOOTH_NN | O.FLAG_SMOOTH_RI)
+    N, sizes = 37, (96, 50, 20, 31)
+    x, bc = O.synthetic_columns(N, p)
+    x = (x + 0.05 * np.random.default_rng(7).normal(size=x.shape)).astype(np.float32)
+    m = O.make_model(sizes, O.ACT_MISH, seed=3, out_scale=0.1)
+    target = np.random.default_rng(8).normal(size=(N, 33)).astype(np.float32) * 0.1
+    model = product_model(opz, m)
+    for which in range(3):
+        t_ref, l1_ref, l2_ref, g_ref, _ = OT.flux_loss_and_grad(x, bc, m, p, which, target, 1e-2)
+        total, l1, l2, grad = opz.flux_loss_grad(model, product_params(opz, p), which, x, bc, target, 1e-2)
+        assert total == pytest.approx(t_ref, rel=TOL_LOSS)
+        assert _rel_l2(grad, g_ref) < TOL_GRAD, (which, _rel_l2(grad, g_ref))
+    model.close()
+
+
+@pytest.mark.parametrize("mode", ["cluster", "segmented"])
+def test_long_horizon_gradient_fixture(opz, oracle, golden_dir, ctx, monkeypatch, mode):
+    """1 152 RK4 steps (4 608 right-hand sides) of the configs[3]-shaped training step against the committed float64
+    autograd fixture (tests/golden/make_golden_bptt_long.py): the gradient the bench TIMES is a long-horizon one, and rounding
+    in a 4 608-link adjoint chain is a different regime from the 12-step checks above.  `segmented` forces the record budget
+    down so that the rollout is cut into recomputed time segments (the path taken when the records do not fit memory)."""
+    g = np.load(os.path.join(golden_dir, "bptt_long_1152.npz"))
+    O = oracle
+    sizes = (96, 400, 400, 31)
+    p = O.Params(tau=float(g["tau"]), flags=int(g["flags"]))
+    m = O.make_model(sizes, O.ACT_RELU, seed=int(g["seed"]), out_scale=float(g["out_scale"]))
+    n_steps, se, B = int(g["n_steps"]), int(g["save_every"]), g["x0"].shape[0]
+    if mode == "segmented":
+        rec_floats = 96 + 3 * 31 + 6 * (400 + 400)
+        monkeypatch.setenv("OPZ_BPTT_RECORD_BYTES", str(4 * rec_floats * B * 4 * 100 + 64))   # records of 100 steps: 12 segments
+    model = product_model(opz, m)
+    total, comps, grad = opz.loss_grad(model, product_params(opz, p), g["x0"], g["bc"], g["target"], g["loss_w"],
+                                       opz.SCHEME_RK4, float(g["dt_nd"]), n_steps, se)
+    model.close()
+    stride = int(g["stride"])
+    e_sub = _rel_l2(grad[::stride], g["grad_sub"])
+    from tests_golden_blocks import blocks
+    bn = np.array([np.linalg.norm(grad[a:b]) for a, b in blocks(m.P, sizes)])
+    e_blk = np.abs(bn - g["block_norms"]) / np.maximum(g["block_norms"], 1e-30)
+    print(f"long-horizon BPTT ({mode}): loss {total:.6e} (fixture {float(g['total']):.6e}); gradient rel L2 err on the stored "
+          f"sample {e_sub:.2e}; worst block-norm err {e_blk.max():.2e}; |grad| {np.linalg.norm(grad):.4e} (fixture {float(g['grad_norm']):.4e})")
+    assert abs(total - float(g["total"])) <= TOL_LOSS * float(g["total"])
+    assert np.isfinite(grad).all() and e_sub < TOL_GRAD
+    assert e_blk.max() < 5e-3
+    assert abs(np.linalg.norm(grad) - float(g["grad_norm"])) <= TOL_GRAD * float(g["grad_norm"])

@@ -148,14 +148,38 @@ def test_tc_nonzero_biases(opz, oracle, ctx, sizes, act, B, prec):
     model.close()
 
 
-def test_tc_rejects_unsupported(opz, oracle, ctx):
-    p = oracle.Params(flags=oracle.FLAG_MPP | oracle.FLAG_RI_EPS | oracle.FLAG_SMOOTH_NN)
-    x0, bc = oracle.synthetic_columns(3, p)
-    m = oracle.make_model((96, 50, 20, 31), oracle.ACT_MISH, seed=1)
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("sizes,act,B,which", [((96, 400, 400, 31), 1, 150, "both"), ((96, 50, 20, 31), 3, 129, "both"),
+                                                ((96, 400, 31), 4, 40, "nn"), ((96, 50, 20, 31), 3, 33, "ri")])
+def test_tc_box_filters(opz, oracle, ctx, sizes, act, B, which, prec):
+    """smooth_NN / smooth_Ri (filtering_operators.jl:1-15 at NDE_training.jl:98-102,121-123) on the tensor-core path: the
+    filtered outputs / Richardson numbers of the two threads that share an ocean column meet at cell 16, and the edge rows of
+    the filter sit on faces 1 and 31."""
+    O = oracle
+    PREC = opz.PREC_FP16 if prec == "fp16" else opz.PREC_BF16
+    fl = O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0
+    fl |= {"both": O.FLAG_SMOOTH_NN | O.FLAG_SMOOTH_RI, "nn": O.FLAG_SMOOTH_NN, "ri": O.FLAG_SMOOTH_RI}[which]
+    p = O.Params(flags=fl)
+    x0, bc = O.synthetic_columns(B, p)
+    x0 = (x0 + 0.02 * np.random.default_rng(5).normal(size=x0.shape)).astype(np.float32)
+    m = O.make_model(sizes, act, seed=6, out_scale=0.1, bias_scale=0.2)
     model = product_model(opz, m)
-    with pytest.raises(opz.OpzError) as e:
-        opz.rollout_forward(model, product_params(opz, p), x0, bc, opz.SCHEME_RK4, 1e-4, 4, 2, precision=opz.PREC_FP16)
-    assert e.value.code == opz.OPZ_EUNSUP
+    pp = product_params(opz, p)
+    dt = 30.0 / p.tau
+    out = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 24, 8, precision=PREC)
+    ref = O.rollout(x0, bc, m, p, O.SCHEME_RK4, dt, 24, 8)
+    refq = O.rollout(x0, bc, m, p, O.SCHEME_RK4, dt, 24, 8, quant=O.TensorPathEmulation(prec, stages=4))
+    p0 = O.Params(flags=fl & ~(O.FLAG_SMOOTH_NN | O.FLAG_SMOOTH_RI))
+    ref0 = O.rollout(x0, bc, m, p0, O.SCHEME_RK4, dt, 24, 8)
+    err, errq, effect = O.profile_error(out, ref, 32), O.profile_error(out, refq, 32), O.profile_error(ref0, ref, 32)
+    print(f"{sizes} filters={which}: {prec} vs fp32 oracle {err:.2e}; vs emulating oracle {errq:.2e}; filter effect {effect:.2e}")
+    assert np.isfinite(out).all()
+    assert effect > 20 * max(err, 1e-5)           # the filters matter at the size of this test
+    assert err < (TOL_BF16 if prec == "bf16" else 2e-3)
+    assert errq < (5e-3 if prec == "bf16" else 5e-4)
+    # and the FP32 path agrees with itself through the same flags
+    o32 = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 24, 8)
+    assert O.profile_error(o32, ref, 32) < 2e-5
     model.close()
 
 
