@@ -68,6 +68,8 @@ struct Args {
   float* KBAR;           // [B][3nz] cotangent of the current stage's tendency
   float* XSUM;           // [B][3nz] sum of the stage-input cotangents of the step
   float* XPHYS;          // [B][3nz] physics part of the current stage-input cotangent
+  float* XSTAR;          // OPZ_IMEX_EULER: [n_steps][B][3nz] the explicit half-step results x* (null otherwise)
+  uint32_t imex_flags;   // OPZ_IMEX_EULER: the caller's full flag set (P.flags then holds the explicit part's: no diffusion)
   double* loss_part;     // [B][6]
   float* loss_out;       // [7]
   float* grad;           // [3P]
@@ -491,6 +493,158 @@ __global__ void __launch_bounds__(1024) first_bwd_kernel(const __grid_constant__
   }
 }
 
+// ---- split implicit step (OPZ_IMEX_EULER): x* = x_n + h k_ex(x_n), then (I + L(nu(x*))) x_{n+1} = x* per variable ------
+// (NDE_oceananigans.jl:61-101; forward twin: rollout_fp32_kernel, oracle step_imex).  L is the tridiagonal diffusion operator
+// with D_f = coef nu_f(x*) on the interior faces: symmetric, so the adjoint solve is the same Thomas solve.
+//   forward   x* (written by final_fwd_kernel as the Euler result) -> XSTAR[n]; solve -> XN[n+1] and the next stage input
+//   backward  lam = dL/dx_{n+1}:  mu_v = M_v^{-1} lam_v;  dL/dD_f = -(mu_f - mu_{f-1}) (x_f - x_{f-1})  (x = x_{n+1});
+//             nubar_f = coef (dD^u + dD^v + [keep] dD^T / Pr);  Ribar -> gradient cotangents -> x*bar = mu + D^f-transpose terms;
+//             LAM <- x*bar, KBAR <- h x*bar, after which the explicit Euler adjoint of the step runs unchanged.
+// One thread per column (the training batch is 18 columns and this is a serial recurrence over the Nz cells).
+struct ImexFaces {
+  float ri_raw[kMaxNz + 1], ri_s[kMaxNz + 1], th[kMaxNz + 1], nu[kMaxNz + 1];
+  bool keep[kMaxNz + 1];
+};
+__device__ void imex_diffusivities(const DevParams& P, const float* xs, ImexFaces& F) {
+  const int nz = P.nz;
+  for (int f = 0; f <= nz; ++f) {
+    const bool in = f > 0 && f < nz;
+    const float gu = in ? (xs[f] - xs[f - 1]) * P.nzf : 0.0f;
+    const float gv = in ? (xs[nz + f] - xs[nz + f - 1]) * P.nzf : 0.0f;
+    const float gT = in ? (xs[2 * nz + f] - xs[2 * nz + f - 1]) * P.nzf : 0.0f;
+    F.ri_raw[f] = richardson(P, gu, gv, gT);
+    F.keep[f] = !(P.flags & OPZ_FLAG_CA) || (((P.flags & OPZ_FLAG_CA_SELECT_DUDZ) ? gu : gT) > 0.0f);
+  }
+  for (int f = 1; f < nz; ++f) {
+    F.ri_s[f] = (P.flags & OPZ_FLAG_SMOOTH_RI) ? (F.ri_raw[f - 1] + F.ri_raw[f] + F.ri_raw[f + 1]) * (1.0f / 3.0f) : F.ri_raw[f];
+    F.th[f] = tanhf((F.ri_s[f] - P.Ric) / P.dRi);
+    F.nu[f] = P.nu0 + P.nu_m * ((1.0f - F.th[f]) / 2.0f);
+  }
+}
+// (I + L) sol = rhs with D[f] on faces 0..nz (D[0] = D[nz] = 0); cp is scratch
+__device__ void imex_thomas(const float* D, const float* rhs, float* sol, float* cp, int nz) {
+  float den = 1.0f + D[0] + D[1];
+  cp[0] = -D[1] / den;
+  sol[0] = rhs[0] / den;
+  for (int c = 1; c < nz; ++c) {
+    den = (1.0f + D[c] + D[c + 1]) + D[c] * cp[c - 1];
+    cp[c] = -D[c + 1] / den;
+    sol[c] = (rhs[c] + D[c] * sol[c - 1]) / den;
+  }
+  for (int c = nz - 2; c >= 0; --c) sol[c] = sol[c] - cp[c] * sol[c + 1];
+}
+__device__ __forceinline__ float imex_coef(const DevParams& P, float h, int v) {   // dt nu / dz^2 per unit nu, as in rollout_fp32_kernel
+  return v == 0 ? h * (-P.A_u) * P.c_u * P.nzf * P.nzf : (v == 1 ? h * (-P.A_v) * P.c_v * P.nzf * P.nzf : h * (-P.A_T) * P.c_T * P.nzf * P.nzf);
+}
+
+__global__ void __launch_bounds__(32) imex_fwd_kernel(const __grid_constant__ Args a, int dn) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.B) return;
+  DevParams P = a.P;
+  P.flags = a.imex_flags;
+  const int nz = P.nz, S3 = a.S3;
+  const int n = a.cur->n + dn;
+  float* xnew = a.XN + ((int64_t)(n + 1) * a.B + col) * S3;      // holds x* on entry
+  float* xstar = a.XSTAR + ((int64_t)n * a.B + col) * S3;
+  float xs[3 * kMaxNz];
+  for (int i = 0; i < S3; ++i) { xs[i] = xnew[i]; xstar[i] = xs[i]; }
+  ImexFaces F;
+  imex_diffusivities(P, xs, F);
+  float D[kMaxNz + 1], cp[kMaxNz], sol[kMaxNz];
+  const int q = rec_index(a, n, 0);
+  int qn;
+  if (a.record) qn = q + 1 < a.rcap ? q + 1 : -1;
+  else qn = 0;
+  for (int v = 0; v < 3; ++v) {
+    const float coef = imex_coef(P, a.h, v);
+    D[0] = 0.0f; D[nz] = 0.0f;
+    for (int f = 1; f < nz; ++f) D[f] = coef * (v < 2 ? F.nu[f] : (F.keep[f] ? F.nu[f] / P.Pr : P.kappa));
+    imex_thomas(D, xs + v * nz, sol, cp, nz);
+    for (int c = 0; c < nz; ++c) {
+      xnew[v * nz + c] = sol[c];
+      if (qn >= 0) a.X[((int64_t)qn * a.B + col) * S3 + v * nz + c] = sol[c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) imex_bwd_kernel(const __grid_constant__ Args a, int dn) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float gp[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (col < a.B) {
+    DevParams P = a.P;
+    P.flags = a.imex_flags;
+    const int nz = P.nz, S3 = a.S3;
+    const int n = a.cur->n + dn;
+    const float* xnew = a.XN + ((int64_t)(n + 1) * a.B + col) * S3;
+    const float* xstar = a.XSTAR + ((int64_t)n * a.B + col) * S3;
+    float xs[3 * kMaxNz];
+    for (int i = 0; i < S3; ++i) xs[i] = xstar[i];
+    ImexFaces F;
+    imex_diffusivities(P, xs, F);
+    float D[kMaxNz + 1], cp[kMaxNz], mu[kMaxNz], lamv[kMaxNz], nubar[kMaxNz + 1], xbar[3 * kMaxNz];
+    for (int f = 0; f <= nz; ++f) nubar[f] = 0.0f;
+    for (int v = 0; v < 3; ++v) {
+      const float coef = imex_coef(P, a.h, v);
+      D[0] = 0.0f; D[nz] = 0.0f;
+      for (int f = 1; f < nz; ++f) D[f] = coef * (v < 2 ? F.nu[f] : (F.keep[f] ? F.nu[f] / P.Pr : P.kappa));
+      for (int c = 0; c < nz; ++c) lamv[c] = a.LAM[col * S3 + v * nz + c];
+      imex_thomas(D, lamv, mu, cp, nz);
+      for (int c = 0; c < nz; ++c) xbar[v * nz + c] = mu[c];
+      for (int f = 1; f < nz; ++f) {
+        const float dD = -(mu[f] - mu[f - 1]) * (xnew[v * nz + f] - xnew[v * nz + f - 1]);
+        if (v < 2) nubar[f] += coef * dD;
+        else if (F.keep[f]) {
+          nubar[f] += coef * dD / P.Pr;
+          gp[4] += coef * dD * (-F.nu[f] / (P.Pr * P.Pr));
+        }
+      }
+    }
+    // nu -> Richardson number the face saw -> raw Richardson numbers -> face gradients of x*
+    float ribar_s[kMaxNz + 1];
+    ribar_s[0] = 0.0f; ribar_s[nz] = 0.0f;
+    for (int f = 1; f < nz; ++f) {
+      const float sech2 = 1.0f - F.th[f] * F.th[f];
+      const bool fin = isfinite(F.ri_s[f]);
+      ribar_s[f] = fin ? nubar[f] * (-P.nu_m / (2.0f * P.dRi) * sech2) : 0.0f;
+      gp[0] += nubar[f];
+      gp[1] += nubar[f] * ((1.0f - F.th[f]) / 2.0f);
+      if (fin) {
+        gp[2] += nubar[f] * (P.nu_m / 2.0f * sech2 * (F.ri_s[f] - P.Ric) / (P.dRi * P.dRi));
+        gp[3] += nubar[f] * (P.nu_m / (2.0f * P.dRi) * sech2);
+      }
+    }
+    float gb[3][2];   // cotangents of the three gradients on faces f (slot 1) and f - 1 (slot 0), rolling
+    gb[0][0] = gb[1][0] = gb[2][0] = 0.0f;
+    for (int f = 1; f <= nz; ++f) {
+      float g3[3] = {0.0f, 0.0f, 0.0f};
+      if (f < nz) {
+        float rb = ribar_s[f];
+        if (P.flags & OPZ_FLAG_SMOOTH_RI) rb = (ribar_s[f - 1] + ribar_s[f] + ribar_s[f + 1]) * (1.0f / 3.0f);
+        const float gu = (xs[f] - xs[f - 1]) * P.nzf, gv = (xs[nz + f] - xs[nz + f - 1]) * P.nzf, gT = (xs[2 * nz + f] - xs[2 * nz + f - 1]) * P.nzf;
+        const float ea = P.s_u * (gu + P.eps), eb = P.s_v * (gv + P.eps);
+        const float S2 = ea * ea + eb * eb;
+        const float Ri = P.cBz * (gT + P.eps) / S2;
+        const float dRi_dgT = P.cBz / S2;
+        if (isfinite(Ri) && isfinite(dRi_dgT)) {
+          g3[0] = rb * (-Ri * 2.0f * P.s_u * ea / S2);
+          g3[1] = rb * (-Ri * 2.0f * P.s_v * eb / S2);
+          g3[2] = rb * dRi_dgT;
+        }
+      }
+      for (int v = 0; v < 3; ++v) {
+        gb[v][1] = g3[v];
+        xbar[v * nz + f - 1] += P.nzf * (gb[v][0] - gb[v][1]);   // cell f - 1 is the upper cell of face f - 1, the lower of face f
+        gb[v][0] = gb[v][1];
+      }
+    }
+    for (int i = 0; i < S3; ++i) {
+      a.LAM[col * S3 + i] = xbar[i];
+      a.KBAR[col * S3 + i] = a.rk_b[0] * xbar[i];
+    }
+  }
+  if (a.gphys) mpp_param_flush(gp, a.gphys);
+}
+
 // ---- lambda_N and the first tendency cotangent ----------------------------------------------------------
 __global__ void init_lambda_kernel(const __grid_constant__ Args a) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,6 +949,8 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
 
   const int stages = c.r.scheme == OPZ_RK4 ? 4 : (c.r.scheme == OPZ_RK2 ? 2 : 1);
   const int n_steps = c.r.n_steps;
+  // split implicit step: an Euler step of the explicit part followed by the tridiagonal solve; only the graph path carries it
+  const bool imex = c.r.scheme == OPZ_IMEX_EULER && (c.r.P.flags & OPZ_FLAG_MPP);
 
   // ---- memory plan ----
   size_t rec_floats = S3 + 3 * (size_t)nout;  // per (column, right-hand side)
@@ -805,7 +961,8 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   size_t free_b = 0, total_b = 0;
   OPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += ctx->scratch_bytes[4] + ctx->scratch_bytes[5];  // our own grow-only buffers can be reused
-  const size_t xn_bytes = sizeof(float) * (size_t)(n_steps + 1) * B * S3;
+  const size_t xn_only = sizeof(float) * (size_t)(n_steps + 1) * B * S3;
+  const size_t xn_bytes = xn_only * (imex ? 2 : 1);   // IMEX keeps the explicit half-step results x* beside the checkpoints
   if (xn_bytes + ((size_t)1 << 30) > free_b) {
     set_error("opz_loss_grad: state checkpoints of " + std::to_string(xn_bytes) + " bytes do not fit device memory");
     return OPZ_ENOMEM;
@@ -837,6 +994,9 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   a.bc = c.r.bc;
   a.target = c.target;
   a.XN = XN;
+  a.XSTAR = imex ? XN + (size_t)(n_steps + 1) * B * S3 : nullptr;
+  a.imex_flags = c.r.P.flags;
+  if (c.r.scheme == OPZ_IMEX_EULER) a.P.flags &= ~(uint32_t)(OPZ_FLAG_MPP | OPZ_FLAG_CA | OPZ_FLAG_SMOOTH_RI);   // the explicit part
   {
     float* p = REC;
     a.X = p; p += (size_t)rows_cap * S3;
@@ -905,7 +1065,7 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
   const bool prof = getenv("OPZ_BPTT_PROFILE") != nullptr;
 
   // ---- cluster path: the whole sweep of a column group inside one 16-CTA cluster (weights in shared memory) ----
-  if (single && n_steps > 0 && !getenv("OPZ_BPTT_NO_CLUSTER")) {
+  if (single && n_steps > 0 && !imex && !getenv("OPZ_BPTT_NO_CLUSTER")) {
     cl::Layout lay;
     int CG = 0, CS = 0, max_active = 0;
     // fewest columns per cluster that still lets all groups run concurrently; else the widest that fits.  Nets whose FP32
@@ -1006,9 +1166,11 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
       }
       final_fwd_kernel<<<(unsigned)B, ff_threads, ff_smem, s>>>(aa, sg, dn);
     }
+    if (imex) imex_fwd_kernel<<<(unsigned)((B + 31) / 32), 32, 0, s>>>(aa, dn);
   };
-  step_kernels_fwd = (int64_t)stages * L;
+  step_kernels_fwd = (int64_t)stages * L + (imex ? 1 : 0);
   auto enqueue_bwd_step = [&](const Args& aa, int dn, cudaStream_t s) {
+    if (imex) imex_bwd_kernel<<<(unsigned)((B + 31) / 32), 32, 0, s>>>(aa, dn);
     for (int sg = stages - 1; sg >= 0; --sg) {
       first_bwd_kernel<<<(unsigned)B, fb_threads, fb_smem, s>>>(aa, sg, dn);
       for (int l = L - 2; l >= 1; --l) {
@@ -1019,7 +1181,7 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
       skinny_kernel<MODE_BWD_IN><<<g, kGemmThreads, gemm_smem, s>>>(aa, 0, sg, dn);
     }
   };
-  step_kernels_bwd = (int64_t)stages * L;
+  step_kernels_bwd = (int64_t)stages * L + (imex ? 1 : 0);
 
   // ---- graphs: U unrolled steps + cursor bump, captured on a private stream ----
   if (!ctx->capture_stream) OPZ_CUDA(cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));

@@ -263,7 +263,6 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
   c.P = make_dev_params(*p);
   c.x0 = x0; c.bc = bc; c.out = out; c.B = B; c.scheme = scheme; c.dt = dt_nd; c.t0 = t0;
   c.n_steps = n_steps; c.save_every = save_every; c.n_save = n_save_of(n_steps, save_every);
-  if (scheme == OPZ_IMEX_EULER && (c.P.flags & OPZ_FLAG_SMOOTH_RI)) { set_error("OPZ_IMEX_EULER: smooth_Ri is not built for the implicit diffusion"); return OPZ_EUNSUP; }
   if (precision == OPZ_PREC_FP32) return fp32_rollout(ctx, m, c);
   if (scheme == OPZ_IMEX_EULER) { set_error("OPZ_IMEX_EULER is built for OPZ_PREC_FP32 only"); return OPZ_EUNSUP; }
   if (precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
@@ -367,7 +366,6 @@ static int loss_grad_dev_impl(opz_ctx* ctx, const opz_model* m, const opz_params
   if (save_every <= 0) { set_error("opz_loss_grad needs save_every > 0"); return OPZ_EINVAL; }
   if (B_total < B || B_total < 1) { set_error("B_total must be >= B and >= 1"); return OPZ_EINVAL; }
   if (precision != OPZ_PREC_FP32) { set_error("opz_loss_grad: only OPZ_PREC_FP32 so far"); return OPZ_EUNSUP; }
-  if (scheme == OPZ_IMEX_EULER) { set_error("opz_loss_grad: the split implicit step is not differentiated yet"); return OPZ_EUNSUP; }
   OPZ_CUDA(cudaSetDevice(ctx->device));
   LossGradCall c{};
   c.r.P = make_dev_params(*p);

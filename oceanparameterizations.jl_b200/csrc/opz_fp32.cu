@@ -141,13 +141,30 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fp32_kernel(const __grid_
               auto CP = [&](int i) -> float& { return s.kacc[i * M + tid]; };
               float Dlo_u = 0.0f, Dlo_v = 0.0f, Dlo_T = 0.0f;     // D on the face below cell c
               float u_lo = XS(0), v_lo = XS(nz), T_lo = XS(2 * nz);   // ORIGINAL values of cell c (read before they are overwritten)
+              // smooth_Ri: raw Richardson numbers of faces c and c + 1 roll along; face c + 2 is formed from cells c + 1, c + 2,
+              // which the elimination has not touched yet
+              const bool smooth_ri = P.flags & OPZ_FLAG_SMOOTH_RI;
+              float Ri_m = 0.0f, Ri_c = 0.0f;
+              if (smooth_ri) {
+                Ri_m = richardson(P, 0.0f, 0.0f, 0.0f);
+                Ri_c = nz > 1 ? richardson(P, (XS(1) - u_lo) * P.nzf, (XS(nz + 1) - v_lo) * P.nzf, (XS(2 * nz + 1) - T_lo) * P.nzf) : Ri_m;
+              }
               for (int c = 0; c < nz; ++c) {
                 float Dhi_u = 0.0f, Dhi_v = 0.0f, Dhi_T = 0.0f;   // face c + 1 (zero on the top boundary)
                 float u_hi = 0.0f, v_hi = 0.0f, T_hi = 0.0f;
                 if (c + 1 < nz) {
                   u_hi = XS(c + 1); v_hi = XS(nz + c + 1); T_hi = XS(2 * nz + c + 1);
                   const float gu = (u_hi - u_lo) * P.nzf, gv = (v_hi - v_lo) * P.nzf, gT = (T_hi - T_lo) * P.nzf;
-                  const float nu = nu_of_ri(P, richardson(P, gu, gv, gT));
+                  float Ri = 0.0f;
+                  if (smooth_ri) {
+                    const float Ri_p = c + 2 < nz ? richardson(P, (XS(c + 2) - u_hi) * P.nzf, (XS(nz + c + 2) - v_hi) * P.nzf, (XS(2 * nz + c + 2) - T_hi) * P.nzf)
+                                                  : richardson(P, 0.0f, 0.0f, 0.0f);
+                    Ri = (Ri_m + Ri_c + Ri_p) * (1.0f / 3.0f);
+                    Ri_m = Ri_c; Ri_c = Ri_p;
+                  } else {
+                    Ri = richardson(P, gu, gv, gT);
+                  }
+                  const float nu = nu_of_ri(P, Ri);
                   const float nuT = nuT_of(P, nu, gu, gT);
                   Dhi_u = coef_u * nu; Dhi_v = coef_v * nu; Dhi_T = coef_T * nuT;
                 }

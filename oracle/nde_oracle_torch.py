@@ -116,7 +116,66 @@ def rhs(x, bc, t, w, sizes, act, p: O.Params, phys=None, return_fluxes=False):
     return torch.cat([du, dv, dT], dim=1).to(dt)
 
 
+def diffusivities(x, p: O.Params, phys=None):
+    """nu, nu_T on the interior faces 1..Nz-1 of the state x (the part of rhs() that the split implicit step needs)."""
+    Nz = p.Nz
+    s_u, s_v, s_T = (float(s) for s in p.sigma[:3])
+    u, v, T = x[:, :Nz], x[:, Nz:2 * Nz], x[:, 2 * Nz:]
+    g = [(c[:, 1:] - c[:, :-1]) * float(Nz) for c in (u, v, T)]
+    e = p.eps if (p.flags & O.FLAG_RI_EPS) else 0.0
+    if p.flags & O.FLAG_SMOOTH_RI:
+        z = torch.zeros_like(g[0][:, :1])
+        gf = [torch.cat([z, a, z], dim=1) for a in g]
+        Ri = (p.H * p.g * p.alpha * s_T * (gf[2] + e)) / ((s_u * (gf[0] + e)) ** 2 + (s_v * (gf[1] + e)) ** 2)
+        Ri = _box3(Ri)[:, 1:-1]
+    else:
+        Ri = (p.H * p.g * p.alpha * s_T * (g[2] + e)) / ((s_u * (g[0] + e)) ** 2 + (s_v * (g[1] + e)) ** 2)
+    nu0, nu_m, dRi, Ric, Pr = (p.nu0, p.nu_m, p.dRi, p.Ric, p.Pr) if phys is None else (phys[0], phys[1], phys[2], phys[3], phys[4])
+    nu = nu0 + nu_m * ((1.0 - torch.tanh((Ri - Ric) / dRi)) / 2.0)
+    if p.flags & O.FLAG_CA:
+        sel = g[0] if (p.flags & O.FLAG_CA_SELECT_DUDZ) else g[2]
+        nuT = torch.where(sel > 0, nu / Pr, torch.full_like(nu, p.kappa))
+    else:
+        nuT = nu / Pr
+    return nu, nuT
+
+
+def step_imex(x, bc, t, h, w, sizes, act, p, phys=None):
+    """Differentiable twin of nde_oracle.step_imex (NDE_oceananigans.jl:61-101): explicit Euler without the vertical
+    diffusion, then backward-Euler diffusion with the diffusivities of the updated state (Thomas algorithm per variable)."""
+    import dataclasses
+    Nz = p.Nz
+    p_ex = dataclasses.replace(p, flags=p.flags & ~(O.FLAG_MPP | O.FLAG_CA | O.FLAG_SMOOTH_RI))
+    xs = x + h * rhs(x, bc, t, w, sizes, act, p_ex, phys)
+    if not (p.flags & O.FLAG_MPP):
+        return xs
+    nu, nuT = diffusivities(xs, p, phys)
+    coef = h * (p.tau / p.H / p.H) * Nz * Nz
+    outs = []
+    zero = torch.zeros_like(xs[:, :1])
+    for v, nn in enumerate((nu, nu, nuT)):
+        D = torch.cat([zero, coef * nn, zero], dim=1)           # faces 0..Nz
+        phi = xs[:, v * Nz:(v + 1) * Nz]
+        cp, dp = [], []
+        b0 = 1.0 + D[:, 0] + D[:, 1]
+        cp.append(-D[:, 1] / b0)
+        dp.append(phi[:, 0] / b0)
+        for c in range(1, Nz):
+            a_c = -D[:, c]
+            den = (1.0 + D[:, c] + D[:, c + 1]) - a_c * cp[c - 1]
+            cp.append(-D[:, c + 1] / den)
+            dp.append((phi[:, c] - a_c * dp[c - 1]) / den)
+        sol = [None] * Nz
+        sol[Nz - 1] = dp[Nz - 1]
+        for c in range(Nz - 2, -1, -1):
+            sol[c] = dp[c] - cp[c] * sol[c + 1]
+        outs.append(torch.stack(sol, dim=1))
+    return torch.cat(outs, dim=1)
+
+
 def step(x, bc, t, h, w, sizes, act, p, scheme, phys=None):
+    if scheme == O.SCHEME_IMEX:
+        return step_imex(x, bc, t, h, w, sizes, act, p, phys)
     if scheme == O.SCHEME_EULER:
         return x + h * rhs(x, bc, t, w, sizes, act, p, phys)
     if scheme == O.SCHEME_RK2:

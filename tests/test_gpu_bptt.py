@@ -440,3 +440,43 @@ def test_long_horizon_gradient_fixture(opz, oracle, golden_dir, ctx, monkeypatch
     assert np.isfinite(grad).all() and e_sub < TOL_GRAD
     assert e_blk.max() < 5e-3
     assert abs(np.linalg.norm(grad) - float(g["grad_norm"])) <= TOL_GRAD * float(g["grad_norm"])
+
+
+@pytest.mark.parametrize("sizes,act,B,flags,kappa", [
+    ((96, 50, 20, 31), 3, 5, "ca", 10.0), ((96, 400, 400, 31), 1, 18, "ca", 10.0), ((96, 64, 31), 4, 7, "train_smooth", 1.0),
+    ((96, 40, 30, 20, 31), 2, 3, "diurnal", 1.0)])
+def test_loss_grad_through_the_split_implicit_step(opz, oracle, ctx, sizes, act, B, flags, kappa):
+    """Gradient through OPZ_IMEX_EULER (explicit NN / boundary / Coriolis step, then backward-Euler vertical diffusion with the
+    diffusivities of the updated state: the reference's production step, NDE_oceananigans.jl:61-101) — including the adjoint
+    of the tridiagonal solve and of its coefficients — against the float64 autograd twin, at a step (dt = 60 s, kappa = 10)
+    where the explicit schemes are unstable.  The five mPP parameters' gradient goes through the same solve."""
+    from oracle import nde_oracle_torch as OT
+    O = oracle
+    fl = {"ca": O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0,
+          "train_smooth": O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_BC_MINUS_SCALE0 | O.FLAG_SMOOTH_NN | O.FLAG_SMOOTH_RI,
+          "diurnal": O.FLAG_MPP | O.FLAG_RI_EPS | O.FLAG_CA | O.FLAG_DIURNAL}[flags]
+    n_steps, save_every = 12, 4
+    p = O.Params(flags=fl, kappa=kappa)
+    x0, bc = O.synthetic_columns(B, p, diurnal=(flags == "diurnal"))
+    x0 = (x0 + 0.02 * np.random.default_rng(4).normal(size=x0.shape)).astype(np.float32)
+    m = O.make_model(sizes, act, seed=2, out_scale=0.1)
+    m_true = O.make_model(sizes, act, seed=102, out_scale=0.1)
+    dt = 60.0 / p.tau
+    target = O.rollout(x0, bc, m_true, p, O.SCHEME_IMEX, dt, n_steps, save_every)
+    lw = np.array([1.0, 0.7, 1.3, 5e-3, 4e-3, 6e-3], dtype=np.float32)
+    model = product_model(opz, m)
+    pp = product_params(opz, p)
+    # forward first: the FP32 rollout of the same scheme sits on the oracle (smooth_Ri inside the implicit part included)
+    sol = opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_IMEX, dt, n_steps, save_every)
+    ref = O.rollout(x0, bc, m, p, O.SCHEME_IMEX, dt, n_steps, save_every)
+    assert O.profile_error(sol, ref, 32) < 2e-5
+    total, comps, grad, gm = opz.loss_grad_mpp(model, pp, x0, bc, target, lw, opz.SCHEME_IMEX, dt, n_steps, save_every, B_total=B + 1)
+    tr, cr, gr, gmr = OT.loss_and_grad(x0, bc, m, p, O.SCHEME_IMEX, dt, n_steps, save_every, target, lw, B_total=B + 1, with_mpp=True)
+    print(f"IMEX {sizes} {flags}: loss {total:.6e} (twin {tr:.6e}); grad rel err {_rel_l2(grad, gr):.2e}; mPP grad {gm} vs {gmr}, rel err {_rel_l2(gm, gmr):.2e}")
+    assert abs(total - tr) <= TOL_LOSS * abs(tr)
+    assert np.isfinite(grad).all() and _rel_l2(grad, gr) < TOL_GRAD
+    assert _rel_l2(gm, gmr) < 5e-3
+    # the implicit part matters: the gradient of the purely explicit Euler step differs
+    _, _, g_ex = OT.loss_and_grad(x0, bc, m, O.Params(flags=fl & ~(O.FLAG_MPP | O.FLAG_CA | O.FLAG_SMOOTH_RI), kappa=kappa), O.SCHEME_EULER, dt, n_steps, save_every, target, lw, B_total=B + 1)
+    assert _rel_l2(g_ex, gr) > 20 * TOL_GRAD
+    model.close()
