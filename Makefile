@@ -5,7 +5,7 @@ PKG := oceanparameterizations.jl_b200
 CSRC := $(PKG)/csrc
 BUILD := build
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -Xptxas -v
-NAMES := opz_capi opz_comm opz_fp32 opz_bptt opz_tc2
+NAMES := opz_capi opz_comm opz_fp32 opz_bptt opz_tc2 opz_gemm
 OBJS := $(NAMES:%=$(BUILD)/%.o)
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/opz.h
 

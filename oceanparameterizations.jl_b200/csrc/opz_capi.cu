@@ -3,6 +3,7 @@
 // are blocking; `_dev` entry points enqueue on the context stream and return.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -181,6 +182,7 @@ int opz_model_create(opz_ctx* ctx, int nz, int n_sizes, const int* sizes, int ac
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { cudaFree(m->w_dev); delete m; return cuda_fail(e, "weights H2D sync"); }
   m->tc_pack_valid = false;
+  m->gm_valid = false;
   ctx->live_models += 1;
   *out = m;
   return OPZ_OK;
@@ -192,6 +194,7 @@ int opz_model_set_weights(opz_model* m, const float* w) {
   OPZ_CUDA(cudaMemcpyAsync(m->w_dev, w, sizeof(float) * 3 * (size_t)m->nd.P, cudaMemcpyHostToDevice, m->ctx->stream));
   OPZ_CUDA(cudaStreamSynchronize(m->ctx->stream));
   m->tc_pack_valid = false;
+  m->gm_valid = false;
   return OPZ_OK;
 }
 
@@ -200,6 +203,7 @@ int opz_model_set_weights_dev(opz_model* m, const float* w) {
   OPZ_CUDA(cudaSetDevice(m->ctx->device));
   OPZ_CUDA(cudaMemcpyAsync(m->w_dev, w, sizeof(float) * 3 * (size_t)m->nd.P, cudaMemcpyDeviceToDevice, m->ctx->stream));
   m->tc_pack_valid = false;
+  m->gm_valid = false;
   return OPZ_OK;
 }
 
@@ -218,6 +222,7 @@ int opz_model_destroy(opz_model* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   tc2_model_release(m);
+  gemm_model_release(m);
   if (m->w_dev) cudaFree(m->w_dev);
   opz_ctx* ctx = m->ctx;
   delete m;
@@ -265,18 +270,23 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
   c.n_steps = n_steps; c.save_every = save_every; c.n_save = n_save_of(n_steps, save_every);
   if (precision == OPZ_PREC_FP32) return fp32_rollout(ctx, m, c);
   if (scheme == OPZ_IMEX_EULER) { set_error("OPZ_IMEX_EULER is built for OPZ_PREC_FP32 only"); return OPZ_EUNSUP; }
-  if (precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
-    set_error("the split-operand tensor-core modes are not built; use OPZ_PREC_FP16, OPZ_PREC_BF16 or OPZ_PREC_FP32");
-    return OPZ_EUNSUP;
-  }
-  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16) {
-    opz_model* mm = const_cast<opz_model*>(m);  // the packed weight tape is a cache
+  if (m->nd.n_layers < 2) { set_error("tensor-core paths: a single Dense layer has no hidden GEMM; use OPZ_PREC_FP32"); return OPZ_EUNSUP; }
+  opz_model* mm = const_cast<opz_model*>(m);  // the packed weight images are caches of w_dev
+  // FP16 / BF16 operands: the fused persistent kernel (opz_tc2.cu) for the shapes it is built for — Nz = 32, hidden <= 400 —
+  // the layered path (opz_gemm.cu) for everything else (Nz = 128, wider / deeper nets); OPZ_FORCE_LAYERED=1 selects the
+  // layered path regardless (cross-checks of the two in the tests)
+  if ((precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16) && tc2_supports(m) && !getenv("OPZ_FORCE_LAYERED")) {
     if (!m->tc_pack_valid || m->tc_pack_precision != precision) {
       if ((rc = tc2_model_prepare(mm, precision))) return rc;
       mm->tc_pack_valid = true;
       mm->tc_pack_precision = precision;
     }
     return tc2_rollout(ctx, m, c, precision);
+  }
+  // split-operand precisions (near-FP32 on the tensor cores) and all other shapes: one batched GEMM per Dense layer
+  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
+    if ((!m->gm_valid || m->gm_precision != precision) && (rc = gemm_model_prepare(mm, precision))) return rc;
+    return gemm_rollout(ctx, m, c, precision);
   }
   set_error("unknown precision");
   return OPZ_EINVAL;
@@ -521,7 +531,9 @@ int opz_mlp_forward(opz_ctx* ctx, const opz_model* m, int which_net, const float
   if (!ctx || !m || !x || !y) { set_error("null argument"); return OPZ_EINVAL; }
   if (m->ctx != ctx) { set_error("model belongs to another context"); return OPZ_EINVAL; }
   if (which_net < 0 || which_net > 2 || Nt < 0) { set_error("which_net must be 0..2, Nt >= 0"); return OPZ_EINVAL; }
-  if (precision != OPZ_PREC_FP32) { set_error("opz_mlp_forward: only OPZ_PREC_FP32"); return OPZ_EUNSUP; }
+  const bool tensor = precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3;
+  if (precision != OPZ_PREC_FP32 && !tensor) { set_error("opz_mlp_forward: unknown precision"); return OPZ_EINVAL; }
+  if (tensor && m->nd.n_layers < 2) { set_error("opz_mlp_forward: a single Dense layer has no hidden GEMM; use OPZ_PREC_FP32"); return OPZ_EUNSUP; }
   if (Nt == 0) return OPZ_OK;
   OPZ_CUDA(cudaSetDevice(ctx->device));
   const size_t S = 3 * (size_t)m->nz, NO = (size_t)m->nz - 1;
@@ -530,7 +542,11 @@ int opz_mlp_forward(opz_ctx* ctx, const opz_model* m, int which_net, const float
   if ((rc = ensure_scratch(ctx, 0, sizeof(float) * Nt * S, (void**)&dx))) return rc;
   if ((rc = ensure_scratch(ctx, 2, sizeof(float) * Nt * NO, (void**)&dy))) return rc;
   OPZ_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * Nt * S, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = fp32_mlp(ctx, m, which_net, dx, Nt, dy))) return rc;
+  if (tensor) {   // the layered tensor path (opz_gemm.cu)
+    opz_model* mm = const_cast<opz_model*>(m);
+    if ((!m->gm_valid || m->gm_precision != precision) && (rc = gemm_model_prepare(mm, precision))) return rc;
+    if ((rc = gemm_mlp(ctx, m, which_net, dx, Nt, precision, dy))) return rc;
+  } else if ((rc = fp32_mlp(ctx, m, which_net, dx, Nt, dy))) return rc;
   OPZ_CUDA(cudaMemcpyAsync(y, dy, sizeof(float) * Nt * NO, cudaMemcpyDeviceToHost, ctx->stream));
   OPZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return OPZ_OK;

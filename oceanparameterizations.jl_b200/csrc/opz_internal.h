@@ -44,6 +44,10 @@ struct opz_model {
   void* tc2_pack = nullptr;
   size_t tc2_pack_bytes = 0;
   void* tc2_plan = nullptr;
+  // layered tensor path (opz_gemm.cu): per-layer weight images (hi [, lo]) + padded biases; a cache of w_dev
+  void* gm_plan = nullptr;
+  bool gm_valid = false;
+  int gm_precision = -1;
 };
 
 namespace opz {
@@ -101,5 +105,11 @@ int fp32_flux_loss_grad(opz_ctx* ctx, const opz_model* m, const DevParams& P, in
 int tc2_model_prepare(opz_model* m, int precision);          // (re)pack weights after set_weights
 void tc2_model_release(opz_model* m);
 int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
+bool tc2_supports(const opz_model* m);   // Nz = 32, two or three Dense layers, hidden widths <= 400
+// layered tensor path (opz_gemm.cu): one batched tcgen05 GEMM per Dense layer; any shape, split-operand precisions
+int gemm_model_prepare(opz_model* m, int precision);
+void gemm_model_release(opz_model* m);
+int gemm_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int precision);
+int gemm_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x_dev, int64_t Nt, int precision, float* y_dev);
 
 }  // namespace opz

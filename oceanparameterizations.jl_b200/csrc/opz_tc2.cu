@@ -1056,6 +1056,14 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
 
 }  // namespace tc2
 
+bool tc2_supports(const opz_model* m) {
+  const int L = m->nd.n_layers;
+  if (m->nz != tc2::kNz || (L != 2 && L != 3)) return false;
+  for (int j = 0; j < L - 1; ++j)
+    if ((m->nd.sizes[j + 1] + 15) / 16 * 16 > tc2::kMaxHidden) return false;
+  return true;
+}
+
 int tc2_model_prepare(opz_model* m, int precision) {
   using namespace tc2;
   const bool fp16 = precision == OPZ_PREC_FP16;

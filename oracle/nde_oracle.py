@@ -210,7 +210,9 @@ def mlp_forward(x: np.ndarray, flat: np.ndarray, sizes: Sequence[int], act: int,
     emu = isinstance(quant, TensorPathEmulation)
     for li, (W, b) in enumerate(layers):
         last = li == len(layers) - 1
-        if emu:
+        if isinstance(quant, SplitOperandEmulation):
+            z = quant.matmul(h, W) + b
+        elif emu:
             z = quant.activations(h, li) @ quant.weights(W, net, li).T + (b if last else quant.bias(b, net, li))
         elif quant is not None:
             z = quant(h) @ quant(W).T + b
@@ -239,6 +241,28 @@ def quant_tf32(a: np.ndarray) -> np.ndarray:
     u = a.view(np.uint32)
     r = ((u >> 13) & 1) + np.uint32(0x0FFF)
     return ((u + r) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+class SplitOperandEmulation:
+    """CPU restatement of the operand handling of the layered tensor path (csrc/opz_gemm.cu): every operand rounded to nearest
+    in the 16-bit format (mode "plain"), the weights additionally split as hi + lo ("x2": h_hi W_hi + h_hi W_lo), or both
+    operands split ("x3": h_hi W_hi + h_hi W_lo + h_lo W_hi), products accumulated in FP32."""
+
+    def __init__(self, fmt: str = "bf16", mode: str = "x3"):
+        assert fmt in ("fp16", "bf16") and mode in ("plain", "x2", "x3")
+        self.q = quant_fp16 if fmt == "fp16" else quant_bf16
+        self.mode = mode
+
+    def matmul(self, h, W):
+        h = np.ascontiguousarray(h, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        hh, wh = self.q(h), self.q(W)
+        z = hh @ wh.T
+        if self.mode != "plain":
+            z = z + hh @ self.q(W - wh).T
+            if self.mode == "x3":
+                z = z + self.q(h - hh) @ wh.T
+        return z
 
 
 class TensorPathEmulation:

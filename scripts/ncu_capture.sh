@@ -17,3 +17,10 @@ BPTT="python bench.py --steps 3 --warmup 3 --no-small --no-fp32 --no-e2e --no-cp
 $BPTT > $O/${T}_plain_bptt.json 2> $O/${T}_plain_bptt.err || exit 1
 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 1 -c 1 -o $O/${T}_bptt_sweep $BPTT > $O/${T}_ncu_bptt.log 2>&1
 ls -la $O/${T}_*.ncu-rep
+# summaries on the box; the reports themselves stay behind except the headline kernel's (gpurun returns at most 64 MiB)
+OUTDIR=$O scripts/ncu_summary.sh ${T}_tc2_construct ${T}_tc2_small ${T}_bptt_sweep
+for n in ${T}_tc2_construct ${T}_tc2_small ${T}_bptt_sweep; do
+  ncu -i $O/$n.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $O/${n}_source.csv.gz
+done
+rm -f $O/${T}_tc2_small.ncu-rep $O/${T}_bptt_sweep.ncu-rep
+du -sh $O

@@ -1,10 +1,13 @@
 #!/bin/bash
 # Off-box: turns gpurun_out/<name>.ncu-rep into profiles/<name>_ncu_summary.txt (the metrics DESIGN.md quotes).
 #   scripts/ncu_summary.sh r02_tc2_construct r02_tc2_small r02_bptt_sweep
+# OUTDIR (default profiles/) receives the summaries: on the GPU box the capture script sets OUTDIR=gpurun_out so that only the
+# small text files travel back (gpurun returns at most 64 MiB).
+OUTDIR=${OUTDIR:-profiles}
 for n in "$@"; do
   rep=gpurun_out/$n.ncu-rep
   [ -f $rep ] || { echo "missing $rep"; continue; }
-  out=profiles/${n}_ncu_summary.txt
+  out=$OUTDIR/${n}_ncu_summary.txt
   {
     echo "# ncu --set full --clock-control none --import-source on (one launch), extracted by scripts/ncu_summary.sh from $rep"
     ncu -i $rep --page raw --csv 2>/dev/null | python3 -c '

@@ -284,7 +284,7 @@ def test_profile_diagnostics_match_oracle(opz, oracle, diurnal):
 def test_nz128_diurnal_fp32_matches_oracle(opz, oracle):
     """BASELINE configs[4] on the FP32 path: Nz = 128 columns (state 384, 127 interior faces) with a widened MLP
     (384-256-256-127 x3) and diurnal surface forcing; parity with the oracle at the FP32 tolerance (1e-4), the single
-    right-hand side, the fluxes and the batched MLP included.  (The tensor-core path is built for Nz = 32 and declines.)"""
+    right-hand side, the fluxes and the batched MLP included.  (The tensor-core side of configs[4]: tests/test_gpu_layered.py.)"""
     O = oracle
     p = O.Params(Nz=128, flags=O.FLAG_MPP | O.FLAG_CA | O.FLAG_BC_MINUS_SCALE0 | O.FLAG_DIURNAL | O.FLAG_DIURNAL_MINUS_SCALE0)
     B = 37
@@ -309,9 +309,6 @@ def test_nz128_diurnal_fp32_matches_oracle(opz, oracle):
     assert fl.shape == (B, 3, 129) and rel_err(fl, np.stack([uw, vw, wT], axis=1)) < 2e-5
     y = opz.mlp_forward(model, 2, x0)
     assert rel_err(y, O.mlp_forward(x0, m.w_wT, sizes, m.act)) < 2e-5
-    with pytest.raises(opz.OpzError) as e:
-        opz.rollout_forward(model, pp, x0, bc, opz.SCHEME_RK4, dt, 4, 2, precision=opz.PREC_FP16)
-    assert e.value.code == opz.OPZ_EUNSUP
     model.close()
 
 
