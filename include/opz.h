@@ -67,10 +67,15 @@ extern "C" {
 /* arithmetic of the batched MLP (physics and time stepping are always FP32) */
 #define OPZ_PREC_FP32 0   /* FP32 FMA on CUDA cores: the parity path (<= 1e-4) */
 #define OPZ_PREC_BF16 1   /* tcgen05 kind::f16, BF16 operands, FP32 accumulate in TMEM */
-#define OPZ_PREC_BF16X2 2 /* as BF16 with weights split hi+lo (2 MMAs): ~TF32-grade */
-#define OPZ_PREC_BF16X3 3 /* activations and weights split hi+lo (3 MMAs): ~FP32-grade */
+#define OPZ_PREC_BF16X2 2 /* as BF16 with the weights split hi + lo (2 MMAs per k-step) */
+#define OPZ_PREC_BF16X3 3 /* activations and weights split hi + lo (hi*hi + hi*lo + lo*hi, 3 MMAs): 16 mantissa bits per operand */
 #define OPZ_PREC_FP16 4   /* tcgen05 kind::f16, IEEE-half operands (saturating), FP32 accumulate in TMEM:
                              same speed as BF16, 8x finer operand rounding; the default reduced-precision path */
+#define OPZ_PREC_FP16X2 5 /* IEEE-half operands with the weights split hi + lo */
+#define OPZ_PREC_FP16X3 6 /* IEEE-half operands, both split (3 MMAs): ~21 mantissa bits per operand, FP32 accumulation —
+                             the near-FP32 tensor-core mode (inside the 1e-4 contract of the FP32 path) */
+/* OPZ_PREC_FP16 / OPZ_PREC_BF16 run the fused persistent kernel for Nz = 32 and hidden widths <= 400, and the layered
+ * path (one batched tcgen05 GEMM per Dense layer) for every other shape; the split precisions always run the layered path. */
 
 #define OPZ_BC_STRIDE 8 /* floats per column in `bc` */
 

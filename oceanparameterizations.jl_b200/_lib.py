@@ -23,7 +23,7 @@ FLAG_SMOOTH_NN = 1 << 7
 FLAG_SMOOTH_RI = 1 << 8
 SCHEME_EULER, SCHEME_RK2, SCHEME_RK4, SCHEME_IMEX = 0, 1, 2, 3
 ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_MISH, ACT_SWISH, ACT_LEAKYRELU = range(6)
-PREC_FP32, PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3, 4
+PREC_FP32, PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_FP16, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3, 4, 5, 6
 BC_STRIDE = 8
 
 EXPORTED_SYMBOLS = (

@@ -284,7 +284,8 @@ int opz_rollout_forward_dev(opz_ctx* ctx, const opz_model* m, const opz_params* 
     return tc2_rollout(ctx, m, c, precision);
   }
   // split-operand precisions (near-FP32 on the tensor cores) and all other shapes: one batched GEMM per Dense layer
-  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3) {
+  if (precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3 ||
+      precision == OPZ_PREC_FP16X2 || precision == OPZ_PREC_FP16X3) {
     if ((!m->gm_valid || m->gm_precision != precision) && (rc = gemm_model_prepare(mm, precision))) return rc;
     return gemm_rollout(ctx, m, c, precision);
   }
@@ -531,7 +532,8 @@ int opz_mlp_forward(opz_ctx* ctx, const opz_model* m, int which_net, const float
   if (!ctx || !m || !x || !y) { set_error("null argument"); return OPZ_EINVAL; }
   if (m->ctx != ctx) { set_error("model belongs to another context"); return OPZ_EINVAL; }
   if (which_net < 0 || which_net > 2 || Nt < 0) { set_error("which_net must be 0..2, Nt >= 0"); return OPZ_EINVAL; }
-  const bool tensor = precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3;
+  const bool tensor = precision == OPZ_PREC_BF16 || precision == OPZ_PREC_FP16 || precision == OPZ_PREC_BF16X2 || precision == OPZ_PREC_BF16X3 ||
+                      precision == OPZ_PREC_FP16X2 || precision == OPZ_PREC_FP16X3;
   if (precision != OPZ_PREC_FP32 && !tensor) { set_error("opz_mlp_forward: unknown precision"); return OPZ_EINVAL; }
   if (tensor && m->nd.n_layers < 2) { set_error("opz_mlp_forward: a single Dense layer has no hidden GEMM; use OPZ_PREC_FP32"); return OPZ_EUNSUP; }
   if (Nt == 0) return OPZ_OK;

@@ -334,6 +334,8 @@ static int precision_mode(int precision, int* mode, bool* fp16) {
     case OPZ_PREC_FP16: *mode = gm::MODE_PLAIN; *fp16 = true; return OPZ_OK;
     case OPZ_PREC_BF16X2: *mode = gm::MODE_X2; *fp16 = false; return OPZ_OK;
     case OPZ_PREC_BF16X3: *mode = gm::MODE_X3; *fp16 = false; return OPZ_OK;
+    case OPZ_PREC_FP16X2: *mode = gm::MODE_X2; *fp16 = true; return OPZ_OK;
+    case OPZ_PREC_FP16X3: *mode = gm::MODE_X3; *fp16 = true; return OPZ_OK;
     default: set_error("layered tensor path: unknown precision"); return OPZ_EINVAL;
   }
 }
