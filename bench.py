@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--no-bptt", action="store_true", help="skip the BPTT grad-steps/s leg")
     ap.add_argument("--no-small", action="store_true", help="skip the informational small-net leg")
     ap.add_argument("--no-fp32", action="store_true", help="skip the FP32 (CUDA-core parity path) leg")
+    ap.add_argument("--no-layered", action="store_true", help="skip the layered tensor path legs (near-FP32 split mode; configs[4] Nz=128)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     ap.add_argument("--bptt-steps", type=int, default=2, help="timed gradient steps of the BPTT leg")
     args = ap.parse_args()
@@ -469,6 +470,59 @@ def main():
                 "finite": bool(torch.isfinite(ffinal).all().item())}
         del ffinal
 
+    # ---- layered tensor path (csrc/opz_gemm.cu): (i) the near-FP32 split-operand mode on the headline workload, to be read
+    #      against the FP32 leg (same <= 1e-4 contract); (ii) BASELINE configs[4]: Nz = 128 columns, 384-1024-1024-127 nets ----
+    layered = None
+    if not args.no_layered:
+        layered = {}
+        lcols = min(cols, 1 << 18)            # 100 MB of profiles: larger than L2 together with the operand images
+        l_steps = 3
+        l_ms, _, lfinal, _, _ = time_windows(opz, torch, dist, stream, ctx, model, pp, x0, bcd, lcols, 1, opz.PREC_FP16X3, dt, l_steps, 2)
+        l_ms = max_over_ranks(torch, dist, l_ms / l_steps)
+        l_flops = lcols * STAGES * FLOP_PER_RHS
+        peak_t = float(measured_peaks()[0].get("bf16_tflops_sustained", 1379.5))
+        layered["near_fp32"] = {
+            "kernel": "layer_gemm_kernel x 3 layers + pack_state_kernel + physics_rk_kernel per right-hand side (tcgen05, A and B from shared memory)",
+            "precision": "fp16x3 (both operands split into two IEEE halves, 3 MMAs per k-step, FP32 accumulate)",
+            "value": lcols * world / (l_ms * 1e-3), "unit": "column-timesteps/s", "columns_per_gpu": lcols, "window_timesteps": 1,
+            "ms_per_step": l_ms, "algorithmic_tflops": l_flops / (l_ms * 1e-3) / 1e12,
+            "tensor_tflops_issued": 3 * l_flops * (448 * 448 + 96 * 448 + 448 * 64) / (400 * 400 + 96 * 400 + 400 * 31) / (l_ms * 1e-3) / 1e12,
+            "frac_of_tensor_peak_issued": 3 * l_flops * (448 * 448 + 96 * 448 + 448 * 64) / (400 * 400 + 96 * 400 + 400 * 31) / (l_ms * 1e-3) / 1e12 / peak_t,
+            "finite": bool(torch.isfinite(lfinal).all().item())}
+        if fp32:
+            layered["near_fp32"]["speedup_over_fp32_path"] = layered["near_fp32"]["value"] / fp32["value"]
+        if rank == 0 and not args.no_parity:
+            from oracle import c_oracle as CO
+            pick = np.arange(0, min(lcols, 4096), 64)
+            got = lfinal[torch.from_numpy(pick).cuda()].cpu().numpy()[:, None, :]
+            ref = CO.rollout(x0[pick], bc[pick], m, p, 2, dt, 2 + l_steps, 0, n_threads=host_cores(CO))
+            layered["near_fp32"]["parity_err"] = float(O.profile_error(got, ref, 32))
+        del lfinal
+        # configs[4]
+        p5 = O.Params(Nz=128, tau=172800.0, flags=O.FLAG_MPP | O.FLAG_BC_MINUS_SCALE0 | O.FLAG_DIURNAL | O.FLAG_DIURNAL_MINUS_SCALE0)
+        sizes5 = (384, 1024, 1024, 127)
+        m5 = O.make_model(sizes5, O.ACT_RELU, seed=0, out_scale=0.03, bias_scale=0.05)
+        model5 = product_model(opz, m5, Nz=128, ctx=ctx)
+        pp5 = product_params(opz, p5)
+        c5 = min(cols, 1 << 16)               # 100 MB of profiles (1 536 B per column)
+        x5s, b5s = O.synthetic_columns(4096, p5, diurnal=True)
+        x5 = np.tile(x5s, ((c5 + 4095) // 4096, 1))[:c5]
+        b5 = torch.from_numpy(np.tile(b5s, ((c5 + 4095) // 4096, 1))[:c5].copy()).cuda()
+        dt5 = 10.0 / p5.tau
+        f5 = 2 * 3 * sum(sizes5[i] * sizes5[i + 1] for i in range(3)) + 7000
+        for pname, pcode in (("fp16", opz.PREC_FP16), ("fp16x3", opz.PREC_FP16X3)):
+            q_ms, _, qfinal, _, _ = time_windows(opz, torch, dist, stream, ctx, model5, pp5, x5, b5, c5, 1, pcode, dt5, 3, 2)
+            q_ms = max_over_ranks(torch, dist, q_ms / 3)
+            nmma = 3 if pname == "fp16x3" else 1
+            layered["config5_" + pname] = {
+                "workload": "BASELINE configs[4]: Nz=128, 384-1024-1024-127 relu x3, mPP, diurnal forcing, RK4 dt=10 s, one timestep per bench step",
+                "value": c5 * world / (q_ms * 1e-3), "unit": "column-timesteps/s", "columns_per_gpu": c5, "ms_per_step": q_ms,
+                "algorithmic_tflops": c5 * STAGES * f5 / (q_ms * 1e-3) / 1e12,
+                "frac_of_tensor_peak_issued": nmma * c5 * STAGES * (f5 - 7000) * (128.0 / 127.0) / (q_ms * 1e-3) / 1e12 / peak_t,
+                "finite": bool(torch.isfinite(qfinal).all().item())}
+            del qfinal
+        model5.close()
+
     # ---- the reference's production net on the same ensemble (96-50-20-31 mish, train_NDE.jl:103) ----
     small = None
     if not args.no_small:
@@ -574,6 +628,8 @@ def main():
         line["other_scaling"] = other
     if fp32:
         line["fp32"] = fp32
+    if layered:
+        line["layered_path"] = layered
     if bptt:
         line["bptt"] = bptt
     if small:

@@ -7,7 +7,7 @@ module OPZ
 using Flux
 
 export Context, Model, Params, Euler, Heun, RK4, IMEXEuler, solve_NDE_mutating, predict_NDE, predict_flux,
-       loss_and_gradient, predict
+       loss_and_gradient, predict, comm_unique_id, comm_init!, shard_range
 
 const libopz = get(ENV, "LIBOPZ", "libopz.so")
 
@@ -16,7 +16,7 @@ const FLAG_MPP, FLAG_CA, FLAG_CA_SELECT_DUDZ, FLAG_BC_MINUS_SCALE0 = UInt32(1) <
 const FLAG_DIURNAL, FLAG_DIURNAL_MINUS_SCALE0, FLAG_RI_EPS = UInt32(1) << 4, UInt32(1) << 5, UInt32(1) << 6
 const FLAG_SMOOTH_NN, FLAG_SMOOTH_RI = UInt32(1) << 7, UInt32(1) << 8
 const SCHEME_EULER, SCHEME_RK2, SCHEME_RK4, SCHEME_IMEX = Cint(0), Cint(1), Cint(2), Cint(3)
-const PREC_FP32, PREC_BF16, PREC_FP16 = Cint(0), Cint(1), Cint(4)
+const PREC_FP32, PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_FP16, PREC_FP16X2, PREC_FP16X3 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4), Cint(5), Cint(6)
 const ACT = Dict(identity => 0, relu => 1, tanh => 2, mish => 3, swish => 4, leakyrelu => 5)
 
 struct OpzParams
@@ -42,6 +42,24 @@ mutable struct Context
 end
 const _ctx = Ref{Union{Nothing,Context}}(nothing)
 ctx() = (_ctx[] === nothing && (_ctx[] = Context(0)); _ctx[])
+# Finalizers run in no particular order; that is safe: opz_ctx_destroy on a context that still has live models is
+# deferred by the library until the last opz_model_destroy (include/opz.h).
+
+# ---- multi-GPU: one Julia process per GPU; the gradient all-reduce happens inside opz_loss_grad -------------------
+# rank 0:  id = comm_unique_id(); ship the 128 bytes to the other ranks (MPI.Bcast!, Distributed, a file ...)
+# all:     comm_init!(ctx(), id, n_ranks, rank)   # collective;  afterwards loss_and_gradient returns GLOBAL values
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:opz_comm_get_unique_id, libopz), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(c::Context, id::Vector{UInt8}, n_ranks::Integer, rank::Integer) =
+    check(ccall((:opz_ctx_comm_init, libopz), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), c.h, id, n_ranks, rank))
+function shard_range(B::Integer, rank::Integer, n_ranks::Integer)   # 0-based [lo, hi) of the cases this rank owns
+    lo = Ref{Int64}(0); hi = Ref{Int64}(0)
+    check(ccall((:opz_shard_range, libopz), Cint, (Int64, Cint, Cint, Ref{Int64}, Ref{Int64}), B, rank, n_ranks, lo, hi))
+    return lo[], hi[]
+end
 
 # ---- model: three Flux Chains -> flat Float32 vectors (Flux.destructure order) --------------------------
 mutable struct Model
@@ -84,12 +102,27 @@ end
 pack_BCs(BCs; Q=0f0) = Float32[BCs.uw.bottom, BCs.uw.top, BCs.vw.bottom, BCs.vw.top, BCs.wT.bottom,
                                BCs.wT.top isa Function ? 0f0 : BCs.wT.top, Q, 0f0]
 
+# Device model for three Chains, cached per ARCHITECTURE (layer sizes, activation, Nz) — never per object identity: NDE()
+# rebuilds its Chains from `p` on every call (NDE_training.jl:62-64).  The weights are uploaded on every call (<= 2.5 MB).
+const _models = Dict{Any,Model}()
+function cached_model(uw_NN, vw_NN, wT_NN, Nz)
+    key = (Tuple(size(l.W) for l in uw_NN), uw_NN[1].σ, Int(Nz))
+    m = get(_models, key, nothing)
+    if m === nothing
+        m = _models[key] = Model(uw_NN, vw_NN, wT_NN, Nz)
+    else
+        set_weights!(m, vcat((Float32.(Flux.destructure(nn)[1]) for nn in (uw_NN, vw_NN, wT_NN))...))
+    end
+    return m
+end
+
 # ---- timesteppers (replace OrdinaryDiffEq algorithm objects; dt in units of τ) --------------------------
 struct Stepper; dt::Float32; scheme::Cint; precision::Cint; end
 Euler(dt; precision=PREC_FP32) = Stepper(dt, SCHEME_EULER, precision)
 Heun(dt; precision=PREC_FP32) = Stepper(dt, SCHEME_RK2, precision)
 RK4(dt; precision=PREC_FP32) = Stepper(dt, SCHEME_RK4, precision)
-# explicit Euler + backward-Euler vertical diffusion: the split step of NDE_oceananigans.jl:61-101 (FP32 only)
+# explicit Euler + backward-Euler vertical diffusion: the split step of NDE_oceananigans.jl:61-101 (FP32 only; differentiable:
+# opz_loss_grad carries the adjoint of the tridiagonal solve)
 IMEXEuler(dt) = Stepper(dt, SCHEME_IMEX, PREC_FP32)
 
 function steps_from_ts(ts, dt)
@@ -101,7 +134,7 @@ end
 
 # ---- solve_NDE_mutating (training_postprocessing.jl:55-159) ---------------------------------------------
 function solve_NDE_mutating(uw_NN, vw_NN, wT_NN, scalings, constants, BCs, derivatives, uvT₀, ts, timestepper::Stepper, conditions; Q_diurnal=0f0)
-    model = Model(uw_NN, vw_NN, wT_NN, constants.Nz)
+    model = cached_model(uw_NN, vw_NN, wT_NN, constants.Nz)
     params = Ref(Params(constants, scalings, conditions; inference=true, diurnal=BCs.wT.top isa Function))
     n_steps, save_every, t0 = steps_from_ts(ts, timestepper.dt)
     x0 = Float32.(uvT₀); bc = pack_BCs(BCs; Q=Q_diurnal)
@@ -114,7 +147,7 @@ end
 
 # ---- predict_NDE / predict_flux (NDE_training.jl:83-165) --------------------------------------------------
 function _rhs(uw_NN, vw_NN, wT_NN, x, BCs, conditions, scalings, constants; t=0f0, fluxes=false)
-    model = Model(uw_NN, vw_NN, wT_NN, constants.Nz)
+    model = cached_model(uw_NN, vw_NN, wT_NN, constants.Nz)
     params = Ref(Params(constants, scalings, conditions; inference=false))
     x32 = Float32.(x); bc = pack_BCs(BCs)
     dxdt = similar(x32); fl = Array{Float32}(undef, constants.Nz + 1, 3)
@@ -131,15 +164,18 @@ function predict_flux(uw_NN, vw_NN, wT_NN, x, BCs, conditions, scalings, constan
 end
 
 # ---- loss_NDE + gradient (NDE_training.jl:290-333) -> (total, components, grad) ---------------------------
+# Multi-GPU: x0 / bc / target hold THIS rank's cases (shard_range) and B_total the global number of simulations; with a
+# communicator on the context (comm_init!) the returned loss and gradient are already summed over the ranks.
 function loss_and_gradient(model::Model, params::OpzParams, weights::Vector{Float32}, x0::Matrix{Float32}, bc::Matrix{Float32},
-                           target::Array{Float32,3}, loss_w::Vector{Float32}, timestepper::Stepper, n_steps, save_every; t0=0f0)
+                           target::Array{Float32,3}, loss_w::Vector{Float32}, timestepper::Stepper, n_steps, save_every; t0=0f0,
+                           B_total=size(x0, 2))
     set_weights!(model, weights)
     B = size(x0, 2)
     loss = zeros(Float32, 7); grad = zeros(Float32, 3model.P)
     GC.@preserve x0 bc target loss_w loss grad check(ccall((:opz_loss_grad, libopz), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ref{OpzParams}, Ptr{Float32}, Ptr{Float32}, Int64, Int64, Cint, Cfloat, Cfloat, Cint, Cint,
          Ptr{Float32}, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}),
-        ctx().h, model.h, Ref(params), x0, bc, B, B, timestepper.scheme, timestepper.dt, t0, n_steps, save_every,
+        ctx().h, model.h, Ref(params), x0, bc, B, B_total, timestepper.scheme, timestepper.dt, t0, n_steps, save_every,
         target, loss_w, timestepper.precision, loss, grad))
     return loss[1], loss[2:7], grad
 end
@@ -159,11 +195,11 @@ function loss_and_gradient_mpp(model::Model, params::OpzParams, x0::Matrix{Float
 end
 
 # ---- predict(𝒱, model) (src/predict.jl:12-34): one batched launch --------------------------------------
-function predict(𝒱, model::Model, which_net::Integer; scaled=false)
+function predict(𝒱, model::Model, which_net::Integer; scaled=false, precision=PREC_FP32)
     x = Float32.(𝒱.uvT_scaled)                      # 3Nz × Nt  == C [Nt][3Nz]
     y = Array{Float32}(undef, model.Nz - 1, size(x, 2))
     GC.@preserve x y check(ccall((:opz_mlp_forward, libopz), Cint,
-        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float32}, Int64, Cint, Ptr{Float32}), ctx().h, model.h, which_net, x, size(x, 2), PREC_FP32, y))
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float32}, Int64, Cint, Ptr{Float32}), ctx().h, model.h, which_net, x, size(x, 2), precision, y))
     return scaled ? (y, 𝒱.scaled) : (𝒱.unscale_fn(y), 𝒱.coarse)
 end
 

@@ -28,7 +28,8 @@ for v in vals:
         if k in d: print(f"{k:90s} {d[k]:>22s} {u.get(k, str())}")
     stalls = sorted(((float(d[k].replace(",", "")), k) for k in d if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio") and d[k] not in ("", "n/a")), reverse=True)
     print("-- warp stall reasons (average warps stalled per issue-active cycle), top 8")
-    for val, k in stalls[:8]: print(f"   {k[len(\"smsp__average_warps_issue_stalled_\"):-len(\"_per_issue_active.ratio\")]:40s} {val:8.2f}")
+    pre, suf = len("smsp__average_warps_issue_stalled_"), len("_per_issue_active.ratio")
+    for val, k in stalls[:8]: print("   %-40s %8.2f" % (k[pre:-suf], val))
 '
   } > $out
   echo wrote $out
