@@ -15,8 +15,8 @@
 // fixed-step solve (solve_NDE_mutating, :55-159).
 //
 // Operand image (activations AND weights), chosen so that one 1-D bulk copy fetches an MMA operand block and the epilogue's
-// stores coalesce: features in blocks of 64 (four k-steps); one block of R rows is the K-major no-swizzle core-matrix layout
-//   half index = ((k / 8) * R + row) * 8 + k % 8          (LBO = 16 R bytes, SBO = 128 bytes)
+// stores coalesce: features in blocks of kKB = 32 (two k-steps); one block of R rows is the K-major no-swizzle core-matrix layout
+//   half index = ((k / 8) * R + row) * 8 + k % 8          (LBO = 16 R bytes, SBO = 128 bytes)      [k inside the block]
 // activations: R = 128 ocean columns of one tile, blocks ordered [tile][k-block]; weights: R = the outputs of one pass
 // (<= 256 = one MMA's N = the tensor-memory columns a CTA allocates), blocks ordered [net][pass][k-block].
 // One CTA = one 128-column tile x one pass of outputs x one net: warp 0 streams operand blocks (cp.async.bulk -> mbarrier),
@@ -33,9 +33,10 @@ namespace opz {
 namespace gm {
 
 constexpr int kM = 128;                    // ocean columns per tile
-constexpr int kKB = 64;                    // features per operand block
+constexpr int kKB = 32;                    // features per operand block (two k-steps): 24 KB (48 KB split) per stage, so that two
+                                           // CTAs share an SM and one's epilogue overlaps the other's MMAs; widths pad to 32
 constexpr int kNT = 256;                   // outputs per pass
-constexpr int kABytes = kM * kKB * 2;      // 16 KB
+constexpr int kABytes = kM * kKB * 2;      // 8 KB
 constexpr int kThreads = 192;
 
 enum { MODE_PLAIN = 0, MODE_X2 = 1, MODE_X3 = 2 };
@@ -50,7 +51,7 @@ struct LayerArgs {
   const uint16_t* w_lo;       // (MODE_X2, MODE_X3)
   size_t w_net;               // halves per net
   const float* bias;          // [net][n_pad]
-  int n_out, n_pad, n_pass;   // true outputs, padded to a multiple of 64, passes of <= 256
+  int n_out, n_pad, n_pass;   // true outputs, padded to a multiple of kKB, passes of <= 256
   uint16_t* o_hi;             // output image (hidden layers) [net][tile][k-block][kM*kKB]
   uint16_t* o_lo;             // (MODE_X3)
   size_t o_net;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kThreads) layer_gemm_kernel(const __grid_const
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t tile = blockIdx.x;
   const int pass = blockIdx.y, net = blockIdx.z;
-  const int rows = min(kNT, a.n_pad - pass * kNT);          // outputs of this pass (multiple of 64)
+  const int rows = min(kNT, a.n_pad - pass * kNT);          // outputs of this pass (multiple of kKB)
   const int n_parts_a = a.mode == MODE_X3 ? 2 : 1, n_parts_w = a.mode == MODE_PLAIN ? 1 : 2;
   const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
   const uint32_t stage_bytes = n_parts_a * kABytes + n_parts_w * w_bytes;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) layer_gemm_kernel(const __grid_const
         const uint32_t base = ring_u32 + (uint32_t)s * stage_bytes;
         const uint32_t a_hi = base, a_lo = base + kABytes;
         const uint32_t w_hi = base + n_parts_a * kABytes, w_lo = w_hi + w_bytes;
-        const int nks = min(4, (a.k_in - kb * kKB + 15) / 16);   // k-steps that hold real features
+        const int nks = min(kKB / 16, (a.k_in - kb * kKB + 15) / 16);   // k-steps that hold real features
         for (int ks = 0; ks < nks; ++ks) {
           const uint64_t ad = ptx::smem_desc(a_hi + ks * (2 * kM * 16), kM * 16, 128);
           const uint64_t bd = ptx::smem_desc(w_hi + ks * (2 * rows * 16), rows * 16, 128);
@@ -163,14 +164,22 @@ __global__ void __launch_bounds__(kThreads) layer_gemm_kernel(const __grid_const
           if (n < a.n_out) a.y[((size_t)net * a.n_out + n) * a.ldy + tile * kM + r] = __uint_as_float(v[j]) + bias[c0 + j];
         }
       } else {
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) + bias[c0 + j];
+        switch (a.act) {   // one dispatch per 32 values, not per value
+#define OPZ_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < 32; ++j) z[j] = act_fn<A>(z[j]); break;
+          OPZ_ACT_CASE(OPZ_ACT_RELU) OPZ_ACT_CASE(OPZ_ACT_TANH) OPZ_ACT_CASE(OPZ_ACT_MISH) OPZ_ACT_CASE(OPZ_ACT_SWISH) OPZ_ACT_CASE(OPZ_ACT_LEAKYRELU)
+#undef OPZ_ACT_CASE
+          default: break;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {   // groups of 8 features = one 16-byte chunk of the image
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + 2 * e;
-            const float z0 = act_dyn(__uint_as_float(v[j]) + bias[c0 + j], a.act);
-            const float z1 = act_dyn(__uint_as_float(v[j + 1]) + bias[c0 + j + 1], a.act);
+            const float z0 = z[j], z1 = z[j + 1];
             hi[e] = pack2(z0, z1, fp16);
             if (a.mode == MODE_X3) {
               const float2 h = unpack2(hi[e], fp16);
@@ -195,7 +204,7 @@ __global__ void pack_state_kernel(const float* __restrict__ xs, int64_t ld, int 
                                   uint16_t* __restrict__ lo, int fp16) {
   const int64_t tile = blockIdx.x;
   const int kb = blockIdx.y;
-  const int r = threadIdx.x % kM, g = threadIdx.x / kM;   // 128 columns x 8 feature groups
+  const int r = threadIdx.x % kM, g = threadIdx.x / kM;   // 128 columns x kKB / 8 feature groups
   const int64_t col = tile * kM + r;
   uint32_t ph[4], pl[4];
 #pragma unroll
@@ -536,7 +545,7 @@ int gemm_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int pre
         float ts = tn;
         if (c.scheme == OPZ_RK4) ts = (sg == 0) ? tn : (sg == 3 ? tn + c.dt : tn + c.dt * 0.5f);
         else if (c.scheme == OPZ_RK2) ts = (sg == 0) ? tn : tn + c.dt;
-        pack_state_kernel<<<dim3((unsigned)tiles, (unsigned)pl->kb[0]), kM * 8, 0, st>>>(w.xs[cur], C, S3, pl->kb[0], nb, w.x_hi, w.x_lo, pl->fp16 ? 1 : 0);
+        pack_state_kernel<<<dim3((unsigned)tiles, (unsigned)pl->kb[0]), kM * (kKB / 8), 0, st>>>(w.xs[cur], C, S3, pl->kb[0], nb, w.x_hi, w.x_lo, pl->fp16 ? 1 : 0);
         ctx->launches += 1;
         if ((rc = run_layers(ctx, m, *pl, w, tiles, C, -1))) return rc;
         PhysArgs pa{};
@@ -581,7 +590,7 @@ int gemm_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, in
     const int64_t nb = std::min<int64_t>(C, Nt - c0);
     const int64_t tiles = (nb + kM - 1) / kM;
     load_rows_kernel<<<(unsigned)((nb * S3 + 255) / 256), 256, 0, st>>>(x + c0 * S3, S3, nb, C, w.xs[0]);
-    pack_state_kernel<<<dim3((unsigned)tiles, (unsigned)pl->kb[0]), kM * 8, 0, st>>>(w.xs[0], C, S3, pl->kb[0], nb, w.x_hi, w.x_lo, pl->fp16 ? 1 : 0);
+    pack_state_kernel<<<dim3((unsigned)tiles, (unsigned)pl->kb[0]), kM * (kKB / 8), 0, st>>>(w.xs[0], C, S3, pl->kb[0], nb, w.x_hi, w.x_lo, pl->fp16 ? 1 : 0);
     ctx->launches += 2;
     if ((rc = run_layers(ctx, m, *pl, w, tiles, C, which_net))) return rc;
     store_mlp_kernel<<<(unsigned)((nb * nout + 255) / 256), 256, 0, st>>>(w.y + (size_t)which_net * nout * C, nout, nb, C, y + c0 * nout);

@@ -63,6 +63,7 @@ if os.environ.get("OPZ_LAYERED_ALL"):
     model1 = product_model(opz, m1, ctx=ctx)
     f1 = 2 * 3 * sum(s1[i] * s1[i + 1] for i in range(3))
     os.environ["OPZ_FORCE_LAYERED"] = "1"
-    for name, prec in (("construct_NN fp16 (layered)", opz.PREC_FP16), ("construct_NN fp16x3", opz.PREC_FP16X3), ("construct_NN bf16x3", opz.PREC_BF16X3)):
+    for name, prec in (("construct_NN fp16 (layered)", opz.PREC_FP16), ("construct_NN bf16x3", opz.PREC_BF16X3), ("construct_NN fp16x3", opz.PREC_FP16X3),
+                       ("construct_NN bf16x3 again", opz.PREC_BF16X3), ("construct_NN bf16 (layered)", opz.PREC_BF16)):
         run(name, model1, product_params(opz, p), x1, b1, prec, 30.0 / p.tau, flop_rhs=f1)
     model1.close()
