@@ -74,6 +74,31 @@ enum : int {
 };
 static_assert(B_COUNT <= 32, "phase bits are tracked in one 32-bit mask");
 
+constexpr int kMaxChunks = 48;       // accumulator chunks per right-hand side
+
+// One accumulator chunk of the per-right-hand-side schedule.  The schedule is the same for every right-hand side, so the host
+// lays it out once (build_plan) and both the MMA issuers and the epilogue warps walk this table instead of re-deriving the
+// nested layer / chunk loops: what is left on their per-chunk critical path is the barrier wait, the fence and the
+// tcgen05 instructions themselves (the wait profile had ~380 cycles of address arithmetic between an issuer's wake-up and its first MMA).
+enum : uint8_t { CH_SPLIT = 1, CH_FUSED = 2, CH_WAIT_H1 = 4 };
+struct ChunkRec {
+  uint32_t offA, offB;     // ring byte offsets of the chunk's weight stage (and of its second stage when CH_SPLIT)
+  uint32_t out_off;        // ring byte offset of the W_out block riding in this chunk's (last) stage, when out_ks > 0
+  uint16_t a_col;          // tensor-memory column of the A operand (X, or the net's HF image)
+  uint16_t dst_col;        // tensor-memory column the drained chunk goes to (its place in HF, or H2c)
+  uint8_t rows;            // accumulator columns of the chunk = N of its MMAs (multiple of 16, <= kCW)
+  uint8_t kin;             // k-steps of the layer input
+  uint8_t stage;           // index of the chunk's first weight stage within the right-hand side
+  uint8_t flags;           // CH_*
+  uint8_t h1_bar;          // H1 barrier the drain of a non-fused chunk signals
+  uint8_t h1_base;         // first H1 barrier of the layer's input (CH_WAIT_H1)
+  uint8_t h1_seq;          // completions of those barriers earlier in the same right-hand side
+  uint8_t out_ks;          // output-layer k-steps of the fused chunk two stages back, issued at the head of this stage (0: none)
+  uint8_t out_net;         // ... and the net (Y accumulator) they belong to
+  uint8_t pad[3];
+};
+static_assert(sizeof(ChunkRec) == 28, "ChunkRec layout");
+
 struct Plan {                     // host-side, cached on the model
   int L = 0;
   int hpad[2] = {0, 0};
@@ -81,6 +106,10 @@ struct Plan {                     // host-side, cached on the model
   bool fp16 = false;
   bool interleave = false;
   int n_stages = 0;
+  int n_chunks = 0;
+  ChunkRec ch[kMaxChunks];
+  uint32_t tail_off = 0;          // ring offset of the tail stage (the W_out blocks of the last two chunks)
+  uint8_t tail_ks[2] = {0, 0}, tail_net[2] = {0, 0};   // [0]: chunk n - 2 (ks 0: not a fused one), [1]: chunk n - 1
   uint32_t st_off[kMaxStages];    // ring offset of the stage (bytes)
   uint32_t st_bytes[kMaxStages];  // bytes PER CTA
   uint32_t st_src[kMaxStages];    // tape offset of the stage (leader half first, then the peer half)
@@ -106,6 +135,11 @@ struct Args {
   int n_mma_warps;   // 1 or 2 issuing warps in the leader CTA
   int interleave;    // 1: layer-major schedule (all three nets' first layers, then their second layers), see build_plan
   int nc1;           // accumulator chunks of the first hidden layer
+  int n_chunks;      // accumulator chunks per right-hand side
+  int h1_mult;       // completions of an H1 barrier per right-hand side (3 net-major, 1 layer-major)
+  uint32_t tail_off;
+  uint8_t tail_ks[2], tail_net[2];
+  ChunkRec ch[kMaxChunks];
   int tape_mask;     // versions of the tape - 1 (0: a single, plainly rounded tape)
   uint32_t tape_stride;
   int n0;            // global index of the first time step of this call (t0 / dt): the dither phases continue across calls
@@ -292,13 +326,15 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
     const uint32_t me = warp == 1 ? 0u : 1u;
     const uint32_t nw = (uint32_t)a.n_mma_warps;
     if (n_rhs > 0 && me < nw && rank == 0) {
-      uint32_t gs = 0, g = 0, rhs_ctr = 0;   // global stage / accumulator-chunk / right-hand-side counters
+      uint32_t rhs_ctr = 0;   // right-hand sides done: chunk g of right-hand side r has the global index r * n_chunks + g (likewise the stages)
       long long wacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const long long t_begin = PROF ? clock64() : 0;
       const uint32_t ring_u32 = ptx::smem_u32(s_ring);
       const uint32_t idesc0 = ptx::idesc_f16kind(2 * kM, 0, FP16);
-      const int L = a.L;
-      auto wait_full = [&]() {
+      const uint32_t idesc_out = idesc0 | ((32u >> 3) << 17);
+      const uint32_t nch = (uint32_t)a.n_chunks, nst = (uint32_t)a.n_stages;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);   // upper half of every B descriptor: SBO = 128 B, version 1
+      auto wait_full = [&](uint32_t gs) {
         if constexpr (PROF) {
           const long long t0 = clock64();
           ptx::mbar_wait(bars + B_FULL + (gs % kNB), (gs / kNB) & 1u);
@@ -307,201 +343,170 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
           ptx::mbar_wait(bars + B_FULL + (gs % kNB), (gs / kNB) & 1u);
         }
       };
+      // issue (elected lane): ks output-layer MMAs Y_net += H2c * W_out[:, chunk]^T, B block of 16 rows per CTA at ring offset boff
+      auto out_mmas = [&](uint32_t boff, uint32_t net, uint32_t ks) {
+        const uint32_t lo = (((ring_u32 + boff) >> 4) & 0x3FFFu) | (16u << 16);
+        const uint32_t dy = tmem + kColY + 32u * net;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < (int)ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, kDescHi, idesc_out, true);   // Y was zeroed by the epilogue
+        ptx::tc_commit2(bars + B_H2EMPTY);
+      };
       for (int64_t item = item0; item < n_items; item += item_stride) {
 #pragma unroll 1
-        for (int r = 0; r < n_rhs; ++r) {
+        for (int r = 0; r < n_rhs; ++r, ++rhs_ctr) {
           // Output-layer MMAs of a fused chunk g (Y_net (+)= H2c * W_out[:, chunk]^T) are issued TWO stages later, at the
           // head of the stage of chunk g + 2: that stage waits for "accumulator buffer of chunk g drained" anyway, which is
           // the moment H2c(g) has been written, so they cost no extra blocking wait and no extra issue region.
-          // q1: issued in the coming stage; q0: in the one after.
-          uint32_t q1_net = 0, q1_c = 0, q1_ks = 0, q0_net = 0, q0_c = 0, q0_ks = 0;   // ks == 0: nothing pending
-          int s = 0;
-          const uint32_t idesc_out = idesc0 | ((32u >> 3) << 17);
-          // issue (elected lane): ks MMAs A = H2c, B block of 16 rows per CTA at ring offset boff
-          auto out_mmas = [&](uint32_t boff, uint32_t net, uint32_t c, uint32_t ks) {
-            const uint64_t bd = ptx::smem_desc(ring_u32 + boff, 16u * 16u, 128);
-            const uint32_t lo = (uint32_t)bd, hi = (uint32_t)(bd >> 32);
-            const uint32_t dy = tmem + kColY + 32u * net;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < (int)ks) ptx::mma_ts2_lohi(dy, tmem + kColH2 + (uint32_t)k * 8u, lo + (uint32_t)k * 32u, hi, idesc_out, true);   // Y was zeroed by the epilogue
-            ptx::tc_commit2(bars + B_H2EMPTY);
-          };
+          const uint32_t g0 = rhs_ctr * nch, gs0 = rhs_ctr * nst;
           wait_phase<PROF>(bars, B_XFULL, rhs_ctr, wacc, W_X);
-          // net-major schedule (net 0: layers ..., net 1: ...) or, for narrow nets, layer-major (the three nets' first layers,
-          // then their second layers): there the three nets' HF images sit side by side and the right-hand side is three
-          // overlapping MMA -> drain -> MMA chains instead of six consecutive ones
 #pragma unroll 1
-          for (int idx = 0; idx < 3 * (L - 1); ++idx) {
-            const int net = a.interleave ? idx % 3 : idx / (L - 1);
-            {
-              const int j = a.interleave ? idx / 3 : idx % (L - 1);
-              const uint32_t h1_phase = a.interleave ? rhs_ctr : 3u * rhs_ctr + (uint32_t)net;   // completions of an H1 barrier so far
-              const int h1_base = a.interleave ? net * a.nc1 : 0;
-              const uint32_t hf_base = kColHF + (a.interleave ? (uint32_t)(net * (a.hpad[0] / 2)) : 0u);
-              const bool fused = (j == L - 2);
-              const int kin = (j == 0) ? kS / 16 : a.hpad[j - 1] / 16;
-              const int hp = a.hpad[j];
-              const uint32_t a_base = (j == 0) ? kColX : hf_base;
-#pragma unroll 1
-              for (int c0 = 0; c0 < hp; c0 += kCW) {
-                const uint32_t rows = (uint32_t)min(kCW, hp - c0);
-                const uint32_t buf = g & 1u;
-                const uint32_t gi = g;                       // global index of this accumulator chunk
-                ++g;
-                const bool split = (rows == (uint32_t)kCW) && (kin == 25);   // two weight stages (see build_plan)
-                const bool mine = (nw == 1u) || ((gi & 1u) == me);            // a warp owns one accumulator buffer
-                if (!mine) {   // the other issuing warp's chunk: only the bookkeeping
-                  q1_net = q0_net; q1_c = q0_c; q1_ks = q0_ks;
-                  q0_net = (uint32_t)net; q0_c = (uint32_t)(c0 / kCW); q0_ks = fused ? (rows >> 4) : 0u;
-                  s += split ? 2 : 1; gs += split ? 2u : 1u;
-                  continue;
-                }
-                wait_full();
-                // "buffer drained" of chunk g - 2 = completion (g >> 1) - 1 of this buffer's barrier (for a fused chunk also:
-                // its H2c is written)
-                if (gi >= 2u) wait_phase<PROF>(bars, B_DEMPTY + (int)buf, (gi >> 1) - 1u, wacc, W_DEMPTY);
-                const bool more = q1_ks > 0;                 // output-layer MMAs of chunk g - 2 lead this stage
-                const uint32_t sbase = ring_u32 + a.st_off[s];
-                const uint64_t bd0 = ptx::smem_desc(sbase, (rows / 2) * 16u, 128);  // this CTA holds rows / 2 rows: [k/8][rows/2][8]
-                const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
-                const uint32_t d = tmem + kColD0 + buf * kCW;
-                // Only the first chunk of a layer fed by HF paces itself on the H1 barriers.  The second chunk (possibly the
-                // other issuing warp's) is covered by its D-empty wait: chunk g - 2 is then the LAST first-layer chunk, whose
-                // drained arrival comes after its tcgen05.st and after all earlier drains — so D-empty must keep being signalled
-                // after the store, not right after the accumulator load.
-                const bool wait_h1 = (j > 0) && (c0 == 0 || a.interleave);
-                const uint32_t blo = (uint32_t)bd0, bhi = (uint32_t)(bd0 >> 32);
-                const uint32_t a0 = tmem + a_base;
-                const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25 || kin == 6);
-                // bias MMA: D += [1, 0, ..] x [b; don't care]: the block of rows / 2 x 8 halves right behind the weights; its
-                // second k-group reads what follows inside the stage (zeros or finite weights), multiplied by the zeros of A
-                const uint32_t bias_lo = blo + (rows / 2) * (uint32_t)kin * 2u;   // descriptor address units of 16 B
-                const uint32_t a_one = tmem + kColOne;
-                const uint32_t out_off = a.st_off[s] + (rows / 2) * ((uint32_t)kin * 32u + 16u);
-                const int ebar = B_EMPTY + (int)(gs % kNB);
-                if (split) {
-                  // ---- 64 rows x 25 k-steps in two weight stages, so that the first 12 KB of the ring are free again after
-                  //      12 MMAs: stage A = k-steps [0, 12) (HF chunks 0..2), stage B = [12, 25) + bias + W_out of chunk g - 2
-                  if (wait_h1)
-                    for (int h = 0; h < 3; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
-                  ptx::tc_fence_after();
-                  if (ptx::elect_one()) {
-                    issue_range<kCW, 0, kSplitK>(d, a0, blo, bhi, idesc);
-                    ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
-                  }
-                  __syncwarp();
-                  ++s; ++gs;
-                  wait_full();
-                  if (wait_h1)
-                    for (int h = 3; h < 7; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
-                  const uint64_t bdB = ptx::smem_desc(ring_u32 + a.st_off[s], (kCW / 2) * 16u, 128);
-                  const uint32_t bloB = (uint32_t)bdB;
-                  const uint32_t out_offB = a.st_off[s] + (kCW / 2) * ((uint32_t)(25 - kSplitK) * 32u + 16u);
-                  ptx::tc_fence_after();
-                  if (ptx::elect_one()) {
-                    if (more) out_mmas(out_offB, q1_net, q1_c, q1_ks);
-                    issue_range<kCW, kSplitK, 25>(d, a0, bloB - (uint32_t)(kSplitK * kCW), bhi, idesc);   // B offsets restart at the stage
-                    ptx::mma_ts2_lohi(d, a_one, bloB + (kCW / 2) * (uint32_t)(25 - kSplitK) * 2u, bhi, idesc, true);
-                    ptx::tc_commit2(bars + B_DFULL + buf);
-                    ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
-                  }
-                  __syncwarp();
-                } else if (static_shape && !wait_h1) {
-                  // hot path: the A operand is already complete; one straight immediate-offset run.  (A wider dispatch that also
-                  // covered the narrow layers' shapes, 12 instantiations in this region, cost construct_NN 3 % and gained the
-                  // narrow nets nothing: they are bound by the epilogue.)
-                  ptx::tc_fence_after();
-                  if (ptx::elect_one()) {
-                    if (more) out_mmas(out_off, q1_net, q1_c, q1_ks);
-                    if (rows == (uint32_t)kCW) {
-                      if (kin == 25) issue_range<kCW, 0, 25>(d, a0, blo, bhi, idesc);
-                      else issue_range<kCW, 0, 6>(d, a0, blo, bhi, idesc);
-                    } else {
-                      if (kin == 25) issue_range<16, 0, 25>(d, a0, blo, bhi, idesc);
-                      else issue_range<16, 0, 6>(d, a0, blo, bhi, idesc);
-                    }
-                    ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
-                    ptx::tc_commit2(bars + B_DFULL + buf);
-                    ptx::tc_commit2(bars + ebar);
-                  }
-                  __syncwarp();
-                } else if (static_shape && kin == 25) {
-                  // first chunk of a 400-wide layer fed by HF: follow the epilogue in three groups of HF chunks
-                  // (k-steps [0,12) need HF chunks 0..2, [12,20) chunks 3..4, [20,25) chunks 5..6)
-#pragma unroll 1
-                  for (int grp = 0; grp < 3; ++grp) {
-                    const int h0 = grp == 0 ? 0 : (grp == 1 ? 3 : 5), h1 = grp == 0 ? 3 : (grp == 1 ? 5 : 7);
-                    for (int h = h0; h < h1; ++h) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one()) {
-                      if (grp == 0 && more) out_mmas(out_off, q1_net, q1_c, q1_ks);
-                      if (rows == (uint32_t)kCW) issue_hf_group<kCW>(grp, d, a0, blo, bhi, idesc);
-                      else issue_hf_group<16>(grp, d, a0, blo, bhi, idesc);
-                      if (grp == 2) {
-                        ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
-                        ptx::tc_commit2(bars + B_DFULL + buf);
-                        ptx::tc_commit2(bars + ebar);
-                      }
-                    }
-                    __syncwarp();
-                  }
-                } else {
-                  if (more) {
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one()) out_mmas(out_off, q1_net, q1_c, q1_ks);
-                    __syncwarp();
-                  }
-#pragma unroll
-                  for (int h = 0; h < kMaxKs / 4; ++h) {
-                    if (h * 4 < kin) {
-                      if (wait_h1) wait_phase<PROF>(bars, B_H1 + h1_base + h, h1_phase, wacc, W_H1);
-                      ptx::tc_fence_after();  // orders the MMAs after the epilogue's tcgen05.st seen through the barriers above
-                      if (ptx::elect_one()) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                          const int k = h * 4 + kk;
-                          if (k < kin) ptx::mma_ts2(d, tmem + a_base + (uint32_t)k * 8u, bd0 + (uint64_t)((uint32_t)k * rows), idesc, k > 0);
-                        }
-                      }
-                      __syncwarp();
-                    }
-                  }
-                  if (ptx::elect_one()) {
-                    ptx::mma_ts2_lohi(d, a_one, bias_lo, bhi, idesc, true);
-                    ptx::tc_commit2(bars + B_DFULL + buf);
-                    ptx::tc_commit2(bars + ebar);
-                  }
-                  __syncwarp();
-                }
-                ++s; ++gs;
-                q1_net = q0_net; q1_c = q0_c; q1_ks = q0_ks;
-                q0_net = (uint32_t)net; q0_c = (uint32_t)(c0 / kCW); q0_ks = fused ? (rows >> 4) : 0u;
+          for (uint32_t ci = 0; ci < nch; ++ci) {
+            const uint32_t gi = g0 + ci;                     // global index of this accumulator chunk
+            if (nw == 2u && (gi & 1u) != me) continue;       // the other issuing warp's chunk (a warp owns one accumulator buffer)
+            // ---- everything that does not depend on a barrier: before the waits ----
+            const ChunkRec& c = a.ch[ci];
+            const uint32_t buf = gi & 1u;
+            const uint32_t rows = c.rows, kin = c.kin;
+            const uint32_t gs = gs0 + c.stage;
+            const bool split = c.flags & CH_SPLIT;           // two weight stages (see build_plan)
+            const bool wait_h1 = c.flags & CH_WAIT_H1;
+            const uint32_t more = c.out_ks;                  // output-layer MMAs of chunk g - 2 lead this stage
+            const uint32_t out_net = c.out_net, out_off = c.out_off;
+            const uint32_t idesc = idesc0 | ((rows >> 3) << 17);
+            const uint32_t d = tmem + kColD0 + buf * kCW;
+            const uint32_t a0 = tmem + c.a_col;
+            const uint32_t a_one = tmem + kColOne;
+            // B descriptor of the stage: this CTA holds rows / 2 rows as [k/8][rows/2][8] (LBO = rows / 2 * 16 B)
+            const uint32_t blo = (((ring_u32 + c.offA) >> 4) & 0x3FFFu) | ((rows >> 1) << 16);
+            const uint32_t bloB = (((ring_u32 + c.offB) >> 4) & 0x3FFFu) | ((uint32_t)(kCW / 2) << 16);
+            // bias MMA: D += [1, 0, ..] x [b; don't care]: the block of rows / 2 x 8 halves right behind the weights; its
+            // second k-group reads what follows inside the stage (zeros or finite weights), multiplied by the zeros of A
+            const uint32_t bias_lo = blo + (rows >> 1) * kin * 2u;   // descriptor address units of 16 B
+            const int h1_first = B_H1 + (int)c.h1_base;
+            const uint32_t h1_phase = rhs_ctr * (uint32_t)a.h1_mult + c.h1_seq;   // completions of these H1 barriers so far
+            const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25u || kin == 6u);
+            // ---- waits: the weights, then "buffer drained" of chunk g - 2 = completion (g >> 1) - 1 of this buffer's barrier
+            //      (for a fused chunk also: its H2c is written) ----
+            wait_full(gs);
+            if (gi >= 2u) wait_phase<PROF>(bars, B_DEMPTY + (int)buf, (gi >> 1) - 1u, wacc, W_DEMPTY);
+            // Only the first chunk of a layer fed by HF paces itself on the H1 barriers (CH_WAIT_H1).  The second chunk (possibly
+            // the other issuing warp's) is covered by its D-empty wait: chunk g - 2 is then the LAST first-layer chunk, whose
+            // drained arrival comes after its tcgen05.st and after all earlier drains — so D-empty must keep being signalled
+            // after the store, not right after the accumulator load.
+            if (split) {
+              // ---- 64 rows x 25 k-steps in two weight stages, so that the first 12 KB of the ring are free again after
+              //      12 MMAs: stage A = k-steps [0, 12) (HF chunks 0..2), stage B = [12, 25) + bias + W_out of chunk g - 2
+              if (wait_h1)
+                for (int h = 0; h < 3; ++h) wait_phase<PROF>(bars, h1_first + h, h1_phase, wacc, W_H1);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                issue_range<kCW, 0, kSplitK>(d, a0, blo, kDescHi, idesc);
+                ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
               }
+              __syncwarp();
+              wait_full(gs + 1u);
+              if (wait_h1)
+                for (int h = 3; h < 7; ++h) wait_phase<PROF>(bars, h1_first + h, h1_phase, wacc, W_H1);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                if (more) out_mmas(out_off, out_net, more);
+                issue_range<kCW, kSplitK, 25>(d, a0, bloB - (uint32_t)(kSplitK * kCW), kDescHi, idesc);   // B offsets restart at the stage
+                ptx::mma_ts2_lohi(d, a_one, bloB + (kCW / 2) * (uint32_t)(25 - kSplitK) * 2u, kDescHi, idesc, true);
+                ptx::tc_commit2(bars + B_DFULL + buf);
+                ptx::tc_commit2(bars + B_EMPTY + ((gs + 1u) % kNB));
+              }
+              __syncwarp();
+            } else if (static_shape && !wait_h1) {
+              // hot path: the A operand is already complete; one straight immediate-offset run.  (A wider dispatch that also
+              // covered the narrow layers' shapes, 12 instantiations in this region, cost construct_NN 3 % and gained the
+              // narrow nets nothing: they are bound by the epilogue.)
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                if (more) out_mmas(out_off, out_net, more);
+                if (rows == (uint32_t)kCW) {
+                  if (kin == 25u) issue_range<kCW, 0, 25>(d, a0, blo, kDescHi, idesc);
+                  else issue_range<kCW, 0, 6>(d, a0, blo, kDescHi, idesc);
+                } else {
+                  if (kin == 25u) issue_range<16, 0, 25>(d, a0, blo, kDescHi, idesc);
+                  else issue_range<16, 0, 6>(d, a0, blo, kDescHi, idesc);
+                }
+                ptx::mma_ts2_lohi(d, a_one, bias_lo, kDescHi, idesc, true);
+                ptx::tc_commit2(bars + B_DFULL + buf);
+                ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+              }
+              __syncwarp();
+            } else if (static_shape && kin == 25u) {
+              // first chunk of a 400-wide layer fed by HF: follow the epilogue in three groups of HF chunks
+              // (k-steps [0,12) need HF chunks 0..2, [12,20) chunks 3..4, [20,25) chunks 5..6)
+#pragma unroll 1
+              for (int grp = 0; grp < 3; ++grp) {
+                const int h0 = grp == 0 ? 0 : (grp == 1 ? 3 : 5), h1 = grp == 0 ? 3 : (grp == 1 ? 5 : 7);
+                for (int h = h0; h < h1; ++h) wait_phase<PROF>(bars, h1_first + h, h1_phase, wacc, W_H1);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                  if (grp == 0 && more) out_mmas(out_off, out_net, more);
+                  if (rows == (uint32_t)kCW) issue_hf_group<kCW>(grp, d, a0, blo, kDescHi, idesc);
+                  else issue_hf_group<16>(grp, d, a0, blo, kDescHi, idesc);
+                  if (grp == 2) {
+                    ptx::mma_ts2_lohi(d, a_one, bias_lo, kDescHi, idesc, true);
+                    ptx::tc_commit2(bars + B_DFULL + buf);
+                    ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+                  }
+                }
+                __syncwarp();
+              }
+            } else {
+              if (more) {
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) out_mmas(out_off, out_net, more);
+                __syncwarp();
+              }
+#pragma unroll
+              for (int h = 0; h < kMaxKs / 4; ++h) {
+                if (h * 4 < (int)kin) {
+                  if (wait_h1) wait_phase<PROF>(bars, h1_first + h, h1_phase, wacc, W_H1);
+                  ptx::tc_fence_after();  // orders the MMAs after the epilogue's tcgen05.st seen through the barriers above
+                  if (ptx::elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                      const int k = h * 4 + kk;
+                      if (k < (int)kin) ptx::mma_ts2_lohi(d, a0 + (uint32_t)k * 8u, blo + (uint32_t)k * rows, kDescHi, idesc, k > 0);
+                    }
+                  }
+                  __syncwarp();
+                }
+              }
+              if (ptx::elect_one()) {
+                ptx::mma_ts2_lohi(d, a_one, bias_lo, kDescHi, idesc, true);
+                ptx::tc_commit2(bars + B_DFULL + buf);
+                ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
+              }
+              __syncwarp();
             }
           }
           // tail stage: the output-layer MMAs of the last two chunks, each behind the "drained" arrival of its buffer
+          const uint32_t g = g0 + nch;
           if (nw == 1u || (g & 1u) == me) {
-            wait_full();
-            uint32_t off = a.st_off[s];
+            const uint32_t gs = gs0 + nst - 1u;
+            wait_full(gs);
+            uint32_t off = a.tail_off;
             wait_phase<PROF>(bars, B_DEMPTY + (int)((g - 2u) & 1u), (g - 2u) >> 1, wacc, W_H2FULL);   // chunk g - 2
-            if (q1_ks > 0) {
+            if (a.tail_ks[0] > 0) {
               ptx::tc_fence_after();
-              if (ptx::elect_one()) out_mmas(off, q1_net, q1_c, q1_ks);
+              if (ptx::elect_one()) out_mmas(off, a.tail_net[0], a.tail_ks[0]);
               __syncwarp();
-              off += q1_ks * 512u;
+              off += (uint32_t)a.tail_ks[0] * 512u;
             }
             wait_phase<PROF>(bars, B_DEMPTY + (int)((g - 1u) & 1u), (g - 1u) >> 1, wacc, W_H2FULL);   // chunk g - 1
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-              out_mmas(off, q0_net, q0_c, q0_ks);
+              out_mmas(off, a.tail_net[1], a.tail_ks[1]);
               ptx::tc_commit2(bars + B_YFULL);
               ptx::tc_commit2(bars + B_EMPTY + (gs % kNB));
             }
             __syncwarp();
           }
-          ++rhs_ctr;
-          ++gs;
         }
       }
       if (PROF && blockIdx.x == 0 && lane == 0 && me == 0u) {
@@ -603,69 +608,82 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
         const float tn = a.t0 + (float)n * h;
 #pragma unroll 1
         for (int st = 0; st < stages; ++st, ++rhs_idx) {
-          // ---- drain the accumulator chunks of the hidden layers ----
+          // ---- drain the accumulator chunks of the hidden layers (the schedule table, see ChunkRec) ----
 #pragma unroll 1
-          for (int idx = 0; idx < 3 * (a.L - 1); ++idx) {
-            const int net = a.interleave ? idx % 3 : idx / (a.L - 1);
-            {
-              const int j = a.interleave ? idx / 3 : idx % (a.L - 1);
-              const int h1_base = a.interleave ? net * a.nc1 : 0;
-              const uint32_t hf_base = kColHF + (a.interleave ? (uint32_t)(net * (a.hpad[0] / 2)) : 0u);
-              const bool fused = (j == a.L - 2);
-              const int hp = a.hpad[j];
-#pragma unroll 1
-              for (int c = 0; c * kCW < hp; ++c) {
-                const uint32_t buf = g & 1u;
-                ++g;
-                const int ncols = min(kCW, hp - c * kCW) - ps * CPW;   // columns of this chunk that belong to this warp (<= 0: none)
-                if (prof_me) bar_wait_t<PROF>(bars, B_DFULL + buf, mask, eacc, E_DFULL - 8);
-                else bar_wait(bars, B_DFULL + buf, mask);
+          for (int ci = 0; ci < a.n_chunks; ++ci) {
+            const ChunkRec& c = a.ch[ci];
+            const uint32_t buf = g & 1u;
+            ++g;
+            const bool fused = c.flags & CH_FUSED;
+            const int ncols = (int)c.rows - ps * CPW;   // columns of this chunk that belong to this warp (<= 0: none)
+            const uint32_t src = tmem + lane_addr + kColD0 + buf * kCW + (uint32_t)(ps * CPW);
+            const uint32_t dst = tmem + lane_addr + (uint32_t)c.dst_col + (uint32_t)(ps * CPW / 2);
+            const int h1_bar = B_H1 + (int)c.h1_bar;
+            if (prof_me) bar_wait_t<PROF>(bars, B_DFULL + buf, mask, eacc, E_DFULL - 8);
+            else bar_wait(bars, B_DFULL + buf, mask);
+            ptx::tc_fence_after();
+            const long long t_ld = prof_me ? clock64() : 0;
+            uint32_t rr[CPW / 16][16];
+            uint32_t pk[CPW / 16][8];
+            if (ncols >= CPW) {
+              // the usual case, free of predicates: this warp's full share of a kCW-column chunk
+#pragma unroll
+              for (int grp = 0; grp < CPW / 16; ++grp) ptx::tmem_ld16(src + grp * 16, rr[grp]);
+              ptx::tmem_wait_ld();
+              if (prof_me) eacc[E_LD - 8] += clock64() - t_ld;
+#pragma unroll
+              for (int grp = 0; grp < CPW / 16; ++grp)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)   // the bias is already in the accumulator (bias MMA)
+                  pk[grp][jj] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][2 * jj]), __uint_as_float(rr[grp][2 * jj + 1]));
+              if (fused) {  // the output-layer MMAs of the previous chunk must have consumed H2c
+                if (prof_me) bar_wait_t<PROF>(bars, B_H2EMPTY, mask, eacc, E_H2EMPTY - 8);
+                else bar_wait(bars, B_H2EMPTY, mask);
                 ptx::tc_fence_after();
-                const long long t_ld = prof_me ? clock64() : 0;
-                const uint32_t src = tmem + lane_addr + kColD0 + buf * kCW + (uint32_t)(ps * CPW);
-                const uint32_t dst = tmem + lane_addr + (fused ? kColH2 : hf_base + (uint32_t)c * (kCW / 2)) + (uint32_t)(ps * CPW / 2);
-                uint32_t rr[CPW / 16][16];
-#pragma unroll
-                for (int grp = 0; grp < CPW / 16; ++grp)
-                  if (grp * 16 < ncols) ptx::tmem_ld16(src + grp * 16, rr[grp]);
-                ptx::tmem_wait_ld();
-                if (prof_me) eacc[E_LD - 8] += clock64() - t_ld;
-                uint32_t pk[CPW / 16][8];
-#pragma unroll
-                for (int grp = 0; grp < CPW / 16; ++grp) {
-                  if (grp * 16 < ncols) {
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)   // the bias is already in the accumulator (bias MMA)
-                      pk[grp][jj] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][2 * jj]), __uint_as_float(rr[grp][2 * jj + 1]));
-                  }
-                }
-                if (fused) {  // the output-layer MMAs of the previous chunk must have consumed H2c
-                  if (prof_me) bar_wait_t<PROF>(bars, B_H2EMPTY, mask, eacc, E_H2EMPTY - 8);
-                  else bar_wait(bars, B_H2EMPTY, mask);
-                  ptx::tc_fence_after();
-                }
-                const long long t_st = prof_me ? clock64() : 0;
-#pragma unroll
-                for (int grp = 0; grp < CPW / 16; ++grp)
-                  if (grp * 16 < ncols) ptx::tmem_st8(dst + grp * 8, pk[grp]);
-                if (idx == 0 && c == 0) {
-                  // first chunk of a right-hand side: zero this thread's share of Y (every output-layer MMA accumulates).  All
-                  // threads have read the previous Y (this chunk's MMAs were issued behind the X-full barrier), and the first
-                  // output-layer MMA waits for a LATER chunk's drained arrival of these same warps.
-                  const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-                  for (int z = 0; z < 96 / PS; z += 8) ptx::tmem_st8(tmem + lane_addr + kColY + (uint32_t)(ps * (96 / PS) + z), zero);
-                }
-                ptx::tmem_wait_st();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                  arrive_issuer(B_DEMPTY + buf);          // accumulator drained AND (fused chunk) H2c written
-                  if (!fused) arrive_issuer(B_H1 + h1_base + c);
-                }
-                if (prof_me) eacc[E_ST - 8] += clock64() - t_st;
               }
+#pragma unroll
+              for (int grp = 0; grp < CPW / 16; ++grp) ptx::tmem_st8(dst + grp * 8, pk[grp]);
+            } else {
+              // narrow last chunk of a layer: groups of 16 columns, predicated
+#pragma unroll
+              for (int grp = 0; grp < CPW / 16; ++grp)
+                if (grp * 16 < ncols) ptx::tmem_ld16(src + grp * 16, rr[grp]);
+              ptx::tmem_wait_ld();
+              if (prof_me) eacc[E_LD - 8] += clock64() - t_ld;
+#pragma unroll
+              for (int grp = 0; grp < CPW / 16; ++grp) {
+                if (grp * 16 < ncols) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj)
+                    pk[grp][jj] = pack_act<FP16, ACT>(__uint_as_float(rr[grp][2 * jj]), __uint_as_float(rr[grp][2 * jj + 1]));
+                }
+              }
+              if (fused) {
+                if (prof_me) bar_wait_t<PROF>(bars, B_H2EMPTY, mask, eacc, E_H2EMPTY - 8);
+                else bar_wait(bars, B_H2EMPTY, mask);
+                ptx::tc_fence_after();
+              }
+#pragma unroll
+              for (int grp = 0; grp < CPW / 16; ++grp)
+                if (grp * 16 < ncols) ptx::tmem_st8(dst + grp * 8, pk[grp]);
             }
+            const long long t_st = prof_me ? clock64() : 0;
+            if (ci == 0) {
+              // first chunk of a right-hand side: zero this thread's share of Y (every output-layer MMA accumulates).  All
+              // threads have read the previous Y (this chunk's MMAs were issued behind the X-full barrier), and the first
+              // output-layer MMA waits for a LATER chunk's drained arrival of these same warps.
+              const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+              for (int z = 0; z < 96 / PS; z += 8) ptx::tmem_st8(tmem + lane_addr + kColY + (uint32_t)(ps * (96 / PS) + z), zero);
+            }
+            ptx::tmem_wait_st();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              arrive_issuer(B_DEMPTY + buf);          // accumulator drained AND (fused chunk) H2c written
+              if (!fused) arrive_issuer(h1_bar);
+            }
+            if (prof_me) eacc[E_ST - 8] += clock64() - t_st;
           }
           // ---- physics, part A: everything that does not need the NN outputs (runs while the last output-layer
           //      MMAs are still in flight).  Index i of the x arrays is cell c0 - 1 + i. ----
@@ -958,6 +976,7 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   for (int i = 0; i < 96; ++i) pl.b3[i] = 0.0f;
   tape.clear();
   pl.n_stages = 0;
+  pl.n_chunks = 0;
   std::vector<uint16_t> half[2];
   // output-layer blocks ride two stages behind their fused chunk (see the MMA issuer): q1 goes into the coming stage
   struct Pending { bool valid; int net, c, cols; } q1{false, 0, 0, 0}, q0{false, 0, 0, 0};
@@ -994,9 +1013,26 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
       const int kin = (j == 0) ? kS : pl.hpad[j - 1];
       const int hp = pl.hpad[j];
       const TapeQuant tq{fp16, tape_idx, n_tapes, net, j};
+      const int nc1 = (pl.hpad[0] + kCW - 1) / kCW;
+      const int h1_base = pl.interleave ? net * nc1 : 0;
+      const uint32_t hf_base = kColHF + (pl.interleave ? (uint32_t)(net * (pl.hpad[0] / 2)) : 0u);
       for (int c = 0; c * kCW < hp; ++c) {
         const int rows = std::min(kCW, hp - c * kCW);
         const bool split = (rows == kCW) && (kin / 16 == 25);   // two stages: k-steps [0, kSplitK) | [kSplitK, 25) + bias + W_out
+        if (pl.n_chunks >= kMaxChunks) { overflow = true; break; }
+        ChunkRec& cr = pl.ch[pl.n_chunks++];
+        cr = ChunkRec{};
+        cr.a_col = (uint16_t)(j == 0 ? kColX : hf_base);
+        cr.dst_col = (uint16_t)(fused ? kColH2 : hf_base + (uint32_t)c * (kCW / 2));
+        cr.rows = (uint8_t)rows;
+        cr.kin = (uint8_t)(kin / 16);
+        cr.stage = (uint8_t)pl.n_stages;
+        cr.flags = (uint8_t)((split ? CH_SPLIT : 0) | (fused ? CH_FUSED : 0) | ((j > 0 && (c == 0 || pl.interleave)) ? CH_WAIT_H1 : 0));
+        cr.h1_bar = (uint8_t)(h1_base + c);
+        cr.h1_base = (uint8_t)h1_base;
+        cr.h1_seq = (uint8_t)(pl.interleave ? 0 : net);
+        cr.out_ks = (uint8_t)(q1.valid ? q1.cols / 16 : 0);
+        cr.out_net = (uint8_t)q1.net;
         if (split) {
           for (int hf = 0; hf < 2; ++hf)
             append_half(half[hf], tq, wn + nd.w_off[j], nd.sizes[j], nd.sizes[j + 1], c * kCW + hf * (rows / 2), rows / 2, 0, kSplitK);
@@ -1026,6 +1062,10 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
   if (q1.valid) out_halves(q1);
   out_halves(q0);   // the last chunk of a net is always a fused one
   close_stage();
+  pl.tail_ks[0] = (uint8_t)(q1.valid ? q1.cols / 16 : 0);
+  pl.tail_net[0] = (uint8_t)q1.net;
+  pl.tail_ks[1] = (uint8_t)(q0.cols / 16);
+  pl.tail_net[1] = (uint8_t)q0.net;
   if (overflow) { set_error("tensor-core path: schedule longer than the stage table"); return OPZ_EUNSUP; }
   pl.tape_bytes = tape.size() * 2;
   // ---- ring placement (byte FIFO, every right-hand side starts at offset 0) and in-flight allowance ----
@@ -1051,6 +1091,19 @@ static int build_plan(const opz_model* m, const std::vector<float>& w, bool fp16
     }
     pl.st_keep[s] = (uint8_t)keep;
   }
+  for (int i = 0; i < pl.n_chunks; ++i) {   // ring offsets of the chunks' stages
+    ChunkRec& cr = pl.ch[i];
+    const int sA = cr.stage;
+    cr.offA = pl.st_off[sA];
+    if (cr.flags & CH_SPLIT) {
+      cr.offB = pl.st_off[sA + 1];
+      cr.out_off = cr.offB + (kCW / 2) * ((uint32_t)(25 - kSplitK) * 32u + 16u);
+    } else {
+      cr.offB = cr.offA;
+      cr.out_off = cr.offA + (uint32_t)(cr.rows / 2) * ((uint32_t)cr.kin * 32u + 16u);
+    }
+  }
+  pl.tail_off = pl.st_off[n - 1];
   return OPZ_OK;
 }
 
@@ -1138,6 +1191,12 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
   a.dither_x = getenv("OPZ_TC_NO_XDITHER") == nullptr;
   a.interleave = pl->interleave ? 1 : 0;
   a.nc1 = (pl->hpad[0] + kCW - 1) / kCW;
+  a.n_chunks = pl->n_chunks;
+  a.h1_mult = pl->interleave ? 1 : 3;
+  a.tail_off = pl->tail_off;
+  std::memcpy(a.tail_ks, pl->tail_ks, sizeof(a.tail_ks));
+  std::memcpy(a.tail_net, pl->tail_net, sizeof(a.tail_net));
+  std::memcpy(a.ch, pl->ch, sizeof(a.ch));
   if (const char* e = getenv("OPZ_TC_MMA_WARPS")) a.n_mma_warps = atoi(e) == 1 ? 1 : 2;
   std::memcpy(a.st_off, pl->st_off, sizeof(a.st_off));
   std::memcpy(a.st_bytes, pl->st_bytes, sizeof(a.st_bytes));
