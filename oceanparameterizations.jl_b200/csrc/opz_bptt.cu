@@ -874,6 +874,7 @@ bool plan_cluster(const opz_ctx* ctx, const NetDesc& nd, int nz, int CP, int CS,
   lay.SL = (std::max(NO3, S3) * CP + CS - 1) / CS;
   lay.recv_small = take(CS * lay.SL);
   lay.rbase = take(CS);
+  lay.mbar = take(2 * cl::kNumXB);
   lay.total = off;
   return (size_t)off * sizeof(float) <= (size_t)ctx->smem_optin;
 }

@@ -45,8 +45,21 @@ struct Layout {                 // float offsets into dynamic shared memory (ide
   int recv_small;               // [kCS][SL]
   int SL;
   int rbase;                    // 16 x uint32: shared::cluster base address of every rank
+  int mbar;                     // kNumXB x uint64 (8-byte aligned): one mbarrier per exchange channel, see XB_*
   int total;
 };
+
+// Exchange channels (CS > 1).  Every exchange of the sweep is data written into a peer's shared memory with
+// st.async ... mbarrier::complete_tx::bytes: the store itself signals the RECEIVER's mbarrier, and a CTA proceeds as soon as the
+// bytes IT expects have landed.  No cluster-wide barrier, no release fence (barrier.cluster.arrive.release costs MEMBAR.ALL.GPU,
+// which also had to drain the HBM record stores): an exchange costs the DSMEM transit (~215 cycles) plus its bytes.
+// Single-buffered receive areas are safe because every reuse of a buffer lies a full all-to-all dependency later: a peer can
+// only be one exchange ahead, and it gets there only with data this CTA produced AFTER its last read of the buffer.
+enum : int { XB_GATHER = 0,                 // [kMaxLayers] all-gather of h_l (forward)
+             XB_AR1F = XB_GATHER + kMaxLayers, XB_AR2F,   // forward all-reduce of the NN outputs: reduce-scatter / broadcast
+             XB_AR1B, XB_AR2B,              // backward all-reduce of the input cotangent
+             XB_RS,                         // [2] reduce-scatter of W^T dz (backward), double-buffered when L >= 4
+             kNumXB = XB_RS + 2 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -72,6 +85,41 @@ __device__ __forceinline__ void st_remote_cols(uint32_t addr, const float (&v)[C
     for (int c = 0; c < CP; ++c) st_remote(addr + 4u * c, v[c]);
   }
 }
+// store + signal: 4 (or 4 CP) bytes into a peer's shared memory, counted on the peer's mbarrier `bar` (both shared::cluster addresses)
+__device__ __forceinline__ void st_async(uint32_t addr, float v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(bar) : "memory");
+}
+template <int CP>
+__device__ __forceinline__ void st_async_cols(uint32_t addr, const float (&v)[CP], uint32_t bar) {
+  if constexpr (CP == 2)
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(bar) : "memory");
+  else if constexpr (CP == 4)
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(bar) : "memory");
+  else {
+#pragma unroll
+    for (int c = 0; c < CP; ++c) st_async(addr + 4u * c, v[c], bar);
+  }
+}
+__device__ __forceinline__ void xb_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
+// the receiver's one arrival of an exchange instance, carrying the bytes it expects (may come after the first bytes have landed)
+__device__ __forceinline__ void xb_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xb_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
 // CS = 1 (the whole net in one CTA): the "exchanges" are local shared-memory stores and the barrier is __syncthreads — none of the
 // MEMBAR.ALL.GPU / CCTL.IVALL that the release / acquire cluster barrier costs
 template <int CS>
@@ -100,6 +148,23 @@ __device__ __forceinline__ void fma_cols(float (&acc)[CP], float w, const float*
     acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
   }
 }
+
+// v[0..CP) = p[0..CP) with one vector load
+template <int CP>
+__device__ __forceinline__ void load_cols(float (&v)[CP], const float* p) {
+  if constexpr (CP == 1) v[0] = p[0];
+  else if constexpr (CP == 2) { const float2 q = *reinterpret_cast<const float2*>(p); v[0] = q.x; v[1] = q.y; }
+  else { const float4 q = *reinterpret_cast<const float4*>(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+}
+template <int CP>
+__device__ __forceinline__ void store_cols(float* p, const float (&v)[CP]) {
+  if constexpr (CP == 1) p[0] = v[0];
+  else if constexpr (CP == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  else *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+constexpr int kRB = 5;   // register blocking of the slice mat-vecs: one vector load of the CP activation columns feeds kRB x CP FMAs.
+                         // These loops are bound by shared-memory instruction passes (an LDS.128 costs 4 even as a broadcast, an
+                         // LDS.32 one): 1 + 4 passes per CP FMAs unblocked, kRB + 4 per kRB x CP blocked.
 
 // per-phase cycle counters of CTA 0 (thread 0), dumped by the host when OPZ_BPTT_PROFILE is set
 __device__ unsigned long long g_phase_cycles[24];
@@ -144,8 +209,44 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
   for (int i = 0; i < 24; ++i) ph[i] = 0;
   long long tlast = clock64();
 
-  // ---- one-time setup: remote bases, weight slices, initial state ----
+  // ---- one-time setup: remote bases, exchange barriers, weight slices, initial state ----
   if (t < CS) rbase[t] = map_to_rank(my_base, (uint32_t)t);
+  const uint32_t xb0 = my_base + 4u * (uint32_t)lay.mbar;     // this CTA's exchange barriers (shared::cta address)
+  const uint32_t xb_off = 4u * (uint32_t)lay.mbar;            // ... and their offset from a peer's base
+  uint32_t xb_par = 0;                                         // parity of the next completion of each channel (bit = channel)
+  // bytes this CTA receives per instance of each channel
+  auto share_of = [&](int count, int r) { return count > r ? (count - r + CS - 1) / CS : 0; };   // entries e < count with e % CS == r
+  auto xb_bytes = [&](int ch) -> uint32_t {
+    if (ch < XB_GATHER + kMaxLayers) { const int l = ch - XB_GATHER; return l <= L - 3 ? 12u * (uint32_t)(a.nd.sizes[l + 1] * CP) : 0u; }
+    if (ch == XB_AR1F) return 4u * (uint32_t)(CS * share_of(NO3 * CP, rank));
+    if (ch == XB_AR2F) return 4u * (uint32_t)(NO3 * CP);
+    if (ch == XB_AR1B) return 4u * (uint32_t)(CS * share_of(S3 * CP, rank));
+    if (ch == XB_AR2B) return 4u * (uint32_t)(S3 * CP);
+    return 0u;   // XB_RS: depends on the layer, posted per use
+  };
+  auto rs_bytes = [&](int l) -> uint32_t {   // reduce-scatter of layer l's input cotangent: this CTA owns ULp units of hidden layer l - 1
+    const int K = a.nd.sizes[l], ULp = lay.UL[l - 1];
+    const int cnt = max(0, min(ULp, K - rank * ULp));
+    return 4u * (uint32_t)(CS * 3 * cnt * CP);
+  };
+  if constexpr (CS > 1) {
+    if (t == 0) {
+      for (int ch = 0; ch < kNumXB; ++ch) xb_init(xb0 + 8u * ch);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (int ch = 0; ch < XB_RS; ++ch) xb_expect(xb0 + 8u * ch, xb_bytes(ch));
+    }
+  }
+  // wait for the current instance of channel ch, then post the expectation of the next one (same byte count every time)
+  auto xb_wait_repost = [&](int ch, uint32_t next_bytes) {
+    if constexpr (CS > 1) {
+      xb_wait(xb0 + 8u * ch, (xb_par >> ch) & 1u);
+      xb_par ^= 1u << ch;
+      __syncthreads();   // the barrier this replaces also ordered the CTA's own threads (reuse of part / hs / dzs ...)
+      if (t == 0) xb_expect(xb0 + 8u * ch, next_bytes);
+    } else {
+      __syncthreads();
+    }
+  };
   for (int l = 0; l < L - 1; ++l) {
     const int K = a.nd.sizes[l], N = a.nd.sizes[l + 1], UL = lay.UL[l], u0 = rank * UL;
     float* W = sm + lay.W[l];
@@ -179,46 +280,117 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
   // two-phase all-reduce of `count` (<= kThreads) per-CTA partials held by threads t < count:
   // reduce-scatter to owner = e % 16; the owner adds bias[e / CP] and broadcasts into dst[e] of every CTA.
   // `between()` runs between the first arrive and wait (HBM record stores go there).
-  auto all_reduce = [&](float value, int count, float* dst, const float* bias_by_item, auto&& between) {
-    if (t < count) {
-      const int owner = t % CS, slot = t / CS;
-      st_remote(rbase[owner] + 4u * (uint32_t)(lay.recv_small + rank * lay.SL + slot), value);
-    }
-    cluster_arrive<CS>();
-    between();
-    cluster_wait<CS>();
-    if (t < lay.SL) {
-      const int e = t * CS + rank;
-      if (e < count) {
-        float s = 0.0f;
-#pragma unroll
-        for (int src = 0; src < CS; ++src) s += recv_small[src * lay.SL + t];
-        if (bias_by_item) s += bias_by_item[e / CP];
-        const uint32_t off = 4u * (uint32_t)((int)(dst - sm) + e);
-#pragma unroll
-        for (int d = 0; d < CS; ++d) st_remote(rbase[d] + off, s);
+  auto all_reduce = [&](float value, int count, float* dst, const float* bias_by_item, int ch1, int ch2, auto&& between) {
+    if constexpr (CS > 1) {
+      if (t < count) {
+        const int owner = t % CS, slot = t / CS;
+        st_async(rbase[owner] + 4u * (uint32_t)(lay.recv_small + rank * lay.SL + slot), value, rbase[owner] + xb_off + 8u * ch1);
       }
+      between();
+      xb_wait_repost(ch1, xb_bytes(ch1));
+      if (t < lay.SL * CS) {   // CS threads per owned entry: each forms the sum and sends it to ONE peer
+        const int sl = t / CS, d = t % CS;
+        const int e = sl * CS + rank;
+        if (e < count) {
+          float s = 0.0f;
+#pragma unroll
+          for (int src = 0; src < CS; ++src) s += recv_small[src * lay.SL + sl];
+          if (bias_by_item) s += bias_by_item[e / CP];
+          st_async(rbase[d] + 4u * (uint32_t)((int)(dst - sm) + e), s, rbase[d] + xb_off + 8u * ch2);
+        }
+      }
+      xb_wait_repost(ch2, xb_bytes(ch2));
+    } else {
+      if (t < count) recv_small[t] = value;   // (SL = count when CS = 1)
+      between();
+      __syncthreads();
+      if (t < count) dst[t] = recv_small[t] + (bias_by_item ? bias_by_item[t / CP] : 0.0f);
+      __syncthreads();
     }
-    cluster_sync_all<CS>();
   };
 
   // hidden layer l, forward, this CTA's slice; `in` is laid out [net][K][CP] (net_stride 0 for the shared
   // state input).  Returns z for threads t < 3 UL CP (item p = t / CP = net*UL + u, column slot t % CP).
   auto slice_forward = [&](int l, const float* in, int net_stride) -> float {
     const int K = a.nd.sizes[l], UL = lay.UL[l], NP = 3 * UL;
-    const int KSL = max(1, min(min(kThreads / NP, K), kMaxKSL));
     const float* W = sm + lay.W[l];
-    if (t < NP * KSL) {
-      const int p = t % NP, ks = t / NP, net = p / UL, u = p - net * UL;
-      float acc[CP];
+    int KSL;
+    constexpr int kKS = 16;   // k-split of the register-blocked form
+    if (CS > 1 && UL % kRB == 0 && 3 * (UL / kRB) * kKS <= kThreads && kKS * NP * CP <= lay.recv_big_size) {
+      // Register-blocked: one thread = kRB consecutive units of one net x all CP columns over every kKS-th input; lanes run over
+      // the k-split, so the weights of a load are UL words apart (UL odd: conflict-free) and the input columns of 16 consecutive k
+      // are one contiguous vector load.  The kKS partial sums per output go through the (forward-idle) reduce-scatter buffer.
+      const int gpn = UL / kRB;
+      float* scratch = sm + lay.recv_big;
+      if (t < 3 * gpn * kKS) {
+        const int grp = t / kKS, ks = t % kKS;
+        const int net = grp / gpn, ug = (grp - net * gpn) * kRB;
+        float acc[kRB][CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
-      const float* Wp = W + (size_t)net * K * UL + u;
-      const float* ip = in + (size_t)net * net_stride;
+        for (int j = 0; j < kRB; ++j)
+#pragma unroll
+          for (int c = 0; c < CP; ++c) acc[j][c] = 0.0f;
+        const float* Wp = W + (size_t)net * K * UL + ug;
+        const float* ip = in + (size_t)net * net_stride;
+#pragma unroll 4
+        for (int k = ks; k < K; k += kKS) {
+          float xv[CP];
+          load_cols<CP>(xv, ip + k * CP);
+#pragma unroll
+          for (int j = 0; j < kRB; ++j) {
+            const float w = Wp[k * UL + j];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) acc[j][c] = fmaf(w, xv[c], acc[j][c]);
+          }
+        }
+        float* sp = scratch + (ks * NP + net * UL + ug) * CP;   // vector stores: 16 B slots of a quarter warp (ks = 0..7) are 1200 B apart: conflict-free
+#pragma unroll
+        for (int j = 0; j < kRB; ++j) store_cols<CP>(sp + j * CP, acc[j]);
+      }
+      __syncthreads();
+      float z = 0.0f;
+      if (t < NP * CP) {
+#pragma unroll
+        for (int ks = 0; ks < kKS; ++ks) z += scratch[ks * NP * CP + t];
+        z += (sm + lay.bias[l])[tq];
+      }
+      return z;
+    }
+    if (UL <= 32) {
+      // One (net, k-split) task per group of LT lanes, lane = unit: the LT weights of a k are consecutive words (one conflict-free
+      // wavefront) and the CP input columns of that k are ONE broadcast address for the whole group.  (With items laid over
+      // threads modulo NP a warp straddled nets and k-splits: 2-way conflicts on the weights and 2 - 3 distinct input
+      // addresses per load; the slice mat-vec is bound by shared-memory wavefronts.)
+      const int LT = UL <= 8 ? 8 : (UL <= 16 ? 16 : 32);
+      const int n_tasks = kThreads / LT;
+      KSL = max(1, min(min(n_tasks / 3, K), kMaxKSL));
+      const int task = t / LT, u = t % LT;
+      if (task < 3 * KSL && u < UL) {
+        const int net = task / KSL, ks = task - net * KSL;
+        float acc[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+        const float* Wp = W + (size_t)net * K * UL + u;
+        const float* ip = in + (size_t)net * net_stride;
 #pragma unroll 8
-      for (int k = ks; k < K; k += KSL) fma_cols<CP>(acc, Wp[k * UL], ip + k * CP);
+        for (int k = ks; k < K; k += KSL) fma_cols<CP>(acc, Wp[k * UL], ip + k * CP);
 #pragma unroll
-      for (int c = 0; c < CP; ++c) part[(ks * NP + p) * CP + c] = acc[c];
+        for (int c = 0; c < CP; ++c) part[(ks * NP + net * UL + u) * CP + c] = acc[c];
+      }
+    } else {
+      KSL = max(1, min(min(kThreads / NP, K), kMaxKSL));
+      if (t < NP * KSL) {
+        const int p = t % NP, ks = t / NP, net = p / UL, u = p - net * UL;
+        float acc[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+        const float* Wp = W + (size_t)net * K * UL + u;
+        const float* ip = in + (size_t)net * net_stride;
+#pragma unroll 8
+        for (int k = ks; k < K; k += KSL) fma_cols<CP>(acc, Wp[k * UL], ip + k * CP);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) part[(ks * NP + p) * CP + c] = acc[c];
+      }
     }
     __syncthreads();
     float z = 0.0f;
@@ -249,10 +421,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
         if (l < L - 2) {
           if (live) {
             const uint32_t off = 4u * (uint32_t)(lay.hfull[l] + (net * N + u0 + u) * CP + tc);
+            if constexpr (CS > 1) {
+              // (one vector store of the CP columns per (item, peer), staged through shared memory, measured slower)
 #pragma unroll
-            for (int d = 0; d < CS; ++d) st_remote(rbase[d] + off, hv);
+              for (int d = 0; d < CS; ++d) st_async(rbase[d] + off, hv, rbase[d] + xb_off + 8u * (uint32_t)(XB_GATHER + l));
+            } else {
+              sm[lay.hfull[l] + (net * N + u0 + u) * CP + tc] = hv;
+            }
           }
-          cluster_arrive<CS>();
         } else if (mine) {
           hs[t] = live ? hv : 0.0f;
         }
@@ -263,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           a.G[l][o] = act_grad_dyn(z, a.nd.act);
         }
         if (l == 0 && recorder && t < S3 * CP && col_ok) a.X[(row0 + tc) * S3 + tq] = xs[t];
-        if (l < L - 2) cluster_wait<CS>();
+        if (l < L - 2) xb_wait_repost(XB_GATHER + l, xb_bytes(XB_GATHER + l));
         else __syncthreads();
         OPZ_PH(1);
       }
@@ -276,11 +452,18 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           const int net = tq / nout, j = tq - net * nout;
           const float* Wp = W + (size_t)net * UL * nout + j;
           const float* hp = hs + net * UL * CP + tc;
-#pragma unroll 5
-          for (int u = 0; u < UL; ++u) yp = fmaf(hp[u * CP], Wp[u * nout], yp);
+          float yq = 0.0f;   // two independent chains: the loop is bound by the FMA / LDS latency, not by throughput
+          int u = 0;
+#pragma unroll 4
+          for (; u + 1 < UL; u += 2) {
+            yp = fmaf(hp[u * CP], Wp[u * nout], yp);
+            yq = fmaf(hp[(u + 1) * CP], Wp[(u + 1) * nout], yq);
+          }
+          if (u < UL) yp = fmaf(hp[u * CP], Wp[u * nout], yp);
+          yp += yq;
         }
         OPZ_PH(2);
-        all_reduce(yp, NO3 * CP, yb, sm + lay.bias[L - 1], [] {});
+        all_reduce(yp, NO3 * CP, yb, sm + lay.bias[L - 1], XB_AR1F, XB_AR2F, [] {});
         OPZ_PH(3);
       }
       // physics + Runge-Kutta update, replicated in every CTA (opz_device.cuh formulas, one thread per face / cell)
@@ -472,9 +655,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           const int net = tq / UL, u = tq - net * UL;
           const float* Wp = W + (size_t)(net * UL + u) * nout;
           const float* dp = dy + net * nout * CP + tc;
-          float sacc = 0.0f;
-#pragma unroll 8
-          for (int j = 0; j < nout; ++j) sacc = fmaf(Wp[j], dp[j * CP], sacc);
+          float sacc = 0.0f, sacc2 = 0.0f;
+          int j = 0;
+#pragma unroll 4
+          for (; j + 1 < nout; j += 2) {
+            sacc = fmaf(Wp[j], dp[j * CP], sacc);
+            sacc2 = fmaf(Wp[j + 1], dp[(j + 1) * CP], sacc2);
+          }
+          if (j < nout) sacc = fmaf(Wp[j], dp[j * CP], sacc);
+          sacc += sacc2;
           const float dz = sacc * (sm + lay.gs[l])[t];
           dzs[t] = dz;
           if (u0 + u < N && col_ok) { pend = dz; pend_layer = l; pend_off = ((int64_t)net * a.rows_cap + row0 + tc) * N + u0 + u; }
@@ -491,23 +680,64 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
         const int ULp = lay.UL[l - 1], u0p = rank * ULp;     // slicing of hidden layer l-1
         const float* W = sm + lay.W[l];
         float* rb = sm + lay.recv_big + rs_parity * lay.recv_big_size;
-        for (int it = t; it < 3 * K; it += kThreads) {
-          const int net = it / K, k = it - net * K;
-          const float* Wp = W + ((size_t)net * K + k) * UL;
-          const float* dp = dzs + net * UL * CP;
-          float acc[CP];
-#pragma unroll
-          for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
-#pragma unroll 5
-          for (int u = 0; u < UL; ++u) fma_cols<CP>(acc, Wp[u], dp + u * CP);
+        const int rs_ch = XB_RS + rs_parity;
+        if constexpr (CS > 1) { if (t == 0) xb_expect(xb0 + 8u * rs_ch, rs_bytes(l)); }   // (every sender's bytes may already be here)
+        auto send_dh = [&](int net, int k, const float (&v)[CP]) {
           const int owner = k / ULp, kl = k - owner * ULp;
-          const uint32_t off = rbase[owner] + 4u * (uint32_t)((int)(rb - sm) + ((rank * 3 + net) * ULp + kl) * CP);
-          st_remote_cols<CP>(off, acc);
+          const int idx = ((rank * 3 + net) * ULp + kl) * CP;
+          if constexpr (CS > 1) {
+            st_async_cols<CP>(rbase[owner] + 4u * (uint32_t)((int)(rb - sm) + idx), v, rbase[owner] + xb_off + 8u * (uint32_t)rs_ch);
+          } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) rb[idx + c] = v[c];
+          }
+        };
+        if (K % kRB == 0) {
+          // one thread = kRB consecutive inputs k of one net x all CP columns
+          const int gpn = K / kRB;
+          for (int it = t; it < 3 * gpn; it += kThreads) {
+            const int net = it / gpn, k0 = (it - net * gpn) * kRB;
+            const float* Wp = W + ((size_t)net * K + k0) * UL;
+            const float* dp = dzs + net * UL * CP;
+            float acc[kRB][CP];
+#pragma unroll
+            for (int j = 0; j < kRB; ++j)
+#pragma unroll
+              for (int c = 0; c < CP; ++c) acc[j][c] = 0.0f;
+#pragma unroll 5
+            for (int u = 0; u < UL; ++u) {
+              float dv[CP];
+              load_cols<CP>(dv, dp + u * CP);
+#pragma unroll
+              for (int j = 0; j < kRB; ++j) {
+                const float w = Wp[j * UL + u];
+#pragma unroll
+                for (int c = 0; c < CP; ++c) acc[j][c] = fmaf(w, dv[c], acc[j][c]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < kRB; ++j) send_dh(net, k0 + j, acc[j]);
+          }
+        } else {
+          for (int it = t; it < 3 * K; it += kThreads) {
+            const int net = it / K, k = it - net * K;
+            const float* Wp = W + ((size_t)net * K + k) * UL;
+            const float* dp = dzs + net * UL * CP;
+            float acc[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+#pragma unroll 5
+            for (int u = 0; u < UL; ++u) fma_cols<CP>(acc, Wp[u], dp + u * CP);
+            send_dh(net, k, acc);
+          }
         }
         OPZ_PH(11);
-        cluster_arrive<CS>();
         flush();
-        cluster_wait<CS>();
+        if constexpr (CS > 1) {
+          xb_wait(xb0 + 8u * rs_ch, (xb_par >> rs_ch) & 1u);
+          xb_par ^= 1u << rs_ch;
+        }
+        __syncthreads();
         OPZ_PH(12);
         if (t < 3 * ULp * CP) {
           const int net = tq / ULp, u = tq - net * ULp;
@@ -528,16 +758,55 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
         const int UL = lay.UL[0];
         const float* W = sm + lay.W[0];
         float xp = 0.0f;
-        if (t < S3 * CP) {
-          for (int net = 0; net < 3; ++net) {
-            const float* Wp = W + ((size_t)net * S3 + tq) * UL;
-            const float* dp = dzs + net * UL * CP + tc;
-#pragma unroll 5
-            for (int u = 0; u < UL; ++u) xp = fmaf(Wp[u], dp[u * CP], xp);
+        constexpr int kIB = 4, kUS = 4;   // register-blocked form: kIB state entries x CP columns per thread, units split kUS ways
+        const int pstride = S3 * CP + 4;   // partial-sum planes 16 B out of phase: the vector stores of a quarter warp do not collide
+        if (CS > 1 && S3 % kIB == 0 && 3 * (S3 / kIB) * kUS <= kThreads && 3 * kUS * pstride <= lay.recv_big_size) {
+          float* scratch = sm + lay.recv_big;   // this right-hand side's reduce-scatter data has been consumed
+          const int ngi = S3 / kIB;
+          if (t < 3 * ngi * kUS) {
+            const int us = t % kUS, ig = (t / kUS) % ngi, net = t / (kUS * ngi);
+            const int ulen = (UL + kUS - 1) / kUS, ua = us * ulen, ub = min(UL, ua + ulen);
+            float acc[kIB][CP];
+#pragma unroll
+            for (int j = 0; j < kIB; ++j)
+#pragma unroll
+              for (int c = 0; c < CP; ++c) acc[j][c] = 0.0f;
+            const float* Wp = W + ((size_t)net * S3 + ig * kIB) * UL;
+            const float* dp = dzs + net * UL * CP;
+            for (int u = ua; u < ub; ++u) {
+              float dv[CP];
+              load_cols<CP>(dv, dp + u * CP);
+#pragma unroll
+              for (int j = 0; j < kIB; ++j) {
+                const float w = Wp[j * UL + u];
+#pragma unroll
+                for (int c = 0; c < CP; ++c) acc[j][c] = fmaf(w, dv[c], acc[j][c]);
+              }
+            }
+            float* sp = scratch + (net * kUS + us) * pstride + ig * kIB * CP;
+#pragma unroll
+            for (int j = 0; j < kIB; ++j) store_cols<CP>(sp + j * CP, acc[j]);
           }
+          __syncthreads();
+          if (t < S3 * CP) {
+#pragma unroll
+            for (int q2 = 0; q2 < 3 * kUS; ++q2) xp += scratch[q2 * pstride + t];
+          }
+        } else if (t < S3 * CP) {
+          float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;   // the three nets as three independent chains (latency-bound loop)
+          const float* Wp = W + (size_t)tq * UL;
+          const float* dp = dzs + tc;
+          const int wn = S3 * UL, dn = UL * CP;
+#pragma unroll 5
+          for (int u = 0; u < UL; ++u) {
+            x0 = fmaf(Wp[u], dp[u * CP], x0);
+            x1 = fmaf(Wp[wn + u], dp[dn + u * CP], x1);
+            x2 = fmaf(Wp[2 * wn + u], dp[2 * dn + u * CP], x2);
+          }
+          xp = (x0 + x1) + x2;
         }
         OPZ_PH(14);
-        all_reduce(xp, S3 * CP, yb, nullptr, [&] {
+        all_reduce(xp, S3 * CP, yb, nullptr, XB_AR1B, XB_AR2B, [&] {
           flush();
           if (recorder && t < (nz + 1) * CP && tq > 0 && tq < nz && col_ok) {
             a.DY[((int64_t)0 * a.rows_cap + row0 + tc) * nout + tq - 1] = dy_u;
