@@ -41,6 +41,9 @@ def _case(oracle, flags, sizes, act, B, n_steps, save_every, seed=1, tau=172800.
     ("two_layer_swish_heun_diurnal", "diurnal", (96, 400, 31), 4, 1, 7),
     ("four_layer_tanh_euler_nn_only", "none", (96, 40, 30, 20, 31), 2, 0, 3),
     ("leakyrelu_ragged_two_column_tiles", "train", (96, 64, 48, 31), 5, 2, 37),
+    # three hidden layers too wide for one SM: the 16-CTA cluster path with two all-gathers and the double-buffered
+    # reduce-scatter channel (st.async exchanges of opz_bptt_cluster.cuh)
+    ("four_layer_relu_wide_cluster", "train", (96, 256, 250, 240, 31), 1, 2, 6),
 ])
 def test_loss_grad_matches_autograd_twin(opz, oracle, ctx, name, flags, sizes, act, scheme, B):
     from oracle import nde_oracle_torch as OT
