@@ -174,7 +174,7 @@ __device__ __forceinline__ void bar_wait(uint64_t* bars, int id, uint32_t& mask)
 
 // wait-time profile (OPZ_TC_PROFILE=1, relu kernels only): [0..7] MMA warp, [8..15] first epilogue warp of CTA 0
 __device__ unsigned long long g_tc2_wait[16];
-enum { W_X = 0, W_DEMPTY = 1, W_H1 = 2, W_FULL = 3, W_H2FULL = 4, W_TOTAL = 5,
+enum { W_X = 0, W_DEMPTY = 1, W_H1 = 2, W_FULL = 3, W_H2FULL = 4, W_TOTAL = 5, W_DECODE = 6, W_ISSUE = 7,
        E_DFULL = 8, E_H2EMPTY = 9, E_YFULL = 10, E_PHYS_A = 11, E_TOTAL = 12, E_PHYS_B = 13, E_LD = 14, E_ST = 15 };
 template <bool PROF>
 __device__ __forceinline__ void bar_wait_t(uint64_t* bars, int id, uint32_t& mask, long long* acc, int slot) {
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const uint32_t gi = g0 + ci;                     // global index of this accumulator chunk
             if (nw == 2u && (gi & 1u) != me) continue;       // the other issuing warp's chunk (a warp owns one accumulator buffer)
             // ---- everything that does not depend on a barrier: before the waits ----
+            const long long t_top = PROF ? clock64() : 0;
             const ChunkRec& c = a.ch[ci];
             const uint32_t buf = gi & 1u;
             const uint32_t rows = c.rows, kin = c.kin;
@@ -388,8 +389,11 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
             const bool static_shape = (rows == (uint32_t)kCW || rows == 16u) && (kin == 25u || kin == 6u);
             // ---- waits: the weights, then "buffer drained" of chunk g - 2 = completion (g >> 1) - 1 of this buffer's barrier
             //      (for a fused chunk also: its H2c is written) ----
+            if constexpr (PROF) wacc[W_DECODE] += clock64() - t_top;
             wait_full(gs);
             if (gi >= 2u) wait_phase<PROF>(bars, B_DEMPTY + (int)buf, (gi >> 1) - 1u, wacc, W_DEMPTY);
+            const long long t_iss = PROF ? clock64() : 0;
+            const long long w_before = PROF ? wacc[W_H1] + wacc[W_FULL] : 0;
             // Only the first chunk of a layer fed by HF paces itself on the H1 barriers (CH_WAIT_H1).  The second chunk (possibly
             // the other issuing warp's) is covered by its D-empty wait: chunk g - 2 is then the LAST first-layer chunk, whose
             // drained arrival comes after its tcgen05.st and after all earlier drains — so D-empty must keep being signalled
@@ -484,6 +488,7 @@ __global__ void __launch_bounds__((3 + E) * 32, 1) rollout_tc2_kernel(const __gr
               }
               __syncwarp();
             }
+            if constexpr (PROF) wacc[W_ISSUE] += (clock64() - t_iss) - (wacc[W_H1] + wacc[W_FULL] - w_before);   // issue region without the waits inside it
           }
           // tail stage: the output-layer MMAs of the last two chunks, each behind the "drained" arrival of its buffer
           const uint32_t g = g0 + nch;
@@ -1256,8 +1261,8 @@ int tc2_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int prec
     const int stages = c.scheme == OPZ_RK4 ? 4 : (c.scheme == OPZ_RK2 ? 2 : 1);
     const double per = 1.0 / ((double)my_items * c.n_steps * stages);
     fprintf(stderr, "opz tc2 profile (CTA 0, cycles per tile right-hand side): MMA warp total %.0f | wait X %.0f, D-empty %.0f, H1 %.0f, "
-            "weights %.0f, H2-full %.0f || epilogue warp total %.0f | wait D-full %.0f, H2-empty %.0f, Y-full %.0f, physics A %.0f, physics B + publish %.0f, drain ld %.0f, drain st+arrive %.0f\n",
-            w[W_TOTAL] * per, w[W_X] * per, w[W_DEMPTY] * per, w[W_H1] * per, w[W_FULL] * per, w[W_H2FULL] * per,
+            "weights %.0f, H2-full %.0f; decode %.0f, issue %.0f || epilogue warp total %.0f | wait D-full %.0f, H2-empty %.0f, Y-full %.0f, physics A %.0f, physics B + publish %.0f, drain ld %.0f, drain st+arrive %.0f\n",
+            w[W_TOTAL] * per, w[W_X] * per, w[W_DEMPTY] * per, w[W_H1] * per, w[W_FULL] * per, w[W_H2FULL] * per, w[W_DECODE] * per, w[W_ISSUE] * per,
             w[E_TOTAL] * per, w[E_DFULL] * per, w[E_H2EMPTY] * per, w[E_YFULL] * per, w[E_PHYS_A] * per, w[E_PHYS_B] * per, w[E_LD] * per, w[E_ST] * per);
   }
   return OPZ_OK;
