@@ -315,15 +315,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
     const int K = a.nd.sizes[l], UL = lay.UL[l], NP = 3 * UL;
     const float* W = sm + lay.W[l];
     int KSL;
-    constexpr int kKS = 16;   // k-split of the register-blocked form
-    if (CS > 1 && UL % kRB == 0 && 3 * (UL / kRB) * kKS <= kThreads && kKS * NP * CP <= lay.recv_big_size) {
-      // Register-blocked: one thread = kRB consecutive units of one net x all CP columns over every kKS-th input; lanes run over
-      // the k-split, so the weights of a load are UL words apart (UL odd: conflict-free) and the input columns of 16 consecutive k
-      // are one contiguous vector load.  The kKS partial sums per output go through the (forward-idle) reduce-scatter buffer.
+    constexpr int kKS = 32, kPL = 16;   // k-split of the register-blocked form = one warp per (net, unit group); partial-sum planes kept
+    if (CS > 1 && UL % kRB == 0 && 3 * (UL / kRB) * kKS <= kThreads && kPL * NP * CP <= lay.recv_big_size) {
+      // Register-blocked: one thread = kRB consecutive units of one net x all CP columns over every 32nd input; the 32 lanes of
+      // a warp are the 32 k-splits of ONE unit group, so the weights of a load are UL words apart (UL odd: 32 distinct banks —
+      // with two unit groups per warp the half-warps collided, 1.9 wavefronts per load in the ncu source view) and the input
+      // columns of 32 consecutive k are one contiguous vector load.  Lanes 16..31 hand their partial sums to lanes 0..15
+      // (one shuffle each); the 16 planes left go through the (forward-idle) reduce-scatter buffer.
       const int gpn = UL / kRB;
       float* scratch = sm + lay.recv_big;
-      if (t < 3 * gpn * kKS) {
-        const int grp = t / kKS, ks = t % kKS;
+      const int grp = t / kKS, ks = t % kKS;
+      if (grp < 3 * gpn) {   // whole warps
         const int net = grp / gpn, ug = (grp - net * gpn) * kRB;
         float acc[kRB][CP];
 #pragma unroll
@@ -343,15 +345,21 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
             for (int c = 0; c < CP; ++c) acc[j][c] = fmaf(w, xv[c], acc[j][c]);
           }
         }
-        float* sp = scratch + (ks * NP + net * UL + ug) * CP;   // vector stores: 16 B slots of a quarter warp (ks = 0..7) are 1200 B apart: conflict-free
 #pragma unroll
-        for (int j = 0; j < kRB; ++j) store_cols<CP>(sp + j * CP, acc[j]);
+        for (int j = 0; j < kRB; ++j)
+#pragma unroll
+          for (int c = 0; c < CP; ++c) acc[j][c] += __shfl_down_sync(0xffffffffu, acc[j][c], kPL);
+        if (ks < kPL) {
+          float* sp = scratch + (ks * NP + net * UL + ug) * CP;   // vector stores: 16 B slots of a quarter warp (ks = 0..7) are 1200 B apart: conflict-free
+#pragma unroll
+          for (int j = 0; j < kRB; ++j) store_cols<CP>(sp + j * CP, acc[j]);
+        }
       }
       __syncthreads();
       float z = 0.0f;
       if (t < NP * CP) {
 #pragma unroll
-        for (int ks = 0; ks < kKS; ++ks) z += scratch[ks * NP * CP + t];
+        for (int ks2 = 0; ks2 < kPL; ++ks2) z += scratch[ks2 * NP * CP + t];
         z += (sm + lay.bias[l])[tq];
       }
       return z;
