@@ -9,6 +9,28 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libopz.so")
 
+
+def _prefer_bundled_nccl() -> None:
+    """libopz binds NCCL at run time (dlopen on first use of a communicator).  The dynamic loader keeps ONE library per SONAME
+    in a process, so if libopz loaded the system libnccl.so.2 first, a later `import torch` would be bound to it as well —
+    and fails when PyTorch's own wheel is newer.  Point libopz at the wheel PyTorch uses (nvidia-nccl), found without
+    importing torch; an explicit OPZ_NCCL_LIB wins."""
+    if os.environ.get("OPZ_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []) if spec else []:
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["OPZ_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+_prefer_bundled_nccl()
+
 # ---- constants mirrored from include/opz.h -------------------------------------------------------
 OPZ_OK, OPZ_EINVAL, OPZ_ENODEV, OPZ_ECUDA, OPZ_ENOMEM, OPZ_EUNSUP, OPZ_ENCCL = 0, -1, -2, -3, -4, -5, -6
 COMM_ID_BYTES = 128

@@ -33,9 +33,14 @@ NcclApi g_nccl;
 std::once_flag g_nccl_once;
 
 void load_nccl() {
+  // 1. a NCCL this process already carries (PyTorch's): share that instance; 2. OPZ_NCCL_LIB; 3. the system library.
+  //    RTLD_LOCAL: nothing else may bind to our choice through the global namespace.  (The loader still de-duplicates by
+  //    SONAME: whoever loads "libnccl.so.2" first decides for the whole process.  A host that will import PyTorch later
+  //    should point OPZ_NCCL_LIB at PyTorch's copy — the Python package does so on import.)
+  g_nccl.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
   const char* names[4] = {getenv("OPZ_NCCL_LIB"), "libnccl.so.2", "libnccl.so", nullptr};
   for (int i = 0; i < 3 && !g_nccl.handle; ++i)
-    if (names[i] && *names[i]) g_nccl.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (names[i] && *names[i]) g_nccl.handle = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
   if (!g_nccl.handle) { g_nccl.why = std::string("cannot load libnccl.so.2 (set OPZ_NCCL_LIB): ") + (dlerror() ? dlerror() : "?"); return; }
 #define OPZ_SYM(field, name)                                                        \
   g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.handle, name)); \
