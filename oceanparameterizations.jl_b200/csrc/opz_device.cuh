@@ -270,6 +270,71 @@ struct NoFlux {
   __device__ __forceinline__ void operator()(int, int, float) const {}
 };
 
+// ---- the same right-hand side, one interior face at a time ---------------------------------------------------------
+// face_flux: total flux (NN + diffusive) on interior face f (1 <= f < Nz), from scratch — the expressions, and their order, of the
+// face loop of column_rhs, so that a column split over several threads gives bit-identical tendencies.
+template <bool SMOOTH = true, bool FAST = false, class XF, class YF>
+__device__ __forceinline__ void face_flux(const DevParams& P, int Nz, XF X, YF Y, int f, float& F_u, float& F_v, float& F_T) {
+  const bool mpp = P.flags & OPZ_FLAG_MPP;
+  const bool smooth_nn = SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_NN);
+  const bool smooth_ri = SMOOTH && (P.flags & OPZ_FLAG_SMOOTH_RI);
+  const float u_lo = X(f - 1), v_lo = X(Nz + f - 1), T_lo = X(2 * Nz + f - 1);
+  const float u_hi = X(f), v_hi = X(Nz + f), T_hi = X(2 * Nz + f);
+  const int j = f - 1;
+  float yu = Y(0, j), yv = Y(1, j), yT = Y(2, j);
+  if (smooth_nn) {
+    const int n = Nz - 1;
+    if (j == 0) { yu = (yu + Y(0, 1)) * 0.5f; yv = (yv + Y(1, 1)) * 0.5f; yT = (yT + Y(2, 1)) * 0.5f; }
+    else if (j == n - 1) { yu = (Y(0, j - 1) + yu) * 0.5f; yv = (Y(1, j - 1) + yv) * 0.5f; yT = (Y(2, j - 1) + yT) * 0.5f; }
+    else {
+      const float third = 1.0f / 3.0f;
+      yu = (Y(0, j - 1) + yu + Y(0, j + 1)) * third;
+      yv = (Y(1, j - 1) + yv + Y(1, j + 1)) * third;
+      yT = (Y(2, j - 1) + yT + Y(2, j + 1)) * third;
+    }
+  }
+  F_u = yu; F_v = yv; F_T = yT;
+  if (mpp) {
+    const float gu = (u_hi - u_lo) * P.nzf;
+    const float gv = (v_hi - v_lo) * P.nzf;
+    const float gT = (T_hi - T_lo) * P.nzf;
+    float Ri;
+    if (smooth_ri) {
+      const float Ri_c = richardson(P, gu, gv, gT);
+      const float Ri_m = f - 1 >= 1 ? richardson(P, (u_lo - X(f - 2)) * P.nzf, (v_lo - X(Nz + f - 2)) * P.nzf, (T_lo - X(2 * Nz + f - 2)) * P.nzf)
+                                    : richardson(P, 0.f, 0.f, 0.f);
+      const float Ri_p = f + 1 < Nz ? richardson(P, (X(f + 1) - u_hi) * P.nzf, (X(Nz + f + 1) - v_hi) * P.nzf, (X(2 * Nz + f + 1) - T_hi) * P.nzf)
+                                    : richardson(P, 0.f, 0.f, 0.f);
+      Ri = (Ri_m + Ri_c + Ri_p) * (1.0f / 3.0f);
+    } else {
+      Ri = richardson<FAST>(P, gu, gv, gT);
+    }
+    const float nu = nu_of_ri<FAST>(P, Ri);
+    const float nuT = nuT_of<FAST>(P, nu, gu, gT);
+    F_u -= P.c_u * nu * gu;
+    F_v -= P.c_v * nu * gv;
+    F_T -= P.c_T * nuT * gT;
+  }
+}
+// tendencies of cells [c_begin, c_end) of one column (cell c lies between faces c and c + 1)
+template <bool SMOOTH = true, bool FAST = false, class XF, class YF, class KF>
+__device__ __forceinline__ void column_rhs_range(const DevParams& P, const float* bc, float t, XF X, YF Y, KF K, int c_begin, int c_end) {
+  const int Nz = P.nz;
+  float Fp_u, Fp_v, Fp_T;
+  if (c_begin == 0) { Fp_u = bc[0] - P.off[0]; Fp_v = bc[2] - P.off[1]; Fp_T = bc[4] - P.off[2]; }
+  else face_flux<SMOOTH, FAST>(P, Nz, X, Y, c_begin, Fp_u, Fp_v, Fp_T);
+  for (int c = c_begin; c < c_end; ++c) {
+    const int f = c + 1;
+    float F_u, F_v, F_T;
+    if (f < Nz) face_flux<SMOOTH, FAST>(P, Nz, X, Y, f, F_u, F_v, F_T);
+    else { F_u = bc[1] - P.off[0]; F_v = bc[3] - P.off[1]; F_T = wT_top_value(P, bc, t); }
+    K(c,          P.A_u * ((F_u - Fp_u) * P.nzf) + P.cor_u * (P.s_v * X(Nz + c) + P.mu_v));
+    K(Nz + c,     P.A_v * ((F_v - Fp_v) * P.nzf) - P.cor_v * (P.s_u * X(c) + P.mu_u));
+    K(2 * Nz + c, P.A_T * ((F_T - Fp_T) * P.nzf));
+    Fp_u = F_u; Fp_v = F_v; Fp_T = F_T;
+  }
+}
+
 // ---- model description on the device --------------------------------------------------------
 struct NetDesc {
   int n_layers;               // Dense layers

@@ -61,6 +61,7 @@ struct LayerArgs {
   int mode;
   int fp16;
   int stages;                 // pipeline depth
+  int n_nets;                 // nets in this launch (3, or 1 for predict())
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool fp16) { return fp16 ? ptx::pack_f16x2(a, b) : ptx::pack_bf16x2(a, b); }
@@ -72,8 +73,13 @@ __device__ __forceinline__ float2 unpack2(uint32_t p, bool fp16) {
 __global__ void __launch_bounds__(kThreads) layer_gemm_kernel(const __grid_constant__ LayerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t tile = blockIdx.x;
-  const int pass = blockIdx.y, net = blockIdx.z;
+  // (pass, net)-major block order: the CTAs that read the same activation tile — its n_pass passes, and for the first layer
+  // the three nets, which share the state image — are scheduled together, so the tile comes from L2 instead of being fetched
+  // from DRAM once per pass
+  const int per_tile = a.n_pass * a.n_nets;
+  const int64_t tile = blockIdx.x / per_tile;
+  const int sub = (int)(blockIdx.x - tile * per_tile);
+  const int pass = sub % a.n_pass, net = sub / a.n_pass;
   const int rows = min(kNT, a.n_pad - pass * kNT);          // outputs of this pass (multiple of kKB)
   const int n_parts_a = a.mode == MODE_X3 ? 2 : 1, n_parts_w = a.mode == MODE_PLAIN ? 1 : 2;
   const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
@@ -221,7 +227,11 @@ __global__ void pack_state_kernel(const float* __restrict__ xs, int64_t ld, int 
   if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
-// ---- physics + Runge-Kutta bookkeeping: one thread per ocean column, state feature-major [i][column] in HBM ----
+// ---- physics + Runge-Kutta bookkeeping: one thread per (ocean column, chunk of kPhysCells cells), state feature-major [i][column]
+//      in HBM.  A whole column per thread left an ensemble of 65 536 columns of Nz = 128 with 14 warps per SM, each walking 128
+//      faces of dependent loads; split by cells the faces are independent (opz_device.cuh::column_rhs_range: the same expressions
+//      per face, bit-identical tendencies). ----
+constexpr int kPhysCells = 16;
 struct PhysArgs {
   DevParams P;
   const float* bc;    // [B][8]
@@ -239,6 +249,7 @@ __global__ void __launch_bounds__(128) physics_rk_kernel(const __grid_constant__
   if (c >= a.B) return;
   const DevParams& P = a.P;
   const int nz = P.nz, nout = nz - 1;
+  const int cell0 = (int)blockIdx.y * kPhysCells, cell1 = min(nz, cell0 + kPhysCells);
   float bc[OPZ_BC_STRIDE];
 #pragma unroll
   for (int q = 0; q < OPZ_BC_STRIDE; ++q) bc[q] = a.bc[(a.col0 + c) * OPZ_BC_STRIDE + q];
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(128) physics_rk_kernel(const __grid_constant__
       const float xv = xo + h * k; a.xn[o] = xv; a.xout[o] = xv;
     }
   };
-  column_rhs(P, bc, a.ts, X, Y, K, NoFlux());
+  column_rhs_range(P, bc, a.ts, X, Y, K, cell0, cell1);
 }
 
 // x0[B][S3] (row per column) <-> feature-major [S3][ld]
@@ -498,7 +509,8 @@ static int run_layers(opz_ctx* ctx, const opz_model* m, const Plan& pl, const Wo
       if (!last) { a.o_hi += (size_t)only * a.o_net; if (a.o_lo) a.o_lo += (size_t)only * a.o_net; }
       else a.y += (size_t)only * a.n_out * ld;
     }
-    dim3 grid((unsigned)tiles, (unsigned)a.n_pass, only >= 0 ? 1u : 3u);
+    a.n_nets = only >= 0 ? 1 : 3;
+    dim3 grid((unsigned)(tiles * a.n_pass * a.n_nets));
     layer_gemm_kernel<<<grid, kThreads, smem, ctx->stream>>>(a);
     OPZ_CUDA(cudaGetLastError());
     ctx->launches += 1;
@@ -551,7 +563,7 @@ int gemm_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int pre
         PhysArgs pa{};
         pa.P = c.P; pa.bc = c.bc; pa.y = w.y; pa.xn = w.xn; pa.kacc = w.kacc; pa.xin = w.xs[cur]; pa.xout = w.xs[cur ^ 1];
         pa.B = nb; pa.ld = C; pa.col0 = c0; pa.scheme = c.scheme; pa.stage = sg; pa.h = c.dt; pa.ts = ts;
-        physics_rk_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(pa);
+        physics_rk_kernel<<<dim3((unsigned)((nb + 127) / 128), (unsigned)((nz + kPhysCells - 1) / kPhysCells)), 128, 0, st>>>(pa);
         ctx->launches += 1;
         cur ^= 1;
       }
