@@ -1,21 +1,23 @@
-// opz_tc2.cu — second-generation tcgen05 / TMEM rollout kernel: CTA pairs, chunk-sized weight stages,
-// eight (or sixteen) epilogue warps and level-parallel physics.
+// opz_tc2.cu — the fused persistent tcgen05 / TMEM rollout kernel: CTA pairs, chunk-sized weight stages, a host-built schedule
+// table, eight epilogue warps and level-parallel physics.
 //
-// What changed against opz_tc.cu (kept as the OPZ_TC_V1=1 fallback and as the measured baseline):
-//   * the wait profile of v1 showed the single MMA-issuing warp as the limiter: ~570 cycles of bookkeeping per
-//     6-MMA weight stage (147 stages per right-hand side) against 192 cycles of tensor work.  Here a weight stage
-//     is a WHOLE accumulator chunk (up to 25 k-steps + the 4 output-layer k-steps of the previous fused chunk),
-//     43 stages per right-hand side, each issued from one unrolled, immediate-offset sequence;
+// Shape of the kernel (what the first-generation kernel of round 1 taught; that kernel is gone):
+//   * a single MMA-issuing warp spending ~570 cycles of bookkeeping per 6-MMA weight stage was the limiter.  Here a weight stage
+//     is a WHOLE accumulator chunk (up to 25 k-steps + the 4 output-layer k-steps of the fused chunk two stages back),
+//     43 stages per right-hand side, each issued from one unrolled, immediate-offset sequence by one of two issuing warps;
 //   * that needs 27.6 KB per stage, which only fits because the kernel always runs as a CTA PAIR
 //     (tcgen05 cta_group::2, M = 256): each CTA stages HALF of every weight block and the hardware shares the
 //     halves, so L2 -> SM weight traffic per SM halves too.  The ring is a byte FIFO (host-computed offsets and
 //     "stages that may stay in flight" per stage) rather than fixed slots;
+//   * the schedule of a right-hand side is the same every time: build_plan() lays it out once as a table of ChunkRec records
+//     (kernel parameters), and issuers and epilogue walk that table — everything that does not depend on a barrier is computed
+//     before the waits, so a hand-over costs the barrier, a fence and the tcgen05 instructions themselves;
 //   * 8 epilogue warps (two per TMEM lane quadrant, 32 accumulator columns each) instead of 4 halve the drain
 //     latency per chunk, and the physics runs LEVEL-PARALLEL: two threads per ocean column, 16 cells each, with
 //     the NN-independent part (gradients, Ri, diffusivities, Coriolis) evaluated BEFORE the last output-layer
 //     MMAs have landed;
-//   * hidden-layer biases are read through L1 (prefetched before the accumulator barrier) — the shared memory
-//     they used to occupy now belongs to the weight ring.
+//   * hidden-layer biases ride in the weight tape as one extra k-step against a constant-one operand: the drain has no bias
+//     loads or adds.
 //
 // The physics evaluates the same FP32 expressions per face as opz_device.cuh::column_rhs<FAST>.
 //
