@@ -37,7 +37,9 @@ constexpr int kKB = 32;                    // features per operand block (two k-
                                            // CTAs share an SM and one's epilogue overlaps the other's MMAs; widths pad to 32
 constexpr int kNT = 256;                   // outputs per pass
 constexpr int kABytes = kM * kKB * 2;      // 8 KB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;   // producer, MMA issuer, epilogue warps
+constexpr int kMaxStages = 8;
 
 enum { MODE_PLAIN = 0, MODE_X2 = 1, MODE_X3 = 2 };
 
@@ -62,6 +64,8 @@ struct LayerArgs {
   int fp16;
   int stages;                 // pipeline depth
   int n_nets;                 // nets in this launch (3, or 1 for predict())
+  int64_t tiles;              // 128-column tiles
+  uint32_t stage_stride;      // bytes per ring slot (a stage of a full 256-row pass)
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool fp16) { return fp16 ? ptx::pack_f16x2(a, b) : ptx::pack_bf16x2(a, b); }
@@ -70,139 +74,172 @@ __device__ __forceinline__ float2 unpack2(uint32_t p, bool fp16) {
   return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xFFFF0000u));
 }
 
-__global__ void __launch_bounds__(kThreads) layer_gemm_kernel(const __grid_constant__ LayerArgs a) {
+// Persistent: one CTA per SM walks the work items (tile x pass x net, (pass, net)-major so that the CTAs running at the same time
+// share activation tiles in L2) with the operand ring and the barriers carried across items, and TWO accumulators of 256
+// tensor-memory columns: the eight epilogue warps drain item i while the issuing warp is already in the k-loop of item i + 1.
+// (One CTA per item paid barrier / tensor-memory set-up and an exposed epilogue per item: the 384-deep first layer of configs[4]
+// ran at 534 TFLOP/s against 900 for the 1024-deep one.)
+__global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_constant__ LayerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  // (pass, net)-major block order: the CTAs that read the same activation tile — its n_pass passes, and for the first layer
-  // the three nets, which share the state image — are scheduled together, so the tile comes from L2 instead of being fetched
-  // from DRAM once per pass
-  const int per_tile = a.n_pass * a.n_nets;
-  const int64_t tile = blockIdx.x / per_tile;
-  const int sub = (int)(blockIdx.x - tile * per_tile);
-  const int pass = sub % a.n_pass, net = sub / a.n_pass;
-  const int rows = min(kNT, a.n_pad - pass * kNT);          // outputs of this pass (multiple of kKB)
   const int n_parts_a = a.mode == MODE_X3 ? 2 : 1, n_parts_w = a.mode == MODE_PLAIN ? 1 : 2;
-  const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
-  const uint32_t stage_bytes = n_parts_a * kABytes + n_parts_w * w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);        // full[S], empty[S], dfull
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * 8 + 1));
+  enum { B_FULL = 0, B_EMPTY = kMaxStages, B_DFULL = 2 * kMaxStages, B_DEMPTY = 2 * kMaxStages + 2, B_N = 2 * kMaxStages + 4 };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * B_N);
   uint8_t* ring = smem + 256;
   const int S = a.stages;
+  const int per_tile = a.n_pass * a.n_nets;
+  const int64_t n_items = a.tiles * per_tile;
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { ptx::mbar_init(bars + s, 1); ptx::mbar_init(bars + 8 + s, 1); }
-      ptx::mbar_init(bars + 16, 1);
+      for (int s = 0; s < S; ++s) { ptx::mbar_init(bars + B_FULL + s, 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(bars + B_DFULL + b, 1); ptx::mbar_init(bars + B_DEMPTY + b, kEpiWarps); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<kNT>(tmem_slot);
+    ptx::tmem_alloc<2 * kNT>(tmem_slot);
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // weight blocks of (net, pass): the passes before this one hold 256 rows each
-  const size_t w_off = (size_t)net * a.w_net + (size_t)pass * kNT * kKB * a.kb_in;
+  // item -> (tile, pass, net, rows)
+  auto decode = [&](int64_t it, int64_t& tile, int& pass, int& net, int& rows) {
+    tile = it / per_tile;
+    const int sub = (int)(it - tile * per_tile);
+    pass = sub % a.n_pass;
+    net = sub / a.n_pass;
+    rows = min(kNT, a.n_pad - pass * kNT);   // outputs of this pass (multiple of kKB)
+  };
 
   if (warp == 0) {
+    // ================= operand producer =================
     if (lane == 0) {
-      for (int kb = 0; kb < a.kb_in; ++kb) {
-        const int s = kb % S;
-        if (kb >= S) ptx::mbar_wait(bars + 8 + s, ((kb / S) - 1) & 1u);
-        uint8_t* dst = ring + (size_t)s * stage_bytes;
-        ptx::mbar_arrive_expect_tx(bars + s, stage_bytes);
-        const size_t a_off = (size_t)net * a.a_net + ((size_t)tile * a.kb_in + kb) * (kM * kKB);
-        ptx::bulk_g2s(dst, a.a_hi + a_off, kABytes, bars + s);
-        dst += kABytes;
-        if (n_parts_a == 2) { ptx::bulk_g2s(dst, a.a_lo + a_off, kABytes, bars + s); dst += kABytes; }
-        const size_t wo = w_off + (size_t)kb * rows * kKB;
-        ptx::bulk_g2s(dst, a.w_hi + wo, w_bytes, bars + s);
-        dst += w_bytes;
-        if (n_parts_w == 2) ptx::bulk_g2s(dst, a.w_lo + wo, w_bytes, bars + s);
+      uint32_t gs = 0;   // stages issued so far (all items)
+      for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        int64_t tile; int pass, net, rows;
+        decode(it, tile, pass, net, rows);
+        const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
+        const uint32_t stage_bytes = n_parts_a * kABytes + n_parts_w * w_bytes;
+        const size_t w_off = (size_t)net * a.w_net + (size_t)pass * kNT * kKB * a.kb_in;   // the passes before this one hold 256 rows each
+        for (int kb = 0; kb < a.kb_in; ++kb, ++gs) {
+          const uint32_t s = gs % (uint32_t)S;
+          if (gs >= (uint32_t)S) ptx::mbar_wait(bars + B_EMPTY + s, ((gs / (uint32_t)S) - 1u) & 1u);
+          uint8_t* dst = ring + (size_t)s * a.stage_stride;
+          ptx::mbar_arrive_expect_tx(bars + B_FULL + s, stage_bytes);
+          const size_t a_off = (size_t)net * a.a_net + ((size_t)tile * a.kb_in + kb) * (kM * kKB);
+          ptx::bulk_g2s(dst, a.a_hi + a_off, kABytes, bars + B_FULL + s);
+          dst += kABytes;
+          if (n_parts_a == 2) { ptx::bulk_g2s(dst, a.a_lo + a_off, kABytes, bars + B_FULL + s); dst += kABytes; }
+          const size_t wo = w_off + (size_t)kb * rows * kKB;
+          ptx::bulk_g2s(dst, a.w_hi + wo, w_bytes, bars + B_FULL + s);
+          dst += w_bytes;
+          if (n_parts_w == 2) ptx::bulk_g2s(dst, a.w_lo + wo, w_bytes, bars + B_FULL + s);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    const uint32_t idesc = ptx::idesc_f16kind(kM, rows, a.fp16 != 0);
+    // ================= MMA issuer =================
     const uint32_t ring_u32 = ptx::smem_u32(ring);
-    for (int kb = 0; kb < a.kb_in; ++kb) {
-      const int s = kb % S;
-      ptx::mbar_wait(bars + s, (kb / S) & 1u);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t base = ring_u32 + (uint32_t)s * stage_bytes;
-        const uint32_t a_hi = base, a_lo = base + kABytes;
-        const uint32_t w_hi = base + n_parts_a * kABytes, w_lo = w_hi + w_bytes;
-        const int nks = min(kKB / 16, (a.k_in - kb * kKB + 15) / 16);   // k-steps that hold real features
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t ad = ptx::smem_desc(a_hi + ks * (2 * kM * 16), kM * 16, 128);
-          const uint64_t bd = ptx::smem_desc(w_hi + ks * (2 * rows * 16), rows * 16, 128);
-          ptx::mma_ss(tmem, ad, bd, idesc, kb > 0 || ks > 0);
-          if (a.mode != MODE_PLAIN) {
-            const uint64_t bl = ptx::smem_desc(w_lo + ks * (2 * rows * 16), rows * 16, 128);
-            ptx::mma_ss(tmem, ad, bl, idesc, true);
-            if (a.mode == MODE_X3) {
-              const uint64_t al = ptx::smem_desc(a_lo + ks * (2 * kM * 16), kM * 16, 128);
-              ptx::mma_ss(tmem, al, bd, idesc, true);
+    uint32_t gs = 0, li = 0;   // stages / items so far
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+      int64_t tile; int pass, net, rows;
+      decode(it, tile, pass, net, rows);
+      const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
+      const uint32_t idesc = ptx::idesc_f16kind(kM, rows, a.fp16 != 0);
+      const uint32_t buf = li & 1u;
+      const uint32_t d = tmem + buf * (uint32_t)kNT;
+      if (li >= 2u) ptx::mbar_wait(bars + B_DEMPTY + buf, ((li >> 1) - 1u) & 1u);   // the epilogue has drained item li - 2
+      for (int kb = 0; kb < a.kb_in; ++kb, ++gs) {
+        const uint32_t s = gs % (uint32_t)S;
+        ptx::mbar_wait(bars + B_FULL + s, (gs / (uint32_t)S) & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t base = ring_u32 + s * a.stage_stride;
+          const uint32_t a_hi = base, a_lo = base + kABytes;
+          const uint32_t w_hi = base + n_parts_a * kABytes, w_lo = w_hi + w_bytes;
+          const int nks = min(kKB / 16, (a.k_in - kb * kKB + 15) / 16);   // k-steps that hold real features
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t ad = ptx::smem_desc(a_hi + ks * (2 * kM * 16), kM * 16, 128);
+            const uint64_t bd = ptx::smem_desc(w_hi + ks * (2 * rows * 16), rows * 16, 128);
+            ptx::mma_ss(d, ad, bd, idesc, kb > 0 || ks > 0);
+            if (a.mode != MODE_PLAIN) {
+              const uint64_t bl = ptx::smem_desc(w_lo + ks * (2 * rows * 16), rows * 16, 128);
+              ptx::mma_ss(d, ad, bl, idesc, true);
+              if (a.mode == MODE_X3) {
+                const uint64_t al = ptx::smem_desc(a_lo + ks * (2 * kM * 16), kM * 16, 128);
+                ptx::mma_ss(d, al, bd, idesc, true);
+              }
             }
           }
+          ptx::tc_commit(bars + B_EMPTY + s);
+          if (kb == a.kb_in - 1) ptx::tc_commit(bars + B_DFULL + buf);
         }
-        ptx::tc_commit(bars + 8 + s);
-        if (kb == a.kb_in - 1) ptx::tc_commit(bars + 16);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ---- epilogue: this thread owns ocean column r of the tile (tensor-memory lane r) ----
-    const int q = warp % 4, r = q * 32 + lane;
+    // ================= epilogue: this thread owns ocean column r of the tile (tensor-memory lane r); the two warps of a lane
+    //                   quadrant take alternate groups of 32 accumulator columns =================
+    const int q = warp % 4, r = q * 32 + lane, half = (warp - 2) / 4;
     const bool fp16 = a.fp16 != 0;
-    ptx::mbar_wait(bars + 16, 0);
-    ptx::tc_fence_after();
-    const float* bias = a.bias + (size_t)net * a.n_pad + pass * kNT;
-    for (int c0 = 0; c0 < rows; c0 += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      ptx::tmem_wait_ld();
-      if (a.y) {   // last layer: FP32 outputs, feature-major (coalesced over the ocean columns)
+    uint32_t li = 0;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+      int64_t tile; int pass, net, rows;
+      decode(it, tile, pass, net, rows);
+      const uint32_t buf = li & 1u;
+      ptx::mbar_wait(bars + B_DFULL + buf, (li >> 1) & 1u);
+      ptx::tc_fence_after();
+      const float* bias = a.bias + (size_t)net * a.n_pad + pass * kNT;
+      for (int c0 = half * 32; c0 < rows; c0 += 64) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kNT + (uint32_t)c0, v);
+        ptx::tmem_wait_ld();
+        if (a.y) {   // last layer: FP32 outputs, feature-major (coalesced over the ocean columns)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = pass * kNT + c0 + j;
-          if (n < a.n_out) a.y[((size_t)net * a.n_out + n) * a.ldy + tile * kM + r] = __uint_as_float(v[j]) + bias[c0 + j];
-        }
-      } else {
-        float z[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) + bias[c0 + j];
-        switch (a.act) {   // one dispatch per 32 values, not per value
-#define OPZ_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < 32; ++j) z[j] = act_fn<A>(z[j]); break;
-          OPZ_ACT_CASE(OPZ_ACT_RELU) OPZ_ACT_CASE(OPZ_ACT_TANH) OPZ_ACT_CASE(OPZ_ACT_MISH) OPZ_ACT_CASE(OPZ_ACT_SWISH) OPZ_ACT_CASE(OPZ_ACT_LEAKYRELU)
-#undef OPZ_ACT_CASE
-          default: break;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {   // groups of 8 features = one 16-byte chunk of the image
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = g * 8 + 2 * e;
-            const float z0 = z[j], z1 = z[j + 1];
-            hi[e] = pack2(z0, z1, fp16);
-            if (a.mode == MODE_X3) {
-              const float2 h = unpack2(hi[e], fp16);
-              lo[e] = pack2(z0 - h.x, z1 - h.y, fp16);
-            }
+          for (int j = 0; j < 32; ++j) {
+            const int n = pass * kNT + c0 + j;
+            if (n < a.n_out) a.y[((size_t)net * a.n_out + n) * a.ldy + tile * kM + r] = __uint_as_float(v[j]) + bias[c0 + j];
           }
-          const int n = pass * kNT + c0 + g * 8;            // first feature of the chunk
-          const size_t o = (size_t)net * a.o_net + ((size_t)tile * (a.n_pad / kKB) + n / kKB) * (kM * kKB) + ((size_t)((n % kKB) / 8) * kM + r) * 8;
-          *reinterpret_cast<uint4*>(a.o_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (a.mode == MODE_X3) *reinterpret_cast<uint4*>(a.o_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else {
+          float z[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) + bias[c0 + j];
+          switch (a.act) {   // one dispatch per 32 values, not per value
+#define OPZ_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < 32; ++j) z[j] = act_fn<A>(z[j]); break;
+            OPZ_ACT_CASE(OPZ_ACT_RELU) OPZ_ACT_CASE(OPZ_ACT_TANH) OPZ_ACT_CASE(OPZ_ACT_MISH) OPZ_ACT_CASE(OPZ_ACT_SWISH) OPZ_ACT_CASE(OPZ_ACT_LEAKYRELU)
+#undef OPZ_ACT_CASE
+            default: break;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {   // groups of 8 features = one 16-byte chunk of the image
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = g * 8 + 2 * e;
+              const float z0 = z[j], z1 = z[j + 1];
+              hi[e] = pack2(z0, z1, fp16);
+              if (a.mode == MODE_X3) {
+                const float2 h = unpack2(hi[e], fp16);
+                lo[e] = pack2(z0 - h.x, z1 - h.y, fp16);
+              }
+            }
+            const int n = pass * kNT + c0 + g * 8;            // first feature of the chunk
+            const size_t o = (size_t)net * a.o_net + ((size_t)tile * (a.n_pad / kKB) + n / kKB) * (kM * kKB) + ((size_t)((n % kKB) / 8) * kM + r) * 8;
+            *reinterpret_cast<uint4*>(a.o_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (a.mode == MODE_X3) *reinterpret_cast<uint4*>(a.o_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       }
+      ptx::tc_fence_before();   // this warp's tcgen05.ld of the accumulator are complete (wait::ld above)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bars + B_DEMPTY + buf);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<kNT>(tmem);
+  if (warp == 1) ptx::tmem_dealloc<2 * kNT>(tmem);
 }
 
 // ---- state image: FP32 stage state xs[i][column] -> 16-bit operand image [tile][k-block] (hi [, lo]) ----
@@ -462,11 +499,11 @@ static size_t carve(const Plan& pl, const NetDesc& nd, int nz, int64_t C, uint8_
   return off;
 }
 
-static size_t layer_smem(const Plan& pl, int l, int stages) {
+static size_t layer_stage(const Plan& pl, int l) {
   const int rows = std::min(kNT, pl.n_pad[l]);
-  const size_t stage = (pl.mode == MODE_X3 ? 2 : 1) * (size_t)kABytes + (pl.mode == MODE_PLAIN ? 1 : 2) * (size_t)rows * kKB * 2;
-  return 256 + stage * stages;
+  return (pl.mode == MODE_X3 ? 2 : 1) * (size_t)kABytes + (pl.mode == MODE_PLAIN ? 1 : 2) * (size_t)rows * kKB * 2;
 }
+static size_t layer_smem(const Plan& pl, int l, int stages) { return 256 + layer_stage(pl, l) * stages; }
 
 // one MLP evaluation of the three nets (or of net `only`, if >= 0) on the state image of `tiles` tiles
 static int run_layers(opz_ctx* ctx, const opz_model* m, const Plan& pl, const Work& w, int64_t tiles, int64_t ld, int only) {
@@ -494,11 +531,15 @@ static int run_layers(opz_ctx* ctx, const opz_model* m, const Plan& pl, const Wo
     a.act = last ? OPZ_ACT_IDENTITY : nd.act;
     a.mode = pl.mode;
     a.fp16 = pl.fp16 ? 1 : 0;
-    int stages = 4;
-    while (stages > 2 && layer_smem(pl, l, stages) > (size_t)110 * 1024) --stages;   // two CTAs per SM when two stages allow it
+    int stages = kMaxStages;   // one persistent CTA per SM: as deep a ring as shared memory holds
+    // as deep as fits under the 164 KB shared-memory carve-out: the next one (228 KB) leaves 28 KB of L1 for the epilogue's bias
+    // reads and measured erratic (configs[4] FP16X3: 216 - 283 TFLOP/s with 4 stages of 48 KB against 350 with 3)
+    while (stages > 2 && layer_smem(pl, l, stages) > (size_t)160 * 1024) --stages;
     while (stages > 1 && layer_smem(pl, l, stages) > (size_t)ctx->smem_optin) --stages;
     if (layer_smem(pl, l, stages) > (size_t)ctx->smem_optin) { set_error("layered tensor path: operand stage exceeds shared memory"); return OPZ_EUNSUP; }
-    a.stages = std::min(stages, std::max(1, a.kb_in));
+    a.stages = stages;
+    a.stage_stride = (uint32_t)layer_stage(pl, l);
+    a.tiles = tiles;
     const size_t smem = layer_smem(pl, l, a.stages);
     OPZ_CUDA(cudaFuncSetAttribute(layer_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (only >= 0) {   // a single net: shift the per-net bases
@@ -510,7 +551,7 @@ static int run_layers(opz_ctx* ctx, const opz_model* m, const Plan& pl, const Wo
       else a.y += (size_t)only * a.n_out * ld;
     }
     a.n_nets = only >= 0 ? 1 : 3;
-    dim3 grid((unsigned)(tiles * a.n_pass * a.n_nets));
+    dim3 grid((unsigned)std::min<int64_t>(tiles * a.n_pass * a.n_nets, ctx->sm_count));
     layer_gemm_kernel<<<grid, kThreads, smem, ctx->stream>>>(a);
     OPZ_CUDA(cudaGetLastError());
     ctx->launches += 1;

@@ -22,7 +22,7 @@ ctx.set_stream(stream.cuda_stream)
 cols = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 16
 
 
-def run(name, model, pp, x0, bc, prec, dt, steps=3, warm=1, flop_rhs=0):
+def run(name, model, pp, x0, bc, prec, dt, steps=10, warm=3, flop_rhs=0):
     xa = torch.from_numpy(x0).cuda()
     xb = torch.empty_like(xa)
     bcd = torch.from_numpy(bc).cuda()
