@@ -37,9 +37,13 @@ constexpr int kKB = 32;                    // features per operand block (two k-
                                            // CTAs share an SM and one's epilogue overlaps the other's MMAs; widths pad to 32
 constexpr int kNT = 256;                   // outputs per pass
 constexpr int kABytes = kM * kKB * 2;      // 8 KB
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (2 + kEpiWarps) * 32;   // producer, MMA issuer, epilogue warps
 constexpr int kMaxStages = 8;
+// Two shapes of the persistent pair kernel (template parameters kAcc, kEpiWarps):
+//   <1, 4>  one 256-column accumulator, four epilogue warps, TWO CTAs per SM: one's epilogue overlaps the other's MMAs, and two
+//           producers per SM pull operands — the plain 16-bit modes are bound by operand bytes (configs[4]: 577 against 504
+//           algorithmic TFLOP/s for the other shape);
+//   <2, 8>  two accumulators, eight epilogue warps, ONE CTA per SM: the epilogue of item i overlaps the k-loop of item i + 1 —
+//           the three-MMA split modes do three times the tensor work per byte and gain from the deeper overlap (369 against 337).
 
 enum { MODE_PLAIN = 0, MODE_X2 = 1, MODE_X3 = 2 };
 
@@ -74,12 +78,14 @@ __device__ __forceinline__ float2 unpack2(uint32_t p, bool fp16) {
   return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xFFFF0000u));
 }
 
-// Persistent: one CTA per SM walks the work items (tile x pass x net, (pass, net)-major so that the CTAs running at the same time
-// share activation tiles in L2) with the operand ring and the barriers carried across items, and TWO accumulators of 256
-// tensor-memory columns: the eight epilogue warps drain item i while the issuing warp is already in the k-loop of item i + 1.
-// (One CTA per item paid barrier / tensor-memory set-up and an exposed epilogue per item: the 384-deep first layer of configs[4]
-// ran at 534 TFLOP/s against 900 for the 1024-deep one.)
-__global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_constant__ LayerArgs a) {
+// Persistent CTA PAIRS (tcgen05 cta_group::2, M = 256): one pair per two SMs walks the work items (tile pair x pass x net,
+// (pass, net)-major so that the pairs running at the same time share activation tiles in L2) with the operand ring and the
+// barriers carried across items, and TWO accumulators of 256 tensor-memory columns per CTA: the eight epilogue warps drain item i
+// while the issuing warp is already in the k-loop of item i + 1.  Each CTA stages its own activation tile and HALF of every
+// weight block — the GEMM is bound by L2 -> SM bytes (24 KB per 256 tensor cycles and CTA with whole weight blocks: 27 B/clk/SM
+// measured, a third of what the tensor pipe would take), and the pair moves 16 KB for the same MMAs.
+template <int kAcc, int kEpiWarps>
+__global__ void __launch_bounds__((2 + kEpiWarps) * 32, kAcc == 1 ? 2 : 1) layer_gemm_kernel(const __grid_constant__ LayerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n_parts_a = a.mode == MODE_X3 ? 2 : 1, n_parts_w = a.mode == MODE_PLAIN ? 1 : 2;
@@ -89,37 +95,41 @@ __global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_co
   uint8_t* ring = smem + 256;
   const int S = a.stages;
   const int per_tile = a.n_pass * a.n_nets;
-  const int64_t n_items = a.tiles * per_tile;
+  const int64_t n_items = (a.tiles / 2) * per_tile;           // a.tiles is even (the last tile may be padding: zero image, never read back)
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int64_t item0 = blockIdx.x / 2, item_stride = gridDim.x / 2;
+  const uint32_t leader_bars = ptx::mapa(ptx::smem_u32(bars), 0u);
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { ptx::mbar_init(bars + B_FULL + s, 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
-      for (int b = 0; b < 2; ++b) { ptx::mbar_init(bars + B_DFULL + b, 1); ptx::mbar_init(bars + B_DEMPTY + b, kEpiWarps); }
+      for (int s = 0; s < S; ++s) { ptx::mbar_init(bars + B_FULL + s, rank == 0 ? 2 : 1); ptx::mbar_init(bars + B_EMPTY + s, 1); }
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(bars + B_DFULL + b, 1); ptx::mbar_init(bars + B_DEMPTY + b, 2 * kEpiWarps); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<2 * kNT>(tmem_slot);
+    ptx::tmem_alloc2<kAcc * kNT>(tmem_slot);
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync();   // both CTAs' barriers exist before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // item -> (tile, pass, net, rows)
+  // item -> (tile of THIS CTA, pass, net, rows)
   auto decode = [&](int64_t it, int64_t& tile, int& pass, int& net, int& rows) {
-    tile = it / per_tile;
-    const int sub = (int)(it - tile * per_tile);
+    const int64_t pair = it / per_tile;
+    const int sub = (int)(it - pair * per_tile);
+    tile = 2 * pair + rank;
     pass = sub % a.n_pass;
     net = sub / a.n_pass;
     rows = min(kNT, a.n_pad - pass * kNT);   // outputs of this pass (multiple of kKB)
   };
 
   if (warp == 0) {
-    // ================= operand producer =================
+    // ================= operand producer (each CTA: its tile, its half of the weight block) =================
     if (lane == 0) {
       uint32_t gs = 0;   // stages issued so far (all items)
-      for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      for (int64_t it = item0; it < n_items; it += item_stride) {
         int64_t tile; int pass, net, rows;
         decode(it, tile, pass, net, rows);
-        const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
+        const uint32_t w_bytes = (uint32_t)(rows / 2) * kKB * 2;
         const uint32_t stage_bytes = n_parts_a * kABytes + n_parts_w * w_bytes;
         const size_t w_off = (size_t)net * a.w_net + (size_t)pass * kNT * kKB * a.kb_in;   // the passes before this one hold 256 rows each
         for (int kb = 0; kb < a.kb_in; ++kb, ++gs) {
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_co
           ptx::bulk_g2s(dst, a.a_hi + a_off, kABytes, bars + B_FULL + s);
           dst += kABytes;
           if (n_parts_a == 2) { ptx::bulk_g2s(dst, a.a_lo + a_off, kABytes, bars + B_FULL + s); dst += kABytes; }
-          const size_t wo = w_off + (size_t)kb * rows * kKB;
+          const size_t wo = w_off + (size_t)kb * rows * kKB + (size_t)rank * (rows / 2) * kKB;   // [k-block][half][(k/8)(rows/2) + row][8]
           ptx::bulk_g2s(dst, a.w_hi + wo, w_bytes, bars + B_FULL + s);
           dst += w_bytes;
           if (n_parts_w == 2) ptx::bulk_g2s(dst, a.w_lo + wo, w_bytes, bars + B_FULL + s);
@@ -139,18 +149,30 @@ __global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_co
       }
     }
     __syncwarp();
+  } else if (warp == 1 && rank != 0) {
+    // ================= peer CTA: forward "my half of the stage has landed" to the leader =================
+    if (lane == 0) {
+      uint32_t gs = 0;
+      for (int64_t it = item0; it < n_items; it += item_stride)
+        for (int kb = 0; kb < a.kb_in; ++kb, ++gs) {
+          const uint32_t s = gs % (uint32_t)S;
+          ptx::mbar_wait(bars + B_FULL + s, (gs / (uint32_t)S) & 1u);
+          ptx::mbar_arrive_remote_relaxed(leader_bars + 8u * (uint32_t)(B_FULL + s));
+        }
+    }
+    __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer (leader CTA) =================
     const uint32_t ring_u32 = ptx::smem_u32(ring);
     uint32_t gs = 0, li = 0;   // stages / items so far
-    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+    for (int64_t it = item0; it < n_items; it += item_stride, ++li) {
       int64_t tile; int pass, net, rows;
       decode(it, tile, pass, net, rows);
-      const uint32_t w_bytes = (uint32_t)rows * kKB * 2;
-      const uint32_t idesc = ptx::idesc_f16kind(kM, rows, a.fp16 != 0);
-      const uint32_t buf = li & 1u;
+      const uint32_t w_bytes = (uint32_t)(rows / 2) * kKB * 2;
+      const uint32_t idesc = ptx::idesc_f16kind(2 * kM, rows, a.fp16 != 0);
+      const uint32_t buf = li % (uint32_t)kAcc;
       const uint32_t d = tmem + buf * (uint32_t)kNT;
-      if (li >= 2u) ptx::mbar_wait(bars + B_DEMPTY + buf, ((li >> 1) - 1u) & 1u);   // the epilogue has drained item li - 2
+      if (li >= (uint32_t)kAcc) ptx::mbar_wait(bars + B_DEMPTY + buf, ((li / (uint32_t)kAcc) - 1u) & 1u);   // both epilogues have drained item li - kAcc
       for (int kb = 0; kb < a.kb_in; ++kb, ++gs) {
         const uint32_t s = gs % (uint32_t)S;
         ptx::mbar_wait(bars + B_FULL + s, (gs / (uint32_t)S) & 1u);
@@ -162,19 +184,19 @@ __global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_co
           const int nks = min(kKB / 16, (a.k_in - kb * kKB + 15) / 16);   // k-steps that hold real features
           for (int ks = 0; ks < nks; ++ks) {
             const uint64_t ad = ptx::smem_desc(a_hi + ks * (2 * kM * 16), kM * 16, 128);
-            const uint64_t bd = ptx::smem_desc(w_hi + ks * (2 * rows * 16), rows * 16, 128);
-            ptx::mma_ss(d, ad, bd, idesc, kb > 0 || ks > 0);
+            const uint64_t bd = ptx::smem_desc(w_hi + ks * (rows * 16), (rows / 2) * 16, 128);   // this CTA's rows / 2 rows
+            ptx::mma_ss2(d, ad, bd, idesc, kb > 0 || ks > 0);
             if (a.mode != MODE_PLAIN) {
-              const uint64_t bl = ptx::smem_desc(w_lo + ks * (2 * rows * 16), rows * 16, 128);
-              ptx::mma_ss(d, ad, bl, idesc, true);
+              const uint64_t bl = ptx::smem_desc(w_lo + ks * (rows * 16), (rows / 2) * 16, 128);
+              ptx::mma_ss2(d, ad, bl, idesc, true);
               if (a.mode == MODE_X3) {
                 const uint64_t al = ptx::smem_desc(a_lo + ks * (2 * kM * 16), kM * 16, 128);
-                ptx::mma_ss(d, al, bd, idesc, true);
+                ptx::mma_ss2(d, al, bd, idesc, true);
               }
             }
           }
-          ptx::tc_commit(bars + B_EMPTY + s);
-          if (kb == a.kb_in - 1) ptx::tc_commit(bars + B_DFULL + buf);
+          ptx::tc_commit2(bars + B_EMPTY + s);
+          if (kb == a.kb_in - 1) ptx::tc_commit2(bars + B_DFULL + buf);
         }
         __syncwarp();
       }
@@ -183,16 +205,17 @@ __global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_co
     // ================= epilogue: this thread owns ocean column r of the tile (tensor-memory lane r); the two warps of a lane
     //                   quadrant take alternate groups of 32 accumulator columns =================
     const int q = warp % 4, r = q * 32 + lane, half = (warp - 2) / 4;
+    constexpr int kColStep = 32 * (kEpiWarps / 4);
     const bool fp16 = a.fp16 != 0;
     uint32_t li = 0;
-    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++li) {
+    for (int64_t it = item0; it < n_items; it += item_stride, ++li) {
       int64_t tile; int pass, net, rows;
       decode(it, tile, pass, net, rows);
-      const uint32_t buf = li & 1u;
-      ptx::mbar_wait(bars + B_DFULL + buf, (li >> 1) & 1u);
+      const uint32_t buf = li % (uint32_t)kAcc;
+      ptx::mbar_wait(bars + B_DFULL + buf, (li / (uint32_t)kAcc) & 1u);
       ptx::tc_fence_after();
       const float* bias = a.bias + (size_t)net * a.n_pad + pass * kNT;
-      for (int c0 = half * 32; c0 < rows; c0 += 64) {
+      for (int c0 = half * 32; c0 < rows; c0 += kColStep) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kNT + (uint32_t)c0, v);
         ptx::tmem_wait_ld();
@@ -234,12 +257,15 @@ __global__ void __launch_bounds__(kThreads, 1) layer_gemm_kernel(const __grid_co
       }
       ptx::tc_fence_before();   // this warp's tcgen05.ld of the accumulator are complete (wait::ld above)
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bars + B_DEMPTY + buf);
+      if (lane == 0) {   // the issuer's barriers live in the leader CTA
+        if (rank != 0) ptx::mbar_arrive_remote_relaxed(leader_bars + 8u * (uint32_t)(B_DEMPTY + buf));
+        else ptx::mbar_arrive_relaxed(bars + B_DEMPTY + buf);
+      }
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<2 * kNT>(tmem);
+  ptx::cluster_sync();   // the peer's tensor / shared memory stay valid until both CTAs are done
+  if (warp == 1) ptx::tmem_dealloc2<kAcc * kNT>(tmem);
 }
 
 // ---- state image: FP32 stage state xs[i][column] -> 16-bit operand image [tile][k-block] (hi [, lo]) ----
@@ -443,7 +469,9 @@ int gemm_model_prepare(opz_model* m, int precision) {
               const int n = pass * kNT + r;
               if (n >= N) continue;
               const float v = wn[nd.w_off[l] + (size_t)k * N + n];   // Flux layout: element (k_in, n_out)
-              const size_t o = pbase + (size_t)kb * rows * kKB + ((size_t)(kk / 8) * rows + r) * 8 + kk % 8;
+              // [k-block][half of the rows (one per CTA of the pair)][(k / 8) (rows / 2) + row][k % 8]
+              const int hr = rows / 2, half = r / hr, rl = r - half * hr;
+              const size_t o = pbase + (size_t)kb * rows * kKB + (size_t)half * hr * kKB + ((size_t)(kk / 8) * hr + rl) * 8 + kk % 8;
               const uint16_t h = fp16 ? f16_bits(v) : bf16_bits(v);
               hi[o] = h;
               if (split_w) { const float res = v - (fp16 ? f16_val(h) : bf16_val(h)); lo[o] = fp16 ? f16_bits(res) : bf16_bits(res); }
@@ -499,9 +527,9 @@ static size_t carve(const Plan& pl, const NetDesc& nd, int nz, int64_t C, uint8_
   return off;
 }
 
-static size_t layer_stage(const Plan& pl, int l) {
+static size_t layer_stage(const Plan& pl, int l) {   // per CTA of the pair: its activation tile + half of the weight block
   const int rows = std::min(kNT, pl.n_pad[l]);
-  return (pl.mode == MODE_X3 ? 2 : 1) * (size_t)kABytes + (pl.mode == MODE_PLAIN ? 1 : 2) * (size_t)rows * kKB * 2;
+  return (pl.mode == MODE_X3 ? 2 : 1) * (size_t)kABytes + (pl.mode == MODE_PLAIN ? 1 : 2) * (size_t)(rows / 2) * kKB * 2;
 }
 static size_t layer_smem(const Plan& pl, int l, int stages) { return 256 + layer_stage(pl, l) * stages; }
 
@@ -534,14 +562,16 @@ static int run_layers(opz_ctx* ctx, const opz_model* m, const Plan& pl, const Wo
     int stages = kMaxStages;   // one persistent CTA per SM: as deep a ring as shared memory holds
     // as deep as fits under the 164 KB shared-memory carve-out: the next one (228 KB) leaves 28 KB of L1 for the epilogue's bias
     // reads and measured erratic (configs[4] FP16X3: 216 - 283 TFLOP/s with 4 stages of 48 KB against 350 with 3)
-    while (stages > 2 && layer_smem(pl, l, stages) > (size_t)160 * 1024) --stages;
+    const bool deep = pl.mode == MODE_X3;   // kernel shape, see the template's comment
+    while (stages > 2 && layer_smem(pl, l, stages) > (size_t)(deep ? 160 : 100) * 1024) --stages;   // under the carve-out that leaves L1 / room for two CTAs
     while (stages > 1 && layer_smem(pl, l, stages) > (size_t)ctx->smem_optin) --stages;
     if (layer_smem(pl, l, stages) > (size_t)ctx->smem_optin) { set_error("layered tensor path: operand stage exceeds shared memory"); return OPZ_EUNSUP; }
     a.stages = stages;
     a.stage_stride = (uint32_t)layer_stage(pl, l);
     a.tiles = tiles;
     const size_t smem = layer_smem(pl, l, a.stages);
-    OPZ_CUDA(cudaFuncSetAttribute(layer_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = deep ? layer_gemm_kernel<2, 8> : layer_gemm_kernel<1, 4>;
+    OPZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (only >= 0) {   // a single net: shift the per-net bases
       a.w_hi += (size_t)only * pl.w_net;
       if (a.w_lo) a.w_lo += (size_t)only * pl.w_net;
@@ -551,8 +581,20 @@ static int run_layers(opz_ctx* ctx, const opz_model* m, const Plan& pl, const Wo
       else a.y += (size_t)only * a.n_out * ld;
     }
     a.n_nets = only >= 0 ? 1 : 3;
-    dim3 grid((unsigned)std::min<int64_t>(tiles * a.n_pass * a.n_nets, ctx->sm_count));
-    layer_gemm_kernel<<<grid, kThreads, smem, ctx->stream>>>(a);
+    if (tiles % 2) { set_error("layered tensor path: internal error (odd tile count)"); return OPZ_EINVAL; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>((tiles / 2) * a.n_pass * a.n_nets, deep ? ctx->sm_count / 2 : ctx->sm_count)));
+    cfg.blockDim = dim3(deep ? 320 : 192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OPZ_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     OPZ_CUDA(cudaGetLastError());
     ctx->launches += 1;
   }
@@ -574,11 +616,11 @@ int gemm_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int pre
   size_t free_b = 0, total_b = 0;
   OPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += ctx->scratch_bytes[7];
-  int64_t C = (c.B + kM - 1) / kM * kM;
+  int64_t C = (c.B + 2 * kM - 1) / (2 * kM) * (2 * kM);   // whole tile PAIRS (the GEMM kernel runs as CTA pairs)
   const size_t per128 = carve(*pl, nd, nz, kM, nullptr, nullptr);
-  const int64_t cmax = std::max<int64_t>(1, (int64_t)((free_b / 4) / per128)) * kM;
+  const int64_t cmax = std::max<int64_t>(1, (int64_t)((free_b / 4) / per128) / 2) * (2 * kM);
   if (C > cmax) C = cmax;
-  if (const char* e = getenv("OPZ_GEMM_CHUNK")) { const int64_t v = atoll(e) / kM * kM; if (v >= kM && v < C) C = v; }
+  if (const char* e = getenv("OPZ_GEMM_CHUNK")) { const int64_t v = atoll(e) / (2 * kM) * (2 * kM); if (v >= 2 * kM && v < C) C = v; }
   uint8_t* base;
   int rc;
   if ((rc = ensure_scratch(ctx, 7, carve(*pl, nd, nz, C, nullptr, nullptr), (void**)&base))) return rc;
@@ -586,7 +628,7 @@ int gemm_rollout(opz_ctx* ctx, const opz_model* m, const RolloutCall& c, int pre
   carve(*pl, nd, nz, C, base, &w);
   for (int64_t c0 = 0; c0 < c.B; c0 += C) {
     const int64_t nb = std::min<int64_t>(C, c.B - c0);
-    const int64_t tiles = (nb + kM - 1) / kM;
+    const int64_t tiles = (nb + 2 * kM - 1) / (2 * kM) * 2;   // an even number: the last tile may be padding
     const unsigned eg = (unsigned)((nb * S3 + 255) / 256);
     load_state_kernel<<<eg, 256, 0, st>>>(c.x0 + c0 * S3, S3, nb, C, w.xn, w.xs[0]);
     if (c.save_every > 0) save_state_kernel<<<eg, 256, 0, st>>>(w.xn, S3, nb, C, c.out + c0 * c.n_save * S3, c.n_save, 0);
@@ -630,9 +672,9 @@ int gemm_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, in
   size_t free_b = 0, total_b = 0;
   OPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
   free_b += ctx->scratch_bytes[7];
-  int64_t C = (Nt + kM - 1) / kM * kM;
+  int64_t C = (Nt + 2 * kM - 1) / (2 * kM) * (2 * kM);
   const size_t per128 = carve(*pl, nd, nz, kM, nullptr, nullptr);
-  const int64_t cmax = std::max<int64_t>(1, (int64_t)((free_b / 4) / per128)) * kM;
+  const int64_t cmax = std::max<int64_t>(1, (int64_t)((free_b / 4) / per128) / 2) * (2 * kM);
   if (C > cmax) C = cmax;
   uint8_t* base;
   int rc;
@@ -641,7 +683,7 @@ int gemm_mlp(opz_ctx* ctx, const opz_model* m, int which_net, const float* x, in
   carve(*pl, nd, nz, C, base, &w);
   for (int64_t c0 = 0; c0 < Nt; c0 += C) {
     const int64_t nb = std::min<int64_t>(C, Nt - c0);
-    const int64_t tiles = (nb + kM - 1) / kM;
+    const int64_t tiles = (nb + 2 * kM - 1) / (2 * kM) * 2;   // an even number: the last tile may be padding
     load_rows_kernel<<<(unsigned)((nb * S3 + 255) / 256), 256, 0, st>>>(x + c0 * S3, S3, nb, C, w.xs[0]);
     pack_state_kernel<<<dim3((unsigned)tiles, (unsigned)pl->kb[0]), kM * (kKB / 8), 0, st>>>(w.xs[0], C, S3, pl->kb[0], nb, w.x_hi, w.x_lo, pl->fp16 ? 1 : 0);
     ctx->launches += 2;

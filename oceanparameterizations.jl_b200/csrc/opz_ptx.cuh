@@ -194,6 +194,16 @@ __device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
+// D[tmem, both CTAs] (+)= A[smem, each CTA its own 128 rows] * B[smem halves of both CTAs]^T, M = 256
+__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
 // same with the 64-bit shared-memory descriptor given as two 32-bit halves (the low half carries the start address, so a
 // k-step advance is a 32-bit add with an immediate)
 __device__ __forceinline__ void mma_ts2_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, bool accumulate) {
