@@ -1122,9 +1122,9 @@ int fp32_loss_grad(opz_ctx* ctx, const opz_model* m, const LossGradCall& c) {
         cudaMemcpyFromSymbol(ph, cl::g_phase_cycles, sizeof(ph));
         const char* names[24] = {"fwd slice matvec", "fwd epilogue+gather", "fwd last-layer partial", "fwd y all-reduce", "fwd physics faces",
                                  "fwd cells+RK", "", "", "bwd land+prefetch", "bwd physics VJP", "bwd dz last", "bwd dh partial+send",
-                                 "bwd reduce-scatter wait", "bwd dz hidden", "bwd dx partial", "bwd dx all-reduce", "bwd RK adjoint"};
+                                 "bwd reduce-scatter wait", "bwd dz hidden", "bwd dx partial", "bwd dx all-reduce", "bwd RK adjoint", "  fwd matvec: loop", "  fwd matvec: shuffle+store", "  fwd matvec: sync", "  fwd matvec: plane sum", "", "", ""};
         const double per = 1.0 / ((double)n_steps * stages);
-        for (int i = 0; i < 17; ++i)
+        for (int i = 0; i < 24; ++i)
           if (ph[i]) fprintf(stderr, "    phase %-26s %8.0f cycles / right-hand side\n", names[i], ph[i] * per);
       }
       return OPZ_OK;

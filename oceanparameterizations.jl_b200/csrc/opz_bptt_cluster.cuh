@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
             for (int c = 0; c < CP; ++c) acc[j][c] = fmaf(w, xv[c], acc[j][c]);
           }
         }
+        OPZ_PH(17);
 #pragma unroll
         for (int j = 0; j < kRB; ++j)
 #pragma unroll
@@ -355,13 +356,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_kernel(const __grid_constan
           for (int j = 0; j < kRB; ++j) store_cols<CP>(sp + j * CP, acc[j]);
         }
       }
+      OPZ_PH(18);
       __syncthreads();
+      OPZ_PH(19);
       float z = 0.0f;
       if (t < NP * CP) {
 #pragma unroll
         for (int ks2 = 0; ks2 < kPL; ++ks2) z += scratch[ks2 * NP * CP + t];
         z += (sm + lay.bias[l])[tq];
       }
+      OPZ_PH(20);
       return z;
     }
     if (UL <= 32) {
