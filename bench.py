@@ -230,7 +230,9 @@ def run_bptt(args, opz, ctx, torch, dist, rank, world, stream):
     gnorm = float(buf[:P3].norm().item())
     model.close()
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # (N = 1 only, as for the forward cpu_baseline: under torchrun the twin ran 315 s on rank 0 — OMP_NUM_THREADS=1 is in force
+        # before torch initialises its thread pool — while every other rank waited)
         # CPU baseline of the gradient step (Julia is absent; the reference differentiates with Zygote through an adjoint ODE
         # solve): the float32 PyTorch-autograd twin of the same discrete adjoint on the host cores, on a bounded sample
         # (all 18 cases, the first BPTT_CPU_STEPS time steps), scaled to the full rollout
