@@ -178,3 +178,21 @@ def test_c_shard_range_matches_host_and_nccl_binds(opz):
         assert v.value >= 21800, v.value          # NCCL >= 2.18
     else:
         assert rc == opz.OPZ_ENCCL and b"nccl" in opz.lib.opz_last_error().lower()
+
+
+def test_nccl_library_preference(opz, monkeypatch):
+    """libopz binds NCCL with dlopen; the Python package points it at the wheel PyTorch uses unless the user chose one
+    (the loader keeps one library per SONAME: loading the system copy first would bind a later `import torch` to it)."""
+    import importlib.util
+    import sys
+    L = sys.modules[opz.__name__ + "._lib"]
+    monkeypatch.setenv("OPZ_NCCL_LIB", "/somewhere/libnccl.so.2")
+    L._prefer_bundled_nccl()
+    assert os.environ["OPZ_NCCL_LIB"] == "/somewhere/libnccl.so.2"     # an explicit choice wins
+    monkeypatch.delenv("OPZ_NCCL_LIB")
+    L._prefer_bundled_nccl()
+    spec = importlib.util.find_spec("nvidia.nccl")
+    if spec is not None and any(os.path.exists(os.path.join(p, "lib", "libnccl.so.2")) for p in spec.submodule_search_locations):
+        assert os.environ["OPZ_NCCL_LIB"].endswith(os.path.join("nvidia", "nccl", "lib", "libnccl.so.2"))
+    else:
+        assert "OPZ_NCCL_LIB" not in os.environ
